@@ -1,0 +1,50 @@
+"""TEST INFRASTRUCTURE -- the named UNet / DDPM parity cases shared by the golden generator and tests.
+
+Each case is (UNet kwargs, batch, conditioning kind).  Shapes are small enough for the CPU oracle to
+finish in seconds; together they cover n = 1, 2, 3, both attention split orders, FiLM and additive
+embedding, all three conditioning paths (none / same-shape embedding / MultiEmbeddings), odd channel
+counts (3) and the reference's own test fixture shape (tests/models/test_unet.py:28-56).
+"""
+from __future__ import annotations
+
+UNET_CASES = {
+    # the reference's own smoke-test fixture: unconditional 2-D, heads=1, additive embedding, legacy order
+    "ref2d": dict(
+        kwargs=dict(data_shape=16, in_channels=3, model_channels=32, out_channels=3, num_res_blocks=2),
+        x_shape=(2, 3, 24, 16), cond=None,
+    ),
+    # 3-D FiLM, 4 heads, new attention order, sha-style same-shape label embedding (config A family)
+    "film3d": dict(
+        kwargs=dict(data_shape=[8, 16, 16], in_channels=1, model_channels=32, out_channels=1, num_res_blocks=1,
+                    attention_resolutions=[2, 4], channel_mult=[1, 2, 4], dims=3, num_classes=20, num_heads=4,
+                    use_scale_shift_norm=True, use_new_attention_order=True, activation="SiLU"),
+        x_shape=(2, 1, 8, 16, 16), cond="same_shape",
+    ),
+    # 1-D FiLM, 2 heads, legacy order, MultiEmbeddings conditioning (config B/C family)
+    "multi1d": dict(
+        kwargs=dict(data_shape=[64], in_channels=1, model_channels=32, out_channels=1, num_res_blocks=1,
+                    attention_resolutions=[4, 8], channel_mult=[1, 2, 4, 4], dims=1, num_classes=25, num_heads=2,
+                    use_scale_shift_norm=True, use_new_attention_order=False, activation="SiLU"),
+        x_shape=(3, 1, 64), cond="multi",
+        parameter_space={"s": [0.25, 0.5, 1.0], "m": [1.0], "t": [400.0, 405.0, 410.0, 415.0]},
+    ),
+    # 2-D deep-galaxy family (config B) at reduced resolution: FiLM, 4 heads, 64-multiple channels at depth
+    "galaxy2d": dict(
+        kwargs=dict(data_shape=[32, 32], in_channels=1, model_channels=32, out_channels=1, num_res_blocks=2,
+                    attention_resolutions=[16, 8], dims=2, num_classes=25, num_heads=4,
+                    use_scale_shift_norm=True, use_new_attention_order=True, activation="SiLU"),
+        x_shape=(2, 1, 32, 32), cond="multi",
+        parameter_space={"s": [0.25, 0.5, 1.0], "m": [1.0], "t": [400.0, 405.0, 410.0], "c": [0.0]},
+    ),
+}
+
+TIMESTEPS = {"ref2d": [0, 7], "film3d": [3, 999], "multi1d": [1, 500, 250], "galaxy2d": [17, 420]}
+
+
+def cond_values(case: str):
+    """Label rows for the 'multi' cases (rows of the parameter space)."""
+    if case == "multi1d":
+        return [[0.5, 1.0, 405.0], [1.0, 1.0, 400.0], [0.25, 1.0, 415.0]]
+    if case == "galaxy2d":
+        return [[0.25, 1.0, 410.0, 0.0], [1.0, 1.0, 400.0, 0.0]]
+    return None

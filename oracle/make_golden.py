@@ -1,0 +1,222 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.pt by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Every fixture is small (inputs are re-derived from seeds via oracle/synth.py; only outputs and a
+key->shape manifest are stored).  The committed fixtures pin the CPU oracle (oracle/torch_oracle.py)
+and are also compared directly against the CUDA path in the ``-m gpu`` tests.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from collections import OrderedDict
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from oracle.cases import TIMESTEPS, UNET_CASES, cond_values  # noqa: E402
+from oracle.synth import synth_input, synth_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def build_ref_unet(ref, case):
+    spec = UNET_CASES[case]
+    kwargs = dict(spec["kwargs"])
+    if spec["cond"] == "multi":
+        space = OrderedDict(spec["parameter_space"])
+        kwargs["cond_fn"] = ref.MultiEmbeddings(parameter_space=space, embedding_dim=4 * kwargs["model_channels"])
+    model = ref.UNet(**kwargs).eval()
+    manifest = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth_state_dict(manifest, seed=777), strict=True)
+    return model, manifest
+
+
+def case_inputs(case):
+    spec = UNET_CASES[case]
+    x = synth_input(case + ".x", spec["x_shape"])
+    t = torch.tensor(TIMESTEPS[case], dtype=torch.long)
+    y = None
+    if spec["cond"] == "same_shape":
+        y = synth_input(case + ".y", (spec["x_shape"][0], 4 * spec["kwargs"]["model_channels"]), kind="rand")
+    elif spec["cond"] == "multi":
+        y = torch.tensor(cond_values(case), dtype=torch.float32)
+    return x, t, y
+
+
+def gen_unet(ref):
+    for case in UNET_CASES:
+        torch.manual_seed(0)
+        model, manifest = build_ref_unet(ref, case)
+        x, t, y = case_inputs(case)
+        taps = {}
+        hooks = []
+
+        def mk(name):
+            def hook(_m, _i, o):
+                taps[name] = o.detach().clone()
+            return hook
+
+        for i, blk in enumerate(model.input_blocks):
+            hooks.append(blk.register_forward_hook(mk(f"input_blocks.{i}")))
+        hooks.append(model.middle_block.register_forward_hook(mk("middle_block")))
+        for i, blk in enumerate(model.output_blocks):
+            hooks.append(blk.register_forward_hook(mk(f"output_blocks.{i}")))
+        hooks.append(model.time_embed.register_forward_hook(mk("time_embed")))
+        with torch.inference_mode():
+            out = model(x, t, y) if y is not None else model(x, t)
+        for h in hooks:
+            h.remove()
+        tap_stats = {k: torch.stack([v.double().mean(), v.double().std(), v.double().abs().max()]).float()
+                     for k, v in taps.items()}
+        small_taps = {k: v.clone() for k, v in taps.items() if v.numel() <= 9000}
+        torch.save({"case": case, "manifest": manifest, "out": out.clone(), "tap_stats": tap_stats,
+                    "taps": small_taps}, os.path.join(OUT, f"unet_{case}.pt"))
+        print(case, "params", sum(int(torch.tensor(s).prod()) for s in manifest.values()),
+              "out", tuple(out.shape), float(out.abs().mean()))
+
+
+def gen_schedule(ref):
+    S = ref.schedule
+    d = {}
+    for name, sch in {
+        "linear_100_kat": S.LinearSchedule(100, 1e-4, 0.02),          # tests/pipeline/test_schedule.py:30
+        "linear_1000": S.LinearSchedule(1000, 1e-3, 0.02),           # examples/config_spherical_harmonics.json
+        "linear_500_default": S.LinearSchedule(500),                 # examples/config_deep_galaxy.json
+        "cosine_50": S.CosineBetaSchedule(50),
+        "cosine_1000": S.CosineBetaSchedule(1000),
+    }.items():
+        d[name] = {k: sch[k].clone() for k in ("beta_t", "alpha_t", "alpha_bar_t", "sigma_t")}
+        d[name]["offset_alpha_bar_t"] = sch.offset_alpha_bar_t.clone()
+    torch.save(d, os.path.join(OUT, "schedule.pt"))
+
+
+def gen_embeddings(ref):
+    d = {}
+    for dim in (32, 64, 128):
+        t = torch.tensor([0, 1, 2, 17, 499, 999], dtype=torch.long)
+        d[f"timestep_{dim}"] = {"t": t, "pe": ref.common.sinosoidal_position_embedding(t, dim)}
+    d["sha512_l2_m-1_256"] = ref.utils.calculate_sha512_embedding({"l": 2, "m": -1}, 256)
+    d["sha512_default_128"] = ref.utils.calculate_sha512_embedding({"a": 1})
+    space = {"l": [-2, -1, 1, 2], "m": [-1, 1, 3]}
+    d["param_space"] = space
+    d["param_space_rows_7"] = ref.parameter_space.sample_from_discrete_parameter_space(space, 7, random=False)
+    d["param_space_embeddings"] = ref.utils.parameter_space_to_embeddings({"m": [1, 2], "n": [3, 4, 5]})
+    # MultiEmbeddings forward
+    pspace = OrderedDict({"s": [0.25, 0.5, 1.0], "t": [400.0, 405.0]})
+    me = ref.MultiEmbeddings(parameter_space=pspace, embedding_dim=16)
+    manifest = {k: tuple(v.shape) for k, v in me.state_dict().items()}
+    me.load_state_dict(synth_state_dict(manifest, seed=5))
+    y = torch.tensor([[0.5, 405.0], [1.0, 400.0], [0.25, 400.0]])
+    d["multi_emb"] = {"space": dict(pspace), "manifest": manifest, "y": y, "out": me(y).detach().clone()}
+    torch.save(d, os.path.join(OUT, "embeddings.pt"))
+
+
+def gen_ddpm(ref):
+    """DDPM.forward_process / training_step / reverse_process on the film3d-family UNet, with the RNG
+    draws recorded so the fixture does not depend on torch's generator implementation."""
+    case = "film3d"
+    spec = UNET_CASES[case]
+    kwargs = dict(spec["kwargs"])
+    T = 50
+    sched = ref.schedule.LinearSchedule(T, 1e-3, 0.02)
+    ddpm = ref.DDPM(ref.UNet, kwargs, sched, "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4})
+    manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+    ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+    ddpm.eval()
+    x0 = synth_input("ddpm.x0", spec["x_shape"], kind="rand")
+    y = synth_input(case + ".y", (spec["x_shape"][0], 4 * kwargs["model_channels"]), kind="rand")
+    d = {"T": T, "manifest": manifest}
+
+    # ---- record every randn_like / randint the pipeline makes
+    rec = {"randn": [], "randint": []}
+    real_randn_like, real_randint = torch.randn_like, torch.randint
+
+    def randn_like(x, *a, **k):
+        r = real_randn_like(x, *a, **k)
+        rec["randn"].append(r.clone())
+        return r
+
+    def randint(*a, **k):
+        r = real_randint(*a, **k)
+        rec["randint"].append(r.clone())
+        return r
+
+    torch.randn_like, torch.randint = randn_like, randint
+    try:
+        torch.manual_seed(21516)
+        # forward_process with explicit t
+        t = torch.tensor([3, 10])
+        x_t, noise = ddpm.forward_process(x0, t)
+        d["q_sample"] = {"t": t, "noise": noise.clone(), "x_t": x_t.clone()}
+        # training_step (list batch => conditional)
+        rec["randn"].clear(); rec["randint"].clear()
+        loss = ddpm.training_step([x0, y])
+        d["train"] = {"t_idx": rec["randint"][0].clone(), "noise": rec["randn"][0].clone(), "loss": loss.detach().clone()}
+        # gradients of a few parameters (for the backward parity tests)
+        ddpm.zero_grad()
+        loss.backward()
+        grads = {}
+        for name, p in ddpm.backbone.named_parameters():
+            if p.grad is not None:
+                g = p.grad.detach()
+                grads[name] = torch.stack([g.double().norm(), g.double().sum()]).float()
+        d["train"]["grad_stats"] = grads
+        names = [n for n, _ in ddpm.backbone.named_parameters()]
+        keep = ["out.2.weight", "out.2.bias", "input_blocks.0.0.weight", "time_embed.0.weight",
+                "middle_block.1.qkv.weight", "middle_block.0.emb_layers.1.weight", "out.0.weight",
+                "middle_block.1.norm.bias", "middle_block.1.proj_out.weight",
+                "input_blocks.1.0.in_layers.2.weight", "input_blocks.1.0.out_layers.0.weight"]
+        keep += [n for n in names if n.endswith("op.weight")][:1]
+        keep += [n for n in names if n.endswith("conv.weight")][:1]
+        keep += [n for n in names if n.endswith("skip_connection.weight")][:1]
+        d["train"]["grads"] = {k: dict(ddpm.backbone.named_parameters())[k].grad.detach().flatten()[:4096].clone() for k in keep}
+        # one AdamW step through the reference's optimizer factory (world = 4 => lr * 2)
+        opt = ddpm.configure_optimizers(4)["optimizer"]
+        d["opt"] = {"lr": opt.param_groups[0]["lr"], "weight_decay": opt.param_groups[0]["weight_decay"],
+                    "betas": tuple(opt.param_groups[0]["betas"]), "eps": opt.param_groups[0]["eps"]}
+        opt.step()
+        d["opt"]["after_step"] = {k: dict(ddpm.backbone.named_parameters())[k].detach().flatten()[:4096].clone() for k in keep}
+        # EMA (ema.py) two updates
+        ema = ref.ExponentialMovingAverage(ddpm.backbone, decay=0.9999)
+        ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=778))
+        ema.update()
+        ema.update()
+        d["ema"] = {"frac": ema.current_ema_frac,
+                    "shadow": {k: dict(ema.ema_model.named_parameters())[k].detach().flatten()[:4096].clone() for k in keep}}
+        # reverse process (weights back to seed 777)
+        ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+        rec["randn"].clear()
+        torch.manual_seed(4242)
+        res = ddpm.reverse_process(torch.zeros(spec["x_shape"]), conditions=y, t_checkpoints=None)
+        draws = rec["randn"]
+        d["reverse"] = {"x_init": draws[0].clone(), "z": [z.clone() for z in draws[1:]],
+                        "denoised": res["denoised"].clone()}
+    finally:
+        torch.randn_like, torch.randint = real_randn_like, real_randint
+    torch.save(d, os.path.join(OUT, "ddpm_film3d.pt"))
+    print("ddpm loss", float(d["train"]["loss"]), "reverse draws", len(d["reverse"]["z"]),
+          "denoised mean", float(d["reverse"]["denoised"].mean()))
+
+
+def main():
+    assert ref_loader.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load()
+    gen_schedule(ref)
+    gen_embeddings(ref)
+    gen_unet(ref)
+    gen_ddpm(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,387 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 restatement of the reference hot path (the parity oracle).
+
+This file restates, in plain functional PyTorch on CPU, the algorithm of intel/rho-diffusion's
+DDPM training step and ancestral sampling loop over the conditional n-D UNet.  It is the checker
+for the CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import it.  The product (``rho_diffusion.*``) never does and has
+no CPU fallback.
+
+Pinning: ``tests/test_oracle_golden.py`` checks every function here against fixtures under
+``tests/golden/`` that were produced by running the UNMODIFIED reference modules
+(``oracle/make_golden.py`` via ``oracle/ref_loader.py``) and against the reference's own
+known-answer test (``tests/pipeline/test_schedule.py:28-46``).  Parity status: PINNED.
+
+All citations are ``path:line`` relative to the reference repository root.
+"""
+from __future__ import annotations
+
+import hashlib
+import itertools
+import json
+import math
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# noise schedules  (rho_diffusion/diffusion/schedule.py)
+# --------------------------------------------------------------------------------------------
+
+
+def linear_schedule(num_steps: int, beta_1: float = 1.0e-3, beta_T: float = 0.02) -> dict:
+    """schedule.py:141-168 -- float64 tables, beta scaled by 1000/T, stored as float32."""
+    scale = 1000 / num_steps
+    beta = torch.linspace(scale * beta_1, scale * beta_T, num_steps, dtype=torch.float64)
+    alpha = 1.0 - beta
+    alpha_bar = alpha.cumprod(0)
+    alpha_bar32 = alpha_bar.to(torch.float32)
+    # offset_alpha_bar_t is built from the *float32* table (schedule.py:80-82, 165-168)
+    prev = F.pad(alpha_bar32[:-1], (1, 0), value=1.0)
+    sigma = torch.sqrt((1 - prev) / (1 - alpha_bar) * beta)
+    return {
+        "beta_t": beta.to(torch.float32),
+        "alpha_t": alpha.to(torch.float32),
+        "alpha_bar_t": alpha_bar32,
+        "sigma_t": sigma.to(torch.float32),
+    }
+
+
+def cosine_schedule(num_steps: int, offset: float = 0.008) -> dict:
+    """schedule.py:171-214 -- T+1 points; beta clipped in place; sigma_t[0] is NaN (0/0)."""
+    t = torch.linspace(0.0, num_steps, num_steps + 1, dtype=torch.float64) / num_steps
+    alpha_bar = torch.cos((t + offset) / (1 + offset) * math.pi * 0.5).pow(2.0)
+    alpha_bar = alpha_bar.div(alpha_bar[0])
+    alpha_bar32 = alpha_bar.to(torch.float32)
+    alpha_bar32[alpha_bar32 < 0] = 0
+    alpha_bar32[alpha_bar32 > 1] = 1
+    prev = F.pad(alpha_bar32[:-1], (1, 0), value=1.0)
+    beta = 1 - (alpha_bar / prev)
+    beta.clip_(0.0001, 0.9999)  # in place: alpha_t / sigma_t below use the clipped values
+    sigma = torch.sqrt((1 - prev) / (1 - alpha_bar) * beta)
+    return {
+        "beta_t": beta.to(torch.float32),
+        "alpha_t": (1 - beta).to(torch.float32),
+        "alpha_bar_t": alpha_bar32,
+        "sigma_t": sigma.to(torch.float32),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# embeddings
+# --------------------------------------------------------------------------------------------
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, wavelength: int = 10000) -> torch.Tensor:
+    """models/common.py:27-43 -- interleaved sin/cos, omega_i = wavelength^(2i/dim), float32."""
+    i = torch.arange(dim // 2)
+    omega = torch.pow(wavelength, 2 * i / dim)
+    arg = t[:, None] / omega[None, :]
+    pe = torch.empty(len(t), dim)
+    pe[:, 0::2] = torch.sin(arg).float()
+    pe[:, 1::2] = torch.cos(arg).float()
+    return pe
+
+
+def multi_embeddings(sd: dict, prefix: str, parameter_space: dict, y: torch.Tensor) -> torch.Tensor:
+    """models/conditioning.py:115-139 -- sum over keys of Embedding[index where y[:, i] == space[key]]."""
+    emb = None
+    for i, (key, values) in enumerate(parameter_space.items()):
+        yi = y if y.dim() == 1 else y[:, i]
+        table = torch.tensor(values, dtype=yi.dtype)
+        idx = torch.where(yi[:, None] == table[None, :])[1]
+        e = sd[f"{prefix}embedding_layers.{key}.weight"][idx]
+        emb = e if emb is None else emb + e
+    return emb
+
+
+def sha512_embedding(d: dict, length: int = 128) -> torch.Tensor:
+    """utils.py:170-177 -- ASCII codes of the sha512 hex digest / 128, each repeated length//128 times."""
+    h = hashlib.sha512(json.dumps(d, sort_keys=True).encode()).hexdigest()
+    codes = np.frombuffer(h.encode("ascii"), dtype=np.uint8)
+    return torch.tensor(codes.repeat(length // 128) / 128, dtype=torch.float32)
+
+
+def sample_from_discrete_parameter_space(space: dict, batch_size: int, random: bool = False,
+                                         generator=None) -> torch.Tensor:
+    """data/parameter_space.py:9-16 -- rows of the Cartesian product."""
+    combos = torch.tensor([v for v in itertools.product(*space.values())])
+    if random:
+        idx = torch.randint(0, combos.shape[0], (batch_size,), generator=generator)
+    else:
+        idx = torch.arange(batch_size)
+    return combos[idx]
+
+
+# --------------------------------------------------------------------------------------------
+# UNetv2 forward  (rho_diffusion/models/unet_v2.py)
+# --------------------------------------------------------------------------------------------
+
+_ACTS = {
+    "SiLU": F.silu, "ReLU": F.relu, "Tanh": torch.tanh, "Sigmoid": torch.sigmoid, "GELU": F.gelu,
+}
+
+
+def _conv(x, w, b, stride=1, padding=0):
+    return {3: F.conv1d, 4: F.conv2d, 5: F.conv3d}[x.dim()](x, w, b, stride=stride, padding=padding)
+
+
+def _gn(x, w, b):
+    """layers.py:71-74 -- GroupNorm(32, C), eps 1e-5, computed in float32."""
+    return F.group_norm(x.float(), 32, w, b, 1e-5).type(x.dtype)
+
+
+def _upsample(x, dims):
+    """unet_v2.py:122-131 -- nearest x2; 3-D keeps depth."""
+    if dims == 3:
+        return F.interpolate(x, (x.shape[2], x.shape[3] * 2, x.shape[4] * 2), mode="nearest")
+    return F.interpolate(x, scale_factor=2, mode="nearest")
+
+
+def _attention(qkv, n_heads, new_order):
+    """unet_v2.py:365-436 -- both head/qkv split orders; fp32 softmax; scale ch^-1/4 on q and k."""
+    bs, width, length = qkv.shape
+    ch = width // (3 * n_heads)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    if new_order:
+        q, k, v = qkv.chunk(3, dim=1)
+        q = q.reshape(bs * n_heads, ch, length)
+        k = k.reshape(bs * n_heads, ch, length)
+        v = v.reshape(bs * n_heads, ch, length)
+    else:
+        q, k, v = qkv.reshape(bs * n_heads, ch * 3, length).split(ch, dim=1)
+    w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
+    w = torch.softmax(w.float(), dim=-1).type(w.dtype)
+    a = torch.einsum("bts,bcs->bct", w, v)
+    return a.reshape(bs, -1, length)
+
+
+class UNetSpec:
+    """The constructor arguments of unet_v2.UNet (unet_v2.py:471-494) that shape the computation."""
+
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks,
+                 attention_resolutions=(16, 8), channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2,
+                 num_classes=None, num_heads=1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 activation="SiLU", parameter_space=None, **_ignored):
+        self.in_channels = in_channels
+        self.mc = model_channels
+        self.out_channels = out_channels
+        self.nrb = num_res_blocks
+        self.attn_res = list(attention_resolutions)
+        self.mult = list(channel_mult)
+        self.conv_resample = bool(conv_resample)
+        self.dims = dims
+        self.num_classes = num_classes
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads if num_heads_upsample == -1 else num_heads_upsample
+        self.film = bool(use_scale_shift_norm)
+        self.updown = bool(resblock_updown)
+        self.new_order = bool(use_new_attention_order)
+        self.act = _ACTS[activation] if isinstance(activation, str) else activation
+        self.parameter_space = parameter_space
+
+
+def _resblock(sd, p, x, emb, spec: UNetSpec, up=False, down=False):
+    """unet_v2.py:273-293."""
+    act = spec.act
+    h = act(_gn(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"]))
+    if up:
+        h = _upsample(h, spec.dims)
+        x = _upsample(x, spec.dims)
+    elif down:
+        k = 2 if spec.dims != 3 else (1, 2, 2)
+        pool = {1: F.avg_pool1d, 2: F.avg_pool2d, 3: F.avg_pool3d}[spec.dims]
+        h = pool(h, k, k)
+        x = pool(x, k, k)
+    h = _conv(h, sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
+    e = F.linear(act(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
+    e = e.reshape(*e.shape, *([1] * (h.dim() - 2)))
+    if spec.film:
+        scale, shift = torch.chunk(e, 2, dim=1)
+        h = _gn(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"]) * (1 + scale) + shift
+        h = act(h)
+    else:
+        h = act(_gn(h + e, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"]))
+    h = _conv(h, sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
+    if p + "skip_connection.weight" in sd:
+        w = sd[p + "skip_connection.weight"]
+        x = _conv(x, w, sd[p + "skip_connection.bias"], padding=(w.shape[-1] - 1) // 2)
+    return x + h
+
+
+def _attnblock(sd, p, x, n_heads, spec: UNetSpec):
+    """unet_v2.py:336-342."""
+    b, c, *sp = x.shape
+    x = x.reshape(b, c, -1)
+    if spec.num_head_channels != -1:
+        n_heads = c // spec.num_head_channels
+    qkv = F.conv1d(_gn(x, sd[p + "norm.weight"], sd[p + "norm.bias"]), sd[p + "qkv.weight"], sd[p + "qkv.bias"])
+    h = _attention(qkv, n_heads, spec.new_order)
+    h = F.conv1d(h, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+    return (x + h).reshape(b, c, *sp)
+
+
+def unet_forward(sd: dict, spec: UNetSpec, x: torch.Tensor, timesteps: torch.Tensor, y=None,
+                 taps: dict | None = None) -> torch.Tensor:
+    """unet_v2.py:685-732 driven by a reference ``state_dict`` (same key names).
+
+    ``taps`` (optional dict) receives named intermediate activations for per-layer parity checks.
+    """
+    act = spec.act
+    emb = timestep_embedding(timesteps, spec.mc)
+    emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    emb = F.linear(act(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    if spec.num_classes is not None:
+        assert y is not None
+        if y.dim() == 2 and y.shape == emb.shape:
+            emb = emb + y
+        else:
+            emb = emb + multi_embeddings(sd, "cond_fn.", spec.parameter_space, y)
+    if taps is not None:
+        taps["emb"] = emb
+
+    def record(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    hs = []
+    h = x.float()
+    # ---- input blocks (unet_v2.py:533-595)
+    idx = 0
+    h = _conv(h, sd["input_blocks.0.0.weight"], sd["input_blocks.0.0.bias"], padding=1)
+    hs.append(record("input_blocks.0", h))
+    idx = 1
+    ds = 1
+    for level, _mult in enumerate(spec.mult):
+        for _ in range(spec.nrb):
+            p = f"input_blocks.{idx}."
+            h = _resblock(sd, p + "0.", h, emb, spec)
+            if ds in spec.attn_res:
+                h = _attnblock(sd, p + "1.", h, spec.num_heads, spec)
+            hs.append(record(f"input_blocks.{idx}", h))
+            idx += 1
+        if level != len(spec.mult) - 1:
+            p = f"input_blocks.{idx}.0."
+            if spec.updown:
+                h = _resblock(sd, p, h, emb, spec, down=True)
+            elif spec.conv_resample:
+                stride = 2 if spec.dims != 3 else (1, 2, 2)
+                h = _conv(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=stride, padding=1)
+            else:
+                k = 2 if spec.dims != 3 else (1, 2, 2)
+                h = {1: F.avg_pool1d, 2: F.avg_pool2d, 3: F.avg_pool3d}[spec.dims](h, k, k)
+            hs.append(record(f"input_blocks.{idx}", h))
+            idx += 1
+            ds *= 2
+    # ---- middle (unet_v2.py:597-623)
+    h = _resblock(sd, "middle_block.0.", h, emb, spec)
+    h = _attnblock(sd, "middle_block.1.", h, spec.num_heads, spec)
+    h = _resblock(sd, "middle_block.2.", h, emb, spec)
+    record("middle_block", h)
+    # ---- output blocks (unet_v2.py:626-677)
+    oidx = 0
+    for level, _mult in list(enumerate(spec.mult))[::-1]:
+        for i in range(spec.nrb + 1):
+            h = torch.cat([h, hs.pop()], dim=1)
+            p = f"output_blocks.{oidx}."
+            h = _resblock(sd, p + "0.", h, emb, spec)
+            sub = 1
+            if ds in spec.attn_res:
+                h = _attnblock(sd, p + f"{sub}.", h, spec.num_heads_upsample, spec)
+                sub += 1
+            if level and i == spec.nrb:
+                if spec.updown:
+                    h = _resblock(sd, p + f"{sub}.", h, emb, spec, up=True)
+                else:
+                    h = _upsample(h, spec.dims)
+                    if spec.conv_resample:
+                        h = _conv(h, sd[p + f"{sub}.conv.weight"], sd[p + f"{sub}.conv.bias"], padding=1)
+                ds //= 2
+            record(f"output_blocks.{oidx}", h)
+            oidx += 1
+    h = h.type(x.dtype)
+    h = act(_gn(h, sd["out.0.weight"], sd["out.0.bias"]))
+    return _conv(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+
+
+# --------------------------------------------------------------------------------------------
+# DDPM  (rho_diffusion/diffusion/ddpm.py)
+# --------------------------------------------------------------------------------------------
+
+
+def q_sample(sched: dict, x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """ddpm.py:104-130 -- x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) eps."""
+    ab = sched["alpha_bar_t"].type(x0.dtype)[t].view(-1, *([1] * (x0.dim() - 1)))
+    return ab.sqrt() * x0 + (1 - ab).sqrt() * noise
+
+
+def p_sample_step(sched: dict, x_t: torch.Tensor, eps: torch.Tensor, z: torch.Tensor, t: int) -> torch.Tensor:
+    """ddpm.py:210-218 -- one ancestral update with the reference's constants (0.8*sqrt(beta_t) noise
+    scale, clamp to [-1, 1]); identity for t == 0.  ``z`` must already be zero for t <= 1 (ddpm.py:196-199)."""
+    if t == 0:
+        return x_t
+    a = sched["alpha_t"].type(x_t.dtype)[t]
+    b = sched["beta_t"].type(x_t.dtype)[t]
+    ab = sched["alpha_bar_t"].type(x_t.dtype)[t]
+    x = (1 / a.sqrt()) * (x_t - (b / (1 - ab).sqrt()) * eps) + 0.8 * torch.sqrt(b) * z
+    return torch.clamp(x, -1, 1)
+
+
+def reverse_process(sched: dict, denoise, x_init: torch.Tensor, noises: Sequence[torch.Tensor] | None,
+                    cond=None, num_steps: int | None = None, trajectory: list | None = None) -> torch.Tensor:
+    """ddpm.py:132-229 with externally supplied noise (``noises[t]`` is z for step t; zeros for t <= 1).
+
+    ``denoise(x, tt, cond)`` is the backbone.  ``num_steps`` defaults to len(alpha_bar_t) (T for the
+    linear schedule, T+1 for cosine -- ddpm.py:168)."""
+    T = len(sched["alpha_bar_t"]) if num_steps is None else num_steps
+    x = x_init
+    for t in range(T - 1, -1, -1):
+        z = noises[t] if (noises is not None and t > 1) else torch.zeros_like(x)
+        tt = torch.full((x.shape[0],), t, dtype=torch.long)
+        eps = denoise(x, tt, cond)
+        x = p_sample_step(sched, x, eps, z, t)
+        if trajectory is not None:
+            trajectory.append(x.clone())
+    return x
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """ddpm.py:280 with nn.MSELoss (mean over all elements)."""
+    return ((pred - target) ** 2).mean()
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer / EMA  (abstract_diffusion.py:86-148, ema.py:29-79)
+# --------------------------------------------------------------------------------------------
+
+
+def adamw_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):
+    """torch.optim.AdamW (the reference's optimizer, abstract_diffusion.py:103-119), single tensor,
+    returns the updated (p, m, v).  ``step`` is 1-based."""
+    p = p * (1 - lr * weight_decay)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v
+
+
+def ema_decay(step: int, decay: float = 0.9999) -> float:
+    """ema.py:33 -- warm-up decay d*(1-exp(-step/2000))."""
+    return decay * (1 - math.exp(-step / 2000))
+
+
+def ema_update(shadow, p, step: int, decay: float = 0.9999):
+    """ema.py:41-57 -- shadow -= (1-d_t)(shadow - p); ``step`` is the post-increment step id."""
+    return shadow - (1.0 - ema_decay(step, decay)) * (shadow - p)
+
+
+def lr_world_scale(lr: float, world: int) -> float:
+    """abstract_diffusion.py:118 -- lr * sqrt(world)."""
+    return lr * math.sqrt(world)

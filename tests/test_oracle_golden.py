@@ -1,0 +1,122 @@
+"""Pins the CPU oracle (oracle/torch_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py) and against the reference's own known-answer test
+(reference tests/pipeline/test_schedule.py:28-46)."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import torch_oracle as O
+from oracle.cases import TIMESTEPS, UNET_CASES, cond_values
+from oracle.synth import synth_input, synth_state_dict
+
+
+def test_linear_schedule_known_answers():
+    s = O.linear_schedule(100, 1e-4, 0.02)
+    assert len(s["beta_t"]) == 100
+    assert s["beta_t"][0] == 0.001 and s["beta_t"][-1] == 0.2
+    assert s["alpha_t"][0] == 0.999 and s["alpha_t"][-1] == 0.8
+    assert s["sigma_t"][0] == 0.0
+    assert float(s["sigma_t"][-1]) == pytest.approx(0.4472, rel=1e-4)
+
+
+@pytest.mark.parametrize("name,fn", [
+    ("linear_100_kat", lambda: O.linear_schedule(100, 1e-4, 0.02)),
+    ("linear_1000", lambda: O.linear_schedule(1000, 1e-3, 0.02)),
+    ("linear_500_default", lambda: O.linear_schedule(500)),
+    ("cosine_50", lambda: O.cosine_schedule(50)),
+    ("cosine_1000", lambda: O.cosine_schedule(1000)),
+])
+def test_schedule_tables_bit_exact(name, fn):
+    g = load_golden("schedule.pt")[name]
+    s = fn()
+    for k in ("beta_t", "alpha_t", "alpha_bar_t", "sigma_t"):
+        assert s[k].dtype == torch.float32
+        assert torch.equal(torch.nan_to_num(s[k], nan=-7.0), torch.nan_to_num(g[k], nan=-7.0)), k
+
+
+def test_embeddings_and_parameter_space():
+    g = load_golden("embeddings.pt")
+    for dim in (32, 64, 128):
+        e = g[f"timestep_{dim}"]
+        assert torch.allclose(O.timestep_embedding(e["t"], dim), e["pe"], rtol=0, atol=1e-6)
+    assert torch.equal(O.sha512_embedding({"l": 2, "m": -1}, 256), g["sha512_l2_m-1_256"])
+    assert torch.equal(O.sha512_embedding({"a": 1}), g["sha512_default_128"])
+    assert torch.equal(O.sample_from_discrete_parameter_space(g["param_space"], 7), g["param_space_rows_7"])
+    me = g["multi_emb"]
+    sd = synth_state_dict(me["manifest"], seed=5)
+    out = O.multi_embeddings(sd, "", OrderedDict(me["space"]), me["y"])
+    assert torch.allclose(out, me["out"], rtol=0, atol=1e-7)
+
+
+def oracle_case(case):
+    spec = UNET_CASES[case]
+    g = load_golden(f"unet_{case}.pt")
+    sd = synth_state_dict(g["manifest"], seed=777)
+    x = synth_input(case + ".x", spec["x_shape"])
+    t = torch.tensor(TIMESTEPS[case], dtype=torch.long)
+    y = None
+    if spec["cond"] == "same_shape":
+        y = synth_input(case + ".y", (spec["x_shape"][0], 4 * spec["kwargs"]["model_channels"]), kind="rand")
+    elif spec["cond"] == "multi":
+        y = torch.tensor(cond_values(case), dtype=torch.float32)
+    uspec = O.UNetSpec(**spec["kwargs"], parameter_space=OrderedDict(spec.get("parameter_space", {})))
+    return g, sd, uspec, x, t, y
+
+
+@pytest.mark.parametrize("case", list(UNET_CASES))
+def test_unet_forward_matches_reference(case):
+    g, sd, uspec, x, t, y = oracle_case(case)
+    taps = {}
+    out = O.unet_forward(sd, uspec, x, t, y, taps=taps)
+    assert out.shape == g["out"].shape
+    err = (out - g["out"]).abs().max() / g["out"].abs().max()
+    assert err < 2e-6, err
+    for k, v in g["taps"].items():
+        if k in taps:
+            assert (taps[k] - v).abs().max() <= 2e-6 * v.abs().max() + 1e-7, k
+
+
+def test_ddpm_q_sample_loss_and_reverse():
+    g = load_golden("ddpm_film3d.pt")
+    spec = UNET_CASES["film3d"]
+    sd = synth_state_dict(g["manifest"], seed=777)
+    uspec = O.UNetSpec(**spec["kwargs"])
+    sched = O.linear_schedule(g["T"], 1e-3, 0.02)
+    x0 = synth_input("ddpm.x0", spec["x_shape"], kind="rand")
+    y = synth_input("film3d.y", (spec["x_shape"][0], 128), kind="rand")
+    q = g["q_sample"]
+    assert torch.allclose(O.q_sample(sched, x0, q["t"], q["noise"]), q["x_t"], rtol=0, atol=1e-6)
+    # training loss with the recorded timesteps / noise
+    tr = g["train"]
+    x_t = O.q_sample(sched, x0, tr["t_idx"], tr["noise"])
+    pred = O.unet_forward(sd, uspec, x_t, tr["t_idx"], y)
+    loss = O.mse_loss(pred, tr["noise"])
+    assert float(loss) == pytest.approx(float(tr["loss"]), rel=2e-6)
+    # reverse process with the recorded draws (draw order: x_T, then z for t = T-1 ... 2)
+    rv = g["reverse"]
+    T = g["T"]
+    noises = {T - 1 - i: z for i, z in enumerate(rv["z"])}
+    den = O.reverse_process(sched, lambda x, tt, c: O.unet_forward(sd, uspec, x, tt, c), rv["x_init"], noises, cond=y)
+    assert (den - rv["denoised"]).abs().max() < 5e-5
+
+
+def test_optimizer_and_ema_restatement():
+    g = load_golden("ddpm_film3d.pt")
+    assert g["opt"]["lr"] == pytest.approx(O.lr_world_scale(1e-4, 4))
+    assert g["opt"]["weight_decay"] == pytest.approx(1e-2)
+    assert g["opt"]["betas"] == (0.9, 0.999) and g["opt"]["eps"] == pytest.approx(1e-8)
+    # AdamW first step from the recorded gradient
+    for k, gflat in g["train"]["grads"].items():
+        p0 = synth_state_dict({k: g["manifest"][k]}, seed=777)[k].flatten()[:4096]
+        p1, _, _ = O.adamw_step(p0, gflat, torch.zeros_like(p0), torch.zeros_like(p0), 1, lr=g["opt"]["lr"])
+        assert torch.allclose(p1, g["opt"]["after_step"][k], rtol=0, atol=2e-7), k
+    # EMA: shadow starts at the post-AdamW weights, model is reloaded with seed-778 weights, two updates
+    assert g["ema"]["frac"] == pytest.approx(O.ema_decay(2))
+    for k, sh in g["ema"]["shadow"].items():
+        s = g["opt"]["after_step"][k]
+        p = synth_state_dict({k: g["manifest"][k]}, seed=778)[k].flatten()[:4096]
+        s = O.ema_update(s, p, 1)
+        s = O.ema_update(s, p, 2)
+        assert torch.allclose(s, sh, rtol=0, atol=1e-7), k
