@@ -1,0 +1,285 @@
+/*
+ * rho_b200.h -- C ABI of the B200-native hot path of rho-diffusion (DDPM training step +
+ * ancestral sampling loop over the conditional n-D UNet).
+ *
+ * This is the drop-in boundary.  The reference (intel/rho-diffusion) is 100 % Python and has no
+ * native FFI; backend acceleration enters it through `ipex.optimize(model, optimizer=...)`
+ * (scripts/training_ddp.py:182-183, scripts/inference.py:161-163), the Lightning XPU
+ * accelerator/strategy registration (rho_diffusion/xpu.py:242, rho_diffusion/__init__.py:27-35)
+ * and `dist.init_process_group("ccl"|"nccl")` (rho_diffusion/utils.py:45-81).  Those hooks hand a
+ * torch module to a vendor library whose kernels then execute the ATen ops listed below.  This
+ * header is what replaces that vendor library: one entry point per ATen op class on the hot path,
+ * each citing the reference call site it stands in for.  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, POD parameter structs; no torch / C++ types.
+ *   - every call is asynchronous on `stream`, never allocates, never synchronises and is therefore
+ *     CUDA-graph capturable.  Scratch memory is caller-allocated: query `*_workspace_bytes` first.
+ *   - return value: RHO_OK (0) or a negative RHO_ERR_* code; `rho_error_string` names it and
+ *     `rho_last_error_message` (thread-local) gives detail.  Nothing throws.
+ *   - activations are CHANNELS-LAST: [N, D, H, W, C] with D = 1 (and H = 1) for 2-D (1-D) data, C
+ *     contiguous.  Parameters keep the PyTorch layouts of the reference state_dict unless a
+ *     `rho_*_pack_*` call says otherwise.
+ *   - dtype enums select the storage type of activations (RHO_F32 | RHO_BF16); all accumulation,
+ *     normalisation statistics and softmax are fp32.
+ *   - one process per GPU; calls are made from the thread that owns the stream; the library keeps
+ *     no mutable global state except a mutex-guarded cache of kernel attributes.
+ */
+#ifndef RHO_B200_H_
+#define RHO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* rho_stream_t; /* == cudaStream_t */
+
+enum {
+  RHO_OK = 0,
+  RHO_ERR_INVALID_ARG = -1,
+  RHO_ERR_UNSUPPORTED = -2,
+  RHO_ERR_CUDA = -3,
+  RHO_ERR_WORKSPACE = -4
+};
+enum { RHO_F32 = 0, RHO_BF16 = 1 };
+enum { RHO_ACT_NONE = 0, RHO_ACT_SILU = 1, RHO_ACT_RELU = 2, RHO_ACT_TANH = 3, RHO_ACT_SIGMOID = 4, RHO_ACT_GELU = 5 };
+/* conv engine selection */
+enum { RHO_CONV_AUTO = 0, RHO_CONV_SIMT = 1, RHO_CONV_TCGEN05 = 2 };
+
+int rho_abi_version(void);
+const char* rho_error_string(int code);
+const char* rho_last_error_message(void);
+/* number of kernels this library has launched in the calling process (all threads) since load */
+uint64_t rho_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * layout: NC[D]HW <-> channels-last, with dtype conversion.  Replaces the implicit layout of
+ * `x.type(self.dtype)` at the UNet boundary (rho_diffusion/models/unet_v2.py:722, 731).
+ * S = product of spatial dims. */
+int rho_nc_to_cl(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t N, int64_t C, int64_t S, rho_stream_t stream);
+int rho_cl_to_nc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t N, int64_t C, int64_t S, rho_stream_t stream);
+/* dst = a (+ b) elementwise with dtype conversion; b may be NULL */
+int rho_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, void* dst, int dst_dtype, int64_t n, rho_stream_t stream);
+/* x *= (*scale_dev if scale_dev else 1) * scale_host, in place (upstream-gradient scaling without a host sync) */
+int rho_scale(void* x, int dtype, int64_t n, const float* scale_dev, float scale_host, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * conv_nd: `conv_nd(dims, Cin, Cout, k, stride, padding)` -> nn.Conv{1,2,3}d
+ * (rho_diffusion/layers.py:77-88; call sites unet_v2.py:120,155-162,215,241,248-256,323,331,535,682),
+ * with the surrounding data movement fused in:
+ *   - channel concat of two inputs, replacing `torch.cat([h, hs.pop()], 1)` (unet_v2.py:729)
+ *   - nearest x2 upsample of the input, replacing `F.interpolate` (unet_v2.py:124-131)
+ *   - bias, and residual add `skip_connection(x) + h` / `x + h` (unet_v2.py:293, 342)
+ * k in {1,3} per dim ("same" padding k/2), stride in {1,2} per dim, upsample in {1,2} per dim.
+ * Output dims: Do = (D*ud + 2*(kd/2) - kd)/sd + 1, etc. */
+typedef struct rho_conv_params {
+  int32_t N, D, H, W;        /* input dims BEFORE the optional upsample */
+  int32_t C1, C2;            /* channels of x and of x2 (0 when x2 == NULL); Cin = C1 + C2 */
+  int32_t Cout;
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t ud, uh, uw;
+  int32_t act_dtype;         /* dtype of x, x2, residual, y (and dy, dx) */
+  int32_t w_dtype;           /* dtype of the packed weights (RHO_F32 or RHO_BF16) */
+  int32_t engine;            /* RHO_CONV_AUTO | _SIMT | _TCGEN05 */
+  int32_t y_f32;             /* 1: y is written as fp32 regardless of act_dtype (final conv -> eps) */
+  const void* x;
+  const void* x2;
+  const void* w_packed;      /* from rho_conv_pack_weight */
+  const float* bias;         /* [Cout] or NULL */
+  const void* residual;      /* [N,Do,Ho,Wo,Cout] or NULL */
+  void* y;                   /* [N,Do,Ho,Wo,Cout] */
+  void* workspace;
+  size_t workspace_bytes;
+} rho_conv_params;
+
+/* packed forward weights: [Cout][taps][Cin] (K-major rows, K = tap*Cin + ci, tap = (kd*KH + kh)*KW + kw).
+ * `w` is the reference state_dict tensor, fp32 [Cout, Cin, kd, kh, kw]. */
+int rho_conv_pack_weight(const float* w, void* packed, int packed_dtype, int32_t Cout, int32_t Cin, int32_t taps, rho_stream_t stream);
+size_t rho_conv_workspace_bytes(const rho_conv_params* p);
+int rho_conv_fwd(const rho_conv_params* p, rho_stream_t stream);
+/* which engine rho_conv_fwd would use for p (RHO_CONV_SIMT or RHO_CONV_TCGEN05) */
+int rho_conv_engine_for(const rho_conv_params* p);
+
+/* backward of the above (autograd of nn.ConvNd in `loss.backward()`, scripts/training_ddp.py:197).
+ * dgrad: dx (and dx2 for the concat partner) from dy, using the same packed forward weights.
+ * wgrad: dw fp32 in the PyTorch layout [Cout, Cin, kd, kh, kw] and dbias [Cout] (either may be NULL). */
+typedef struct rho_conv_bwd_params {
+  rho_conv_params fwd;       /* geometry + x/x2 (wgrad) + w_packed (dgrad); y/bias/residual ignored */
+  const void* dy;            /* [N,Do,Ho,Wo,Cout], act_dtype */
+  void* dx;                  /* [N,D,H,W,C1] act_dtype, or NULL */
+  void* dx2;                 /* [N,D,H,W,C2] act_dtype, or NULL */
+  float* dw;                 /* or NULL */
+  float* dbias;              /* or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} rho_conv_bwd_params;
+size_t rho_conv_bwd_workspace_bytes(const rho_conv_bwd_params* p);
+int rho_conv_dgrad(const rho_conv_bwd_params* p, rho_stream_t stream);
+int rho_conv_wgrad(const rho_conv_bwd_params* p, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm32 (+ embedding add / FiLM) + activation:
+ *   `normalization(C)` = GroupNorm32(32, C) (layers.py:71-74, 122-129), the activation that follows it
+ *   (unet_v2.py:214, 238, 681) and the conditioning in ResBlock._forward (unet_v2.py:285-292):
+ *     FiLM   : act( GN(h) * (1 + scale) + shift )
+ *     add    : act( GN(h + emb) )                      (pre_add)
+ *   The input may be the channel concat of x and x2 (up-path ResBlocks), never materialised.
+ * Two launches: rho_gn_stats (mean, rstd per (n, group); deterministic two-stage Welford merge) and
+ * rho_gn_apply.  HBM-bound: 1 read for stats, 1 read + 1 write for apply. */
+typedef struct rho_gn_params {
+  int32_t N;
+  int64_t S;                 /* spatial positions per sample */
+  int32_t C1, C2;            /* C = C1 + C2 */
+  int32_t groups;            /* 32 */
+  int32_t in_dtype, out_dtype;
+  int32_t act;
+  float eps;
+  const void* x;
+  const void* x2;
+  const float* pre_add;      /* [N, pre_add_stride] or NULL */
+  int32_t pre_add_stride;
+  const float* gamma;        /* [C] */
+  const float* beta;         /* [C] */
+  const float* scale;        /* FiLM scale [N, film_stride] or NULL */
+  const float* shift;        /* FiLM shift, same stride */
+  int32_t film_stride;
+  float* stats;              /* [N, groups, 2] = (mean, rstd) */
+  void* y;                   /* [N, S, C] out_dtype */
+  void* workspace;
+  size_t workspace_bytes;
+} rho_gn_params;
+size_t rho_gn_workspace_bytes(const rho_gn_params* p);
+int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream);
+int rho_gn_apply(const rho_gn_params* p, rho_stream_t stream);
+
+typedef struct rho_gn_bwd_params {
+  rho_gn_params fwd;         /* same tensors as the forward call (x, stats, gamma, FiLM...) ; y unused */
+  const void* dy;            /* [N,S,C] out_dtype */
+  void* dx;                  /* [N,S,C1] in_dtype */
+  void* dx2;                 /* [N,S,C2] in_dtype or NULL */
+  float* dgamma;             /* [C] */
+  float* dbeta;              /* [C] */
+  float* dscale;             /* [N, dfilm_stride] or NULL */
+  float* dshift;
+  int32_t dfilm_stride;
+  float* dpre_add;           /* [N, C] or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} rho_gn_bwd_params;
+size_t rho_gn_bwd_workspace_bytes(const rho_gn_bwd_params* p);
+int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * QKVAttentionLegacy / QKVAttention (unet_v2.py:365-436): softmax_fp32((q*s)^T (k*s)) v, s = ch^-1/4,
+ * flash-style (the T x T weight matrix is never materialised).  qkv is channels-last [N, T, 3*heads*ch];
+ * order 0 (legacy): channel = head*3ch + {q,k,v}*ch + c;  order 1 (new): channel = {q,k,v}*heads*ch + head*ch + c. */
+typedef struct rho_attn_params {
+  int32_t N, T, heads, ch;
+  int32_t order;
+  int32_t dtype;
+  const void* qkv;
+  void* out;                 /* [N, T, heads*ch] */
+  float* lse;                /* [N, heads, T] log-sum-exp of the scaled logits, or NULL (inference) */
+} rho_attn_params;
+int rho_attention_fwd(const rho_attn_params* p, rho_stream_t stream);
+typedef struct rho_attn_bwd_params {
+  rho_attn_params fwd;       /* qkv, out, lse from the forward */
+  const void* dout;          /* [N, T, heads*ch] */
+  void* dqkv;                /* [N, T, 3*heads*ch] */
+  void* workspace;
+  size_t workspace_bytes;
+} rho_attn_bwd_params;
+size_t rho_attention_bwd_workspace_bytes(const rho_attn_bwd_params* p);
+int rho_attention_bwd(const rho_attn_bwd_params* p, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * embedding path (all fp32; tiny):
+ *   sinosoidal_position_embedding (models/common.py:27-43), nn.Linear of time_embed / emb_layers
+ *   (unet_v2.py:521-525, 229-235), MultiEmbeddings.forward (models/conditioning.py:115-139). */
+/* omega: device table [dim/2] fp32, omega[i] = wavelength^(2i/dim) (built once on the host like the schedule tables);
+ * out[b, 2i] = sin(t[b]/omega[i]), out[b, 2i+1] = cos(t[b]/omega[i]) */
+int rho_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, const float* omega, float* out, rho_stream_t stream);
+typedef struct rho_linear_params {
+  int32_t B, I, O;
+  int32_t act_in;            /* y = W act_in(x) + b (+ add) */
+  const float* x;  int32_t x_stride;
+  const float* w;            /* [O, I] */
+  const float* b;            /* [O] or NULL */
+  const float* add; int32_t add_stride; /* optional [B, O] */
+  float* y; int32_t y_stride;
+} rho_linear_params;
+int rho_linear_fwd(const rho_linear_params* p, rho_stream_t stream);
+/* dx = act_in'(x) * (W^T dy) ; dw = dy^T act_in(x) ; db = sum_b dy.  Any output may be NULL. */
+int rho_linear_bwd(const rho_linear_params* p, const float* dy, int32_t dy_stride, float* dx, int32_t dx_stride,
+                   float* dw, float* db, rho_stream_t stream);
+/* out[b,:] (+)= table[index of y[b*y_stride] in values[0..V)] ; idx_out[b] receives the index (-1: no match) */
+int rho_embedding_match(const float* y, int32_t y_stride, int32_t B, const float* values, int32_t V,
+                        const float* table, int32_t dim, float* out, int32_t accumulate, int32_t* idx_out,
+                        rho_stream_t stream);
+/* dtable[idx[b], :] += dout[b, :]  (dtable must be zero-initialised by the caller; deterministic order) */
+int rho_embedding_match_bwd(const int32_t* idx, int32_t B, const float* dout, int32_t dim, float* dtable, int32_t V,
+                            rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * diffusion math (rho_diffusion/diffusion/ddpm.py):
+ *   rho_randn            torch.randn_like (ddpm.py:101-102, 171, 196-199): Philox4x32-10 + Box-Muller,
+ *                        element i of call (seed, offset) is counter (i/4, offset), lane i%4.
+ *   rho_q_sample         forward_process (ddpm.py:104-130): x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) eps
+ *   rho_p_sample_step    one iteration of reverse_process (ddpm.py:196-218), step index read from device
+ *                        memory so that a captured CUDA graph can be replayed T times:
+ *                          t == 0 : x unchanged;  t <= 1 : z = 0
+ *                          x <- clamp((x - beta_t/sqrt(1-abar_t) eps)/sqrt(alpha_t) + noise_scale sqrt(beta_t) z, lo, hi)
+ *                        z is read from `z` if non-NULL, else generated in-kernel from (seed, t).
+ *   rho_advance_timestep t_vec[b] = *t - 1 ; *t = *t - 1   (the host loop `for t in steps`, ddpm.py:195-205)
+ *   rho_mse_loss         nn.MSELoss (ddpm.py:280) and its gradient, deterministic two-stage reduction. */
+int rho_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, rho_stream_t stream);
+/* test hook: raw Philox4x32-10 words, out[4g + j] = philox(counter = (g, offset), key = seed)[j] */
+int rho_philox_raw(uint32_t* out, int64_t groups, uint64_t seed, uint64_t offset, rho_stream_t stream);
+int rho_q_sample(const float* x0, const float* noise, const int64_t* t, const float* alpha_bar, int32_t T,
+                 int32_t N, int64_t per_sample, float* x_t, rho_stream_t stream);
+typedef struct rho_p_sample_params {
+  float* x;                  /* in/out, fp32 */
+  const float* eps;          /* model output, fp32 */
+  const float* z;            /* optional externally supplied noise for this step */
+  const int64_t* t;          /* device scalar: current step index */
+  const float* alpha; const float* beta; const float* alpha_bar; /* [T] fp32 tables */
+  int32_t T;
+  int64_t n;                 /* total elements */
+  float noise_scale;         /* 0.8 (ddpm.py:215) */
+  float clamp_lo, clamp_hi;  /* -1, 1 (ddpm.py:218) */
+  uint64_t seed;
+} rho_p_sample_params;
+int rho_p_sample_step(const rho_p_sample_params* p, rho_stream_t stream);
+int rho_advance_timestep(int64_t* t_scalar, int64_t* t_vec, int32_t B, rho_stream_t stream);
+size_t rho_mse_workspace_bytes(int64_t n);
+int rho_mse_loss(const void* pred, int pred_dtype, const float* target, int64_t n, float* loss,
+                 void* dpred /* same dtype as pred, or NULL */, float grad_scale, void* workspace, size_t workspace_bytes,
+                 rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * optimizer: torch.optim.AdamW as configured by configure_optimizers (abstract_diffusion.py:86-148)
+ * fused with ExponentialMovingAverage.update (ema.py:41-57), over flat fp32 buffers:
+ *   g' = g * grad_scale ; p *= 1 - lr*wd ; m,v update ; p -= lr/bc1 * m/(sqrt(v)/sqrt(bc2) + eps)
+ *   shadow -= (1 - ema_decay_t) * (shadow - p)      (skipped when shadow == NULL)
+ *   p_bf16 (optional) receives the bf16 copy used by the next forward. */
+typedef struct rho_adamw_params {
+  float* p; const float* g; float* m; float* v; float* shadow;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;              /* 1-based */
+  float ema_decay_t;         /* d * (1 - exp(-step/2000)) */
+  float grad_scale;
+} rho_adamw_params;
+int rho_adamw_ema_step(const rho_adamw_params* p, rho_stream_t stream);
+/* stand-alone ExponentialMovingAverage.update for one tensor (ema.py:52-57): shadow -= one_minus_decay * (shadow - p) */
+int rho_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, rho_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHO_B200_H_ */

@@ -385,3 +385,41 @@ def ema_update(shadow, p, step: int, decay: float = 0.9999):
 def lr_world_scale(lr: float, world: int) -> float:
     """abstract_diffusion.py:118 -- lr * sqrt(world)."""
     return lr * math.sqrt(world)
+
+
+# --------------------------------------------------------------------------------------------
+# RNG: Philox4x32-10 (Salmon et al. 2011, Random123) -- integer restatement for bit-exact checks of the
+# in-kernel noise generator that replaces torch.randn_like (ddpm.py:101-102, 171, 196-199)
+# --------------------------------------------------------------------------------------------
+
+
+def philox4x32_10(groups: int, offset: int, seed: int) -> np.ndarray:
+    """uint32 [groups, 4]: counter = (g_lo, g_hi, offset_lo, offset_hi), key = (seed_lo, seed_hi)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    g = np.arange(groups, dtype=np.uint64)
+    c = [g & np.uint64(0xFFFFFFFF), g >> np.uint64(32),
+         np.full(groups, offset & 0xFFFFFFFF, dtype=np.uint64), np.full(groups, (offset >> 32) & 0xFFFFFFFF, dtype=np.uint64)]
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def philox_normal(n: int, offset: int, seed: int) -> np.ndarray:
+    """float32 [n]: Box-Muller on 24-bit uniforms, 4 normals per counter (cos, sin, cos, sin)."""
+    groups = (n + 3) // 4
+    w = philox4x32_10(groups, offset, seed).astype(np.float64)
+    u = (np.floor(w / 256.0) + 0.5) * 2.0 ** -24
+    out = np.empty((groups, 4), dtype=np.float64)
+    for h in range(2):
+        r = np.sqrt(-2.0 * np.log(u[:, 2 * h]))
+        out[:, 2 * h] = r * np.cos(2 * np.pi * u[:, 2 * h + 1])
+        out[:, 2 * h + 1] = r * np.sin(2 * np.pi * u[:, 2 * h + 1])
+    return out.reshape(-1)[:n].astype(np.float32)

@@ -1,0 +1,84 @@
+// C-ABI entry points of conv_nd and engine selection (tcgen05 implicit GEMM vs CUDA-core fallback).
+#include "conv_geom.cuh"
+
+namespace rho {
+// conv_simt.cu
+int conv_fwd_simt(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
+int conv_dgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
+int conv_wgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
+size_t conv_wgrad_simt_workspace(const ConvGeom& g);
+// conv_tc.cu
+bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p);
+int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
+bool conv_dgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
+int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
+size_t conv_dgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
+
+static int validate_fwd(const rho_conv_params* p, ConvGeom& g) {
+  int rc = make_geom(p, g);
+  if (rc) return rc;
+  RHO_REQUIRE(p->x && p->w_packed && p->y, "conv_fwd: null tensor");
+  RHO_REQUIRE((p->C2 == 0) == (p->x2 == nullptr), "conv_fwd: x2/C2 mismatch");
+  RHO_REQUIRE(g.M > 0, "conv_fwd: empty output");
+  return RHO_OK;
+}
+}  // namespace rho
+
+using namespace rho;
+
+extern "C" {
+
+int rho_conv_engine_for(const rho_conv_params* p) {
+  ConvGeom g;
+  if (make_geom(p, g)) return RHO_ERR_INVALID_ARG;
+  if (p->engine == RHO_CONV_SIMT) return RHO_CONV_SIMT;
+  return conv_fwd_tc_supported(g, p) ? RHO_CONV_TCGEN05 : RHO_CONV_SIMT;
+}
+
+size_t rho_conv_workspace_bytes(const rho_conv_params* p) {
+  (void)p;
+  return 0;
+}
+
+int rho_conv_fwd(const rho_conv_params* p, rho_stream_t stream) {
+  ConvGeom g;
+  int rc = validate_fwd(p, g);
+  if (rc) return rc;
+  const bool tc_ok = conv_fwd_tc_supported(g, p);
+  if (p->engine == RHO_CONV_TCGEN05 && !tc_ok) return fail(RHO_ERR_UNSUPPORTED, "conv_fwd: tcgen05 engine does not take this shape");
+  if (p->engine != RHO_CONV_SIMT && tc_ok) return conv_fwd_tc(g, p, as_stream(stream));
+  return conv_fwd_simt(g, p, as_stream(stream));
+}
+
+size_t rho_conv_bwd_workspace_bytes(const rho_conv_bwd_params* p) {
+  ConvGeom g;
+  if (!p || make_geom(&p->fwd, g)) return 0;
+  size_t a = conv_wgrad_simt_workspace(g);
+  size_t b = conv_dgrad_tc_workspace(g, p);
+  return a > b ? a : b;
+}
+
+int rho_conv_dgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
+  RHO_REQUIRE(p, "conv_dgrad: null params");
+  ConvGeom g;
+  int rc = make_geom(&p->fwd, g);
+  if (rc) return rc;
+  RHO_REQUIRE(p->dy && p->dx && p->fwd.w_packed, "conv_dgrad: null tensor");
+  RHO_REQUIRE((g.C2 == 0) || p->dx2, "conv_dgrad: dx2 required for a concat input");
+  const bool tc_ok = conv_dgrad_tc_supported(g, p);
+  if (p->fwd.engine == RHO_CONV_TCGEN05 && !tc_ok) return fail(RHO_ERR_UNSUPPORTED, "conv_dgrad: tcgen05 engine does not take this shape");
+  if (p->fwd.engine != RHO_CONV_SIMT && tc_ok) return conv_dgrad_tc(g, p, as_stream(stream));
+  return conv_dgrad_simt(g, p, as_stream(stream));
+}
+
+int rho_conv_wgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
+  RHO_REQUIRE(p, "conv_wgrad: null params");
+  ConvGeom g;
+  int rc = make_geom(&p->fwd, g);
+  if (rc) return rc;
+  RHO_REQUIRE(p->dy, "conv_wgrad: null dy");
+  RHO_REQUIRE(p->dw || p->dbias, "conv_wgrad: nothing to compute");
+  return conv_wgrad_simt(g, p, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+// Error plumbing, ABI version and the layout / cast kernels at the UNet boundary.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rho {
+
+thread_local char g_last_error[512] = {0};
+std::atomic<uint64_t> g_launch_count{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// NC[S] -> N[S]C through a 32x32 shared-memory tile (coalesced on both sides).
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_cs_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t R, int64_t Cc) {
+  // src: [batch][R][Cc] -> dst: [batch][Cc][R]
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t tiles_c = (Cc + 31) / 32;
+  const int64_t c0 = ((int64_t)blockIdx.x % tiles_c) * 32, r0 = ((int64_t)blockIdx.x / tiles_c) * 32;
+  const TS* s = src + b * R * Cc;
+  TD* d = dst + b * R * Cc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t r = r0 + ty + i * 8, c = c0 + tx;
+    if (r < R && c < Cc) tile[ty + i * 8][tx] = to_f32(s[r * Cc + c]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < R && c < Cc) d[c * R + r] = from_f32<TD>(tile[tx][ty + i * 8]);
+  }
+}
+
+template <typename TA, typename TB, typename TD>
+__global__ void add_cast_kernel(const TA* __restrict__ a, const TB* __restrict__ b, TD* __restrict__ d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = to_f32(a[i]);
+    if (b) v += to_f32(b[i]);
+    d[i] = from_f32<TD>(v);
+  }
+}
+
+template <typename T>
+__global__ void scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ s_dev, float s_host) {
+  const float s = (s_dev ? *s_dev : 1.0f) * s_host;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = from_f32<T>(to_f32(x[i]) * s);
+}
+
+template <typename TS, typename TD>
+static int launch_transpose(const void* src, void* dst, int64_t batch, int64_t R, int64_t Cc, cudaStream_t st) {
+  if (batch == 0 || R == 0 || Cc == 0) return RHO_OK;
+  if (R == 1 || Cc == 1) {  // pure cast/copy
+    int64_t n = batch * R * Cc;
+    int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 16);
+    add_cast_kernel<TS, TS, TD><<<blocks, 256, 0, st>>>((const TS*)src, (const TS*)nullptr, (TD*)dst, n);
+    RHO_CHECK_LAUNCH("cast");
+    return RHO_OK;
+  }
+  int64_t tiles = ceil_div(Cc, 32) * ceil_div(R, 32);
+  if (tiles > 2147483647LL || batch > 65535) return fail(RHO_ERR_UNSUPPORTED, "transpose: dims too large");
+  dim3 grid((unsigned)tiles, 1, (unsigned)batch);
+  transpose_cs_kernel<TS, TD><<<grid, 256, 0, st>>>((const TS*)src, (TD*)dst, R, Cc);
+  RHO_CHECK_LAUNCH("transpose");
+  return RHO_OK;
+}
+
+static int transpose_dispatch(const void* src, int sdt, void* dst, int ddt, int64_t batch, int64_t R, int64_t Cc, cudaStream_t st) {
+  if (sdt == RHO_F32 && ddt == RHO_F32) return launch_transpose<float, float>(src, dst, batch, R, Cc, st);
+  if (sdt == RHO_F32 && ddt == RHO_BF16) return launch_transpose<float, bf16>(src, dst, batch, R, Cc, st);
+  if (sdt == RHO_BF16 && ddt == RHO_F32) return launch_transpose<bf16, float>(src, dst, batch, R, Cc, st);
+  if (sdt == RHO_BF16 && ddt == RHO_BF16) return launch_transpose<bf16, bf16>(src, dst, batch, R, Cc, st);
+  return fail(RHO_ERR_INVALID_ARG, "transpose: bad dtype");
+}
+
+}  // namespace rho
+
+using namespace rho;
+
+extern "C" {
+
+int rho_abi_version(void) { return 1; }
+
+const char* rho_error_string(int code) {
+  switch (code) {
+    case RHO_OK: return "ok";
+    case RHO_ERR_INVALID_ARG: return "invalid argument";
+    case RHO_ERR_UNSUPPORTED: return "unsupported configuration";
+    case RHO_ERR_CUDA: return "CUDA error";
+    case RHO_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+const char* rho_last_error_message(void) { return g_last_error; }
+
+uint64_t rho_launch_count(void) { return g_launch_count.load(); }
+
+int rho_nc_to_cl(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t N, int64_t C, int64_t S, rho_stream_t stream) {
+  RHO_REQUIRE(src && dst, "nc_to_cl: null pointer");
+  // src [N][C][S] -> dst [N][S][C]
+  return transpose_dispatch(src, src_dtype, dst, dst_dtype, N, C, S, as_stream(stream));
+}
+
+int rho_cl_to_nc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t N, int64_t C, int64_t S, rho_stream_t stream) {
+  RHO_REQUIRE(src && dst, "cl_to_nc: null pointer");
+  // src [N][S][C] -> dst [N][C][S]
+  return transpose_dispatch(src, src_dtype, dst, dst_dtype, N, S, C, as_stream(stream));
+}
+
+int rho_scale(void* x, int dtype, int64_t n, const float* scale_dev, float scale_host, rho_stream_t stream) {
+  RHO_REQUIRE(x, "scale: null pointer");
+  if (n == 0) return RHO_OK;
+  int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 16);
+  if (dtype == RHO_F32) scale_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((float*)x, n, scale_dev, scale_host);
+  else if (dtype == RHO_BF16) scale_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((bf16*)x, n, scale_dev, scale_host);
+  else return fail(RHO_ERR_INVALID_ARG, "scale: bad dtype");
+  RHO_CHECK_LAUNCH("scale");
+  return RHO_OK;
+}
+
+int rho_add_cast(const void* a, int adt, const void* b, int bdt, void* d, int ddt, int64_t n, rho_stream_t stream) {
+  RHO_REQUIRE(a && d, "add_cast: null pointer");
+  if (n == 0) return RHO_OK;
+  cudaStream_t st = as_stream(stream);
+  int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 16);
+#define RHO_AC(TA, TB, TD) add_cast_kernel<TA, TB, TD><<<blocks, 256, 0, st>>>((const TA*)a, (const TB*)b, (TD*)d, n)
+  int key = adt * 4 + (b ? bdt : adt) * 2 + ddt;
+  switch (key) {
+    case 0: RHO_AC(float, float, float); break;
+    case 1: RHO_AC(float, float, bf16); break;
+    case 2: RHO_AC(float, bf16, float); break;
+    case 3: RHO_AC(float, bf16, bf16); break;
+    case 4: RHO_AC(bf16, float, float); break;
+    case 5: RHO_AC(bf16, float, bf16); break;
+    case 6: RHO_AC(bf16, bf16, float); break;
+    case 7: RHO_AC(bf16, bf16, bf16); break;
+    default: return fail(RHO_ERR_INVALID_ARG, "add_cast: bad dtype");
+  }
+#undef RHO_AC
+  RHO_CHECK_LAUNCH("add_cast");
+  return RHO_OK;
+}
+
+}  // extern "C"

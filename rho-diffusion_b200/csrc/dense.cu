@@ -1,0 +1,158 @@
+// Embedding path (fp32, tiny): sinusoidal timestep embedding (rho_diffusion/models/common.py:27-43), the
+// nn.Linear layers of `time_embed` and `emb_layers` (rho_diffusion/models/unet_v2.py:521-525, 229-235)
+// with the preceding activation fused, and MultiEmbeddings.forward
+// (rho_diffusion/models/conditioning.py:115-139).  B is the batch (<= a few hundred), so these are
+// latency-bound GEMVs: one warp per output element, coalesced over the reduction dimension.
+#include "common.cuh"
+
+namespace rho {
+
+// omega[k] = wavelength^(2k/dim) is a per-model constant table built on the host exactly as the reference builds
+// it (float32 torch.pow); powf on the device may differ by an ulp, which sin/cos at t ~ 1000 would amplify to 1e-4.
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, int dim, const float* __restrict__ omega_tab,
+                                          float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int half = dim / 2;
+  if (i >= B * half) return;
+  int b = i / half, k = i % half;
+  float arg = (float)t[b] / omega_tab[k];
+  out[(long long)b * dim + 2 * k] = sinf(arg);
+  out[(long long)b * dim + 2 * k + 1] = cosf(arg);
+}
+
+// y[b][o] = sum_i act(x[b][i]) * w[o][i] + bias[o] (+ add[b][o]); one warp per (b, o)
+__global__ void __launch_bounds__(256) linear_fwd_kernel(rho_linear_params p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B * p.O) return;
+  const int b = warp / p.O, o = warp % p.O;
+  const float* x = p.x + (long long)b * p.x_stride;
+  const float* w = p.w + (long long)o * p.I;
+  float s = 0.f;
+  for (int i = lane; i < p.I; i += 32) s = fmaf(apply_act(x[i], p.act_in), w[i], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (p.b) s += p.b[o];
+    if (p.add) s += p.add[(long long)b * p.add_stride + o];
+    p.y[(long long)b * p.y_stride + o] = s;
+  }
+}
+
+// dx[b][i] = act'(x[b][i]) * sum_o dy[b][o] * w[o][i]; thread per (b, i) (coalesced over i in w rows)
+__global__ void linear_bwd_dx_kernel(rho_linear_params p, const float* __restrict__ dy, int dy_stride, float* __restrict__ dx, int dx_stride) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * p.I) return;
+  int b = idx / p.I, i = idx % p.I;
+  float s = 0.f;
+  for (int o = 0; o < p.O; ++o) s = fmaf(dy[(long long)b * dy_stride + o], p.w[(long long)o * p.I + i], s);
+  dx[(long long)b * dx_stride + i] = s * act_grad(p.x[(long long)b * p.x_stride + i], p.act_in);
+}
+
+// dw[o][i] = sum_b dy[b][o] * act(x[b][i]); thread per (o, i)
+__global__ void linear_bwd_dw_kernel(rho_linear_params p, const float* __restrict__ dy, int dy_stride, float* __restrict__ dw) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.O * p.I) return;
+  int o = (int)(idx / p.I), i = (int)(idx % p.I);
+  float s = 0.f;
+  for (int b = 0; b < p.B; ++b) s = fmaf(dy[(long long)b * dy_stride + o], apply_act(p.x[(long long)b * p.x_stride + i], p.act_in), s);
+  dw[idx] = s;
+}
+
+__global__ void linear_bwd_db_kernel(int B, int O, const float* __restrict__ dy, int dy_stride, float* __restrict__ db) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += dy[(long long)b * dy_stride + o];
+  db[o] = s;
+}
+
+__global__ void embedding_match_kernel(const float* __restrict__ y, int y_stride, int B, const float* __restrict__ values, int V,
+                                       const float* __restrict__ table, int dim, float* __restrict__ out, int accumulate,
+                                       int* __restrict__ idx_out) {
+  const int b = blockIdx.x;
+  __shared__ int s_idx;
+  if (threadIdx.x == 0) {
+    const float v = y[(long long)b * y_stride];
+    int found = -1;
+    for (int k = 0; k < V; ++k)
+      if (values[k] == v) { found = k; break; }
+    s_idx = found;
+    if (idx_out) idx_out[b] = found;
+  }
+  __syncthreads();
+  const int k = s_idx;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float e = k >= 0 ? table[(long long)k * dim + d] : 0.f;
+    float* o = out + (long long)b * dim + d;
+    *o = accumulate ? *o + e : e;
+  }
+}
+
+// thread per (v, d): deterministic accumulation over the batch in index order
+__global__ void embedding_match_bwd_kernel(const int* __restrict__ idx, int B, const float* __restrict__ dout, int dim,
+                                           float* __restrict__ dtable, int V) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * dim) return;
+  int v = i / dim, d = i % dim;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b)
+    if (idx[b] == v) s += dout[(long long)b * dim + d];
+  dtable[i] += s;
+}
+
+}  // namespace rho
+
+using namespace rho;
+
+extern "C" {
+
+int rho_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, const float* omega, float* out, rho_stream_t stream) {
+  RHO_REQUIRE(t && out && omega && B > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad args (dim must be even)");
+  int total = B * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(t, B, dim, omega, out);
+  RHO_CHECK_LAUNCH("timestep_embedding");
+  return RHO_OK;
+}
+
+int rho_linear_fwd(const rho_linear_params* p, rho_stream_t stream) {
+  RHO_REQUIRE(p && p->x && p->w && p->y && p->B > 0 && p->I > 0 && p->O > 0, "linear_fwd: bad args");
+  long long warps = (long long)p->B * p->O;
+  linear_fwd_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, as_stream(stream)>>>(*p);
+  RHO_CHECK_LAUNCH("linear_fwd");
+  return RHO_OK;
+}
+
+int rho_linear_bwd(const rho_linear_params* p, const float* dy, int32_t dy_stride, float* dx, int32_t dx_stride, float* dw, float* db,
+                   rho_stream_t stream) {
+  RHO_REQUIRE(p && p->x && p->w && dy && p->B > 0 && p->I > 0 && p->O > 0, "linear_bwd: bad args");
+  cudaStream_t st = as_stream(stream);
+  if (dx) {
+    linear_bwd_dx_kernel<<<(unsigned)ceil_div((long long)p->B * p->I, 128), 128, 0, st>>>(*p, dy, dy_stride, dx, dx_stride);
+    RHO_CHECK_LAUNCH("linear_bwd_dx");
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<(unsigned)ceil_div((long long)p->O * p->I, 128), 128, 0, st>>>(*p, dy, dy_stride, dw);
+    RHO_CHECK_LAUNCH("linear_bwd_dw");
+  }
+  if (db) {
+    linear_bwd_db_kernel<<<(p->O + 127) / 128, 128, 0, st>>>(p->B, p->O, dy, dy_stride, db);
+    RHO_CHECK_LAUNCH("linear_bwd_db");
+  }
+  return RHO_OK;
+}
+
+int rho_embedding_match(const float* y, int32_t y_stride, int32_t B, const float* values, int32_t V, const float* table, int32_t dim,
+                        float* out, int32_t accumulate, int32_t* idx_out, rho_stream_t stream) {
+  RHO_REQUIRE(y && values && table && out && B > 0 && V > 0 && dim > 0, "embedding_match: bad args");
+  embedding_match_kernel<<<B, 128, 0, as_stream(stream)>>>(y, y_stride, B, values, V, table, dim, out, accumulate, idx_out);
+  RHO_CHECK_LAUNCH("embedding_match");
+  return RHO_OK;
+}
+
+int rho_embedding_match_bwd(const int32_t* idx, int32_t B, const float* dout, int32_t dim, float* dtable, int32_t V, rho_stream_t stream) {
+  RHO_REQUIRE(idx && dout && dtable && B > 0 && V > 0 && dim > 0, "embedding_match_bwd: bad args");
+  embedding_match_bwd_kernel<<<(V * dim + 127) / 128, 128, 0, as_stream(stream)>>>(idx, B, dout, dim, dtable, V);
+  RHO_CHECK_LAUNCH("embedding_match_bwd");
+  return RHO_OK;
+}
+
+}  // extern "C"

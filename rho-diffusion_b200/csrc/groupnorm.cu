@@ -1,0 +1,616 @@
+// GroupNorm32 (+ embedding add / FiLM) + activation, forward and backward, channels-last.
+//
+// Replaces `normalization(C)` = GroupNorm32(32, C) (rho_diffusion/layers.py:71-74,122-129) fused with
+// the activation that follows it and with the conditioning of ResBlock._forward
+// (rho_diffusion/models/unet_v2.py:285-292).  The input may be the (never materialised) channel
+// concat of two tensors (unet_v2.py:729).
+//
+// HBM-bound.  Data layout [N][S][C] (C contiguous): a CTA streams a contiguous slab of
+// `positions x C` so every load is a fully coalesced 16-byte (fp32) / 8-byte (bf16) vector; each
+// thread owns a fixed 4-channel column, so the per-channel parameters live in registers.
+// Statistics use shifted sums per thread and Chan's pairwise merge across threads / CTAs in a fixed
+// order (deterministic, no atomics).
+#include "common.cuh"
+
+namespace rho {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_C = 2048;
+
+struct GnMap {
+  int CV;             // 4-channel vectors per position
+  int rows_per_pass;  // positions handled concurrently by one CTA pass
+  int cv_blocks;      // passes over the channel dimension (1 unless C > 1024)
+};
+
+__host__ __device__ inline GnMap gn_map(int C) {
+  GnMap m;
+  m.CV = C / 4;
+  if (m.CV <= GN_THREADS) {
+    m.rows_per_pass = GN_THREADS / m.CV;
+    m.cv_blocks = 1;
+  } else {
+    m.rows_per_pass = 1;
+    m.cv_blocks = (m.CV + GN_THREADS - 1) / GN_THREADS;
+  }
+  return m;
+}
+
+template <typename T>
+__device__ __forceinline__ void gn_load(const T* __restrict__ x, const T* __restrict__ x2, int C1, int C2, int64_t row, int c,
+                                        float (&v)[4]) {
+  if (c < C1) load4(x + row * C1 + c, v);
+  else load4(x2 + row * C2 + (c - C1), v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stats
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2,
+                                                              const float* __restrict__ pre_add, int pre_stride, int C1, int C2,
+                                                              int64_t S, int G, int chunks, float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const GnMap mp = gn_map(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per;
+  const int64_t p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+
+  __shared__ float ch_n[GN_MAX_C], ch_mean[GN_MAX_C], ch_m2[GN_MAX_C];
+  __shared__ float sc_n[1024], sc_mean[1024], sc_m2[1024];
+
+  const T* xb = x + (int64_t)n * S * C1;
+  const T* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+
+  for (int cvb = 0; cvb < mp.cv_blocks; ++cvb) {
+    int row, cv;
+    bool active;
+    if (mp.cv_blocks == 1) {
+      row = tid / mp.CV;
+      cv = tid % mp.CV;
+      active = row < mp.rows_per_pass;
+    } else {
+      row = 0;
+      cv = cvb * GN_THREADS + tid;
+      active = cv < mp.CV;
+    }
+    const int c = cv * 4;
+    float K[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float cnt = 0.f;
+    if (active) {
+      float pa[4] = {0, 0, 0, 0};
+      if (pre_add) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pa[j] = pre_add[(int64_t)n * pre_stride + c + j];
+      }
+      int64_t p = p0 + row;
+      if (p < p1) {
+        float v[4];
+        gn_load(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) K[j] = v[j] + pa[j];
+      }
+      for (; p < p1; p += mp.rows_per_pass) {
+        float v[4];
+        gn_load(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d = (v[j] + pa[j]) - K[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+        cnt += 1.f;
+      }
+    }
+    // per-thread channel moments -> scratch[row][channel within pass]
+    if (mp.cv_blocks == 1) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int idx = row * C + c + j;
+          float mean = cnt > 0.f ? K[j] + s1[j] / cnt : 0.f;
+          float m2 = cnt > 0.f ? fmaxf(s2[j] - s1[j] * s1[j] / cnt, 0.f) : 0.f;
+          sc_n[idx] = cnt; sc_mean[idx] = mean; sc_m2[idx] = m2;
+        }
+      }
+      __syncthreads();
+      for (int cc = tid; cc < C; cc += GN_THREADS) {
+        Moments a = {sc_n[cc], sc_mean[cc], sc_m2[cc]};
+        for (int r = 1; r < mp.rows_per_pass; ++r) {
+          Moments b = {sc_n[r * C + cc], sc_mean[r * C + cc], sc_m2[r * C + cc]};
+          a = merge(a, b);
+        }
+        ch_n[cc] = a.n; ch_mean[cc] = a.mean; ch_m2[cc] = a.m2;
+      }
+    } else if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float mean = cnt > 0.f ? K[j] + s1[j] / cnt : 0.f;
+        float m2 = cnt > 0.f ? fmaxf(s2[j] - s1[j] * s1[j] / cnt, 0.f) : 0.f;
+        ch_n[c + j] = cnt; ch_mean[c + j] = mean; ch_m2[c + j] = m2;
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += GN_THREADS) {
+    Moments a = {ch_n[g * cpg], ch_mean[g * cpg], ch_m2[g * cpg]};
+    for (int j = 1; j < cpg; ++j) {
+      Moments b = {ch_n[g * cpg + j], ch_mean[g * cpg + j], ch_m2[g * cpg + j]};
+      a = merge(a, b);
+    }
+    float* o = partial + (((int64_t)n * chunks + chunk) * G + g) * 3;
+    o[0] = a.n; o[1] = a.mean; o[2] = a.m2;
+  }
+}
+
+__global__ void gn_stats_finalize_kernel(const float* __restrict__ partial, int NG, int G, int chunks, float eps,
+                                         float* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  int n = i / G, g = i % G;
+  Moments a = {0.f, 0.f, 0.f};
+  for (int k = 0; k < chunks; ++k) {
+    const float* o = partial + (((int64_t)n * chunks + k) * G + g) * 3;
+    Moments b = {o[0], o[1], o[2]};
+    a = merge(a, b);
+  }
+  float var = a.n > 0.f ? a.m2 / a.n : 0.f;
+  stats[2 * i] = a.mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply
+// ------------------------------------------------------------------------------------------------
+struct GnCoef {
+  float mean[4], rstd[4], gamma[4], beta[4], pa[4], sc[4], sh[4];
+};
+
+__device__ __forceinline__ void gn_load_coef(GnCoef& k, int n, int c, int C, int G, const float* __restrict__ stats,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             const float* __restrict__ pre_add, int pre_stride, const float* __restrict__ scale,
+                                             const float* __restrict__ shift, int film_stride) {
+  const int cpg = C / G;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int g = (c + j) / cpg;
+    k.mean[j] = stats[((int64_t)n * G + g) * 2];
+    k.rstd[j] = stats[((int64_t)n * G + g) * 2 + 1];
+    k.gamma[j] = gamma[c + j];
+    k.beta[j] = beta[c + j];
+    k.pa[j] = pre_add ? pre_add[(int64_t)n * pre_stride + c + j] : 0.f;
+    k.sc[j] = scale ? scale[(int64_t)n * film_stride + c + j] : 0.f;
+    k.sh[j] = shift ? shift[(int64_t)n * film_stride + c + j] : 0.f;
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const TI* __restrict__ x, const TI* __restrict__ x2,
+                                                              const float* __restrict__ pre_add, int pre_stride,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              int film_stride, const float* __restrict__ stats, int C1, int C2,
+                                                              int64_t S, int G, int chunks, int act, TO* __restrict__ y) {
+  const int C = C1 + C2;
+  const GnMap mp = gn_map(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per;
+  const int64_t p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const TI* xb = x + (int64_t)n * S * C1;
+  const TI* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+  TO* yb = y + (int64_t)n * S * C;
+  const bool film = scale != nullptr;
+
+  for (int cvb = 0; cvb < mp.cv_blocks; ++cvb) {
+    int row, cv;
+    bool active;
+    if (mp.cv_blocks == 1) {
+      row = tid / mp.CV; cv = tid % mp.CV; active = row < mp.rows_per_pass;
+    } else {
+      row = 0; cv = cvb * GN_THREADS + tid; active = cv < mp.CV;
+    }
+    if (!active) continue;
+    const int c = cv * 4;
+    GnCoef k;
+    gn_load_coef(k, n, c, C, G, stats, gamma, beta, pre_add, pre_stride, scale, shift, film_stride);
+    const int step = mp.rows_per_pass;
+    int64_t p = p0 + row;
+    // 4 rows in flight per thread
+    for (; p + 3 * (int64_t)step < p1; p += 4 * (int64_t)step) {
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gn_load(xb, x2b, C1, C2, p + (int64_t)u * step, c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = ((v[u][j] + k.pa[j]) - k.mean[j]) * k.rstd[j] * k.gamma[j] + k.beta[j];
+          if (film) t = t * (1.f + k.sc[j]) + k.sh[j];
+          v[u][j] = apply_act(t, act);
+        }
+        store4(yb + (p + (int64_t)u * step) * C + c, v[u]);
+      }
+    }
+    for (; p < p1; p += step) {
+      float v[4];
+      gn_load(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = ((v[j] + k.pa[j]) - k.mean[j]) * k.rstd[j] * k.gamma[j] + k.beta[j];
+        if (film) t = t * (1.f + k.sc[j]) + k.sh[j];
+        v[j] = apply_act(t, act);
+      }
+      store4(yb + p * C + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+//   xhat = ((x + pa) - mean) * rstd ; u = xhat*gamma + beta ; v = film ? u*(1+sc)+sh : u ; y = act(v)
+//   dv = dy * act'(v)
+//   pass 1: per (n, c) S1 = sum_p dv, S2 = sum_p dv*xhat, S3 = sum_p xhat            (chunk partials)
+//   reduce: dshift = S1 ; dscale = gamma*S2 + beta*S1 ; A = gamma*(1+sc)
+//           m1[n,g] = sum_{c in g} A*S1 / (cpg*S) ; m2[n,g] = sum_{c in g} A*S2 / (cpg*S)
+//           dgamma[c] = sum_n (1+sc)*S2 ; dbeta[c] = sum_n (1+sc)*S1
+//           dpre[n,c] = rstd*(A*S1 - S*m1 - m2*S3)
+//   pass 2: dx = rstd * (A*dv - m1 - xhat*m2)
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_pass1_kernel(const TI* __restrict__ x, const TI* __restrict__ x2,
+                                                                  const TO* __restrict__ dy, const float* __restrict__ pre_add,
+                                                                  int pre_stride, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int film_stride,
+                                                                  const float* __restrict__ stats, int C1, int C2, int64_t S, int G,
+                                                                  int chunks, int act, float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const GnMap mp = gn_map(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per;
+  const int64_t p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const TI* xb = x + (int64_t)n * S * C1;
+  const TI* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+  const TO* dyb = dy + (int64_t)n * S * C;
+  const bool film = scale != nullptr;
+  __shared__ float sc1[1024], sc2[1024], sc3[1024];
+  float* out = partial + ((int64_t)n * chunks + chunk) * C * 3;
+
+  for (int cvb = 0; cvb < mp.cv_blocks; ++cvb) {
+    int row, cv;
+    bool active;
+    if (mp.cv_blocks == 1) {
+      row = tid / mp.CV; cv = tid % mp.CV; active = row < mp.rows_per_pass;
+    } else {
+      row = 0; cv = cvb * GN_THREADS + tid; active = cv < mp.CV;
+    }
+    const int c = cv * 4;
+    float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, a3[4] = {0, 0, 0, 0};
+    if (active) {
+      GnCoef k;
+      gn_load_coef(k, n, c, C, G, stats, gamma, beta, pre_add, pre_stride, scale, shift, film_stride);
+      for (int64_t p = p0 + row; p < p1; p += mp.rows_per_pass) {
+        float v[4], d[4];
+        gn_load(xb, x2b, C1, C2, p, c, v);
+        load4(dyb + p * C + c, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float xh = ((v[j] + k.pa[j]) - k.mean[j]) * k.rstd[j];
+          float t = xh * k.gamma[j] + k.beta[j];
+          if (film) t = t * (1.f + k.sc[j]) + k.sh[j];
+          float dv = d[j] * act_grad(t, act);
+          a1[j] += dv;
+          a2[j] = fmaf(dv, xh, a2[j]);
+          a3[j] += xh;
+        }
+      }
+    }
+    if (mp.cv_blocks == 1) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int idx = row * C + c + j;
+          sc1[idx] = a1[j]; sc2[idx] = a2[j]; sc3[idx] = a3[j];
+        }
+      }
+      __syncthreads();
+      for (int cc = tid; cc < C; cc += GN_THREADS) {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        for (int r = 0; r < mp.rows_per_pass; ++r) {
+          t1 += sc1[r * C + cc]; t2 += sc2[r * C + cc]; t3 += sc3[r * C + cc];
+        }
+        out[cc * 3] = t1; out[cc * 3 + 1] = t2; out[cc * 3 + 2] = t3;
+      }
+    } else if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        out[(c + j) * 3] = a1[j]; out[(c + j) * 3 + 1] = a2[j]; out[(c + j) * 3 + 2] = a3[j];
+      }
+    }
+  }
+}
+
+// one CTA per sample n: reduce chunk partials -> S[n][c][3], group means, per-sample param grads
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const float* __restrict__ partial, int chunks, int C, int G,
+                                                                   int64_t S, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const float* __restrict__ scale,
+                                                                   int film_stride, const float* __restrict__ stats,
+                                                                   float* __restrict__ sums /*[N][C][3]*/,
+                                                                   float* __restrict__ gmean /*[N][G][2]*/,
+                                                                   float* __restrict__ dscale, float* __restrict__ dshift,
+                                                                   int dfilm_stride, float* __restrict__ dpre_add) {
+  const int n = blockIdx.x;
+  __shared__ float g1[GN_MAX_C], g2[GN_MAX_C];
+  __shared__ float m1s[64], m2s[64];
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* o = partial + (((int64_t)n * chunks + k) * C + c) * 3;
+      t1 += o[0]; t2 += o[1]; t3 += o[2];
+    }
+    float* so = sums + ((int64_t)n * C + c) * 3;
+    so[0] = t1; so[1] = t2; so[2] = t3;
+    float sc = scale ? scale[(int64_t)n * film_stride + c] : 0.f;
+    float A = gamma[c] * (1.f + sc);
+    g1[c] = A * t1;
+    g2[c] = A * t2;
+    if (dshift) dshift[(int64_t)n * dfilm_stride + c] = t1;
+    if (dscale) dscale[(int64_t)n * dfilm_stride + c] = gamma[c] * t2 + beta[c] * t1;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < cpg; ++j) { t1 += g1[g * cpg + j]; t2 += g2[g * cpg + j]; }
+    float inv = 1.f / ((float)cpg * (float)S);
+    m1s[g] = t1 * inv; m2s[g] = t2 * inv;
+    gmean[((int64_t)n * G + g) * 2] = t1 * inv;
+    gmean[((int64_t)n * G + g) * 2 + 1] = t2 * inv;
+  }
+  __syncthreads();
+  if (dpre_add) {
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+      int g = c / cpg;
+      float rstd = stats[((int64_t)n * G + g) * 2 + 1];
+      const float* so = sums + ((int64_t)n * C + c) * 3;
+      dpre_add[(int64_t)n * C + c] = rstd * (g1[c] - (float)S * m1s[g] - m2s[g] * so[2]);
+    }
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const float* __restrict__ sums, int N, int C, const float* __restrict__ scale, int film_stride,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float dg = 0.f, db = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float sc = scale ? scale[(int64_t)n * film_stride + c] : 0.f;
+    const float* so = sums + ((int64_t)n * C + c) * 3;
+    dg += (1.f + sc) * so[1];
+    db += (1.f + sc) * so[0];
+  }
+  if (dgamma) dgamma[c] = dg;
+  if (dbeta) dbeta[c] = db;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_pass2_kernel(const TI* __restrict__ x, const TI* __restrict__ x2,
+                                                                  const TO* __restrict__ dy, const float* __restrict__ pre_add,
+                                                                  int pre_stride, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int film_stride,
+                                                                  const float* __restrict__ stats, const float* __restrict__ gmean,
+                                                                  int C1, int C2, int64_t S, int G, int chunks, int act,
+                                                                  TI* __restrict__ dx, TI* __restrict__ dx2) {
+  const int C = C1 + C2;
+  const GnMap mp = gn_map(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per;
+  const int64_t p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const TI* xb = x + (int64_t)n * S * C1;
+  const TI* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+  const TO* dyb = dy + (int64_t)n * S * C;
+  TI* dxb = dx + (int64_t)n * S * C1;
+  TI* dx2b = dx2 ? dx2 + (int64_t)n * S * C2 : nullptr;
+  const bool film = scale != nullptr;
+  const int cpg = C / G;
+
+  for (int cvb = 0; cvb < mp.cv_blocks; ++cvb) {
+    int row, cv;
+    bool active;
+    if (mp.cv_blocks == 1) {
+      row = tid / mp.CV; cv = tid % mp.CV; active = row < mp.rows_per_pass;
+    } else {
+      row = 0; cv = cvb * GN_THREADS + tid; active = cv < mp.CV;
+    }
+    if (!active) continue;
+    const int c = cv * 4;
+    GnCoef k;
+    gn_load_coef(k, n, c, C, G, stats, gamma, beta, pre_add, pre_stride, scale, shift, film_stride);
+    float m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int g = (c + j) / cpg;
+      m1[j] = gmean[((int64_t)n * G + g) * 2];
+      m2[j] = gmean[((int64_t)n * G + g) * 2 + 1];
+    }
+    for (int64_t p = p0 + row; p < p1; p += mp.rows_per_pass) {
+      float v[4], d[4], o[4];
+      gn_load(xb, x2b, C1, C2, p, c, v);
+      load4(dyb + p * C + c, d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float xh = ((v[j] + k.pa[j]) - k.mean[j]) * k.rstd[j];
+        float t = xh * k.gamma[j] + k.beta[j];
+        float f = 1.f;
+        if (film) { f = 1.f + k.sc[j]; t = t * f + k.sh[j]; }
+        float dv = d[j] * act_grad(t, act);
+        o[j] = k.rstd[j] * (k.gamma[j] * f * dv - m1[j] - xh * m2[j]);
+      }
+      if (c < C1) store4(dxb + p * C1 + c, o);
+      else store4(dx2b + p * C2 + (c - C1), o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int gn_chunks(int N, int64_t S, int C) {
+  GnMap mp = gn_map(C);
+  int64_t target = (int64_t)sm_count() * 4;
+  int64_t chunks = ceil_div(target, N);
+  int64_t max_chunks = ceil_div(S, (int64_t)mp.rows_per_pass * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 4096) chunks = 4096;
+  return (int)chunks;
+}
+
+static int gn_validate(const rho_gn_params* p, const char* who) {
+  RHO_REQUIRE(p, "%s: null params", who);
+  RHO_REQUIRE(p->N > 0 && p->S > 0 && p->C1 > 0 && p->C2 >= 0, "%s: bad dims", who);
+  const int C = p->C1 + p->C2;
+  RHO_REQUIRE(p->groups > 0 && p->groups <= 64 && C % p->groups == 0, "%s: C=%d not divisible by groups=%d", who, C, p->groups);
+  RHO_REQUIRE(C % 4 == 0 && p->C1 % 4 == 0, "%s: channel counts must be multiples of 4 (C1=%d C2=%d)", who, p->C1, p->C2);
+  RHO_REQUIRE(C <= GN_MAX_C, "%s: C=%d exceeds %d", who, C, GN_MAX_C);
+  RHO_REQUIRE(p->x && p->stats, "%s: null tensor", who);
+  RHO_REQUIRE((p->C2 == 0) == (p->x2 == nullptr), "%s: x2/C2 mismatch", who);
+  RHO_REQUIRE(p->N <= 65535, "%s: N too large", who);
+  return RHO_OK;
+}
+
+}  // namespace rho
+
+using namespace rho;
+
+extern "C" {
+
+size_t rho_gn_workspace_bytes(const rho_gn_params* p) {
+  if (!p) return 0;
+  int chunks = gn_chunks(p->N, p->S, p->C1 + p->C2);
+  return (size_t)p->N * chunks * p->groups * 3 * sizeof(float);
+}
+
+int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream) {
+  int rc = gn_validate(p, "gn_stats");
+  if (rc) return rc;
+  const int C = p->C1 + p->C2;
+  int chunks = gn_chunks(p->N, p->S, C);
+  size_t need = (size_t)p->N * chunks * p->groups * 3 * sizeof(float);
+  if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "gn_stats: workspace %zu < %zu", p->workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(chunks, p->N);
+  float* partial = (float*)p->workspace;
+  if (p->in_dtype == RHO_F32)
+    gn_stats_kernel<float><<<grid, GN_THREADS, 0, st>>>((const float*)p->x, (const float*)p->x2, p->pre_add, p->pre_add_stride, p->C1,
+                                                         p->C2, p->S, p->groups, chunks, partial);
+  else if (p->in_dtype == RHO_BF16)
+    gn_stats_kernel<bf16><<<grid, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->C1,
+                                                        p->C2, p->S, p->groups, chunks, partial);
+  else
+    return fail(RHO_ERR_INVALID_ARG, "gn_stats: bad dtype");
+  RHO_CHECK_LAUNCH("gn_stats");
+  int NG = p->N * p->groups;
+  gn_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, st>>>(partial, NG, p->groups, chunks, p->eps, p->stats);
+  RHO_CHECK_LAUNCH("gn_stats_finalize");
+  return RHO_OK;
+}
+
+int rho_gn_apply(const rho_gn_params* p, rho_stream_t stream) {
+  int rc = gn_validate(p, "gn_apply");
+  if (rc) return rc;
+  RHO_REQUIRE(p->y && p->gamma && p->beta, "gn_apply: null tensor");
+  RHO_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "gn_apply: scale/shift must both be set");
+  const int C = p->C1 + p->C2;
+  int chunks = gn_chunks(p->N, p->S, C);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(chunks, p->N);
+#define RHO_GNA(TI, TO)                                                                                                        \
+  gn_apply_kernel<TI, TO><<<grid, GN_THREADS, 0, st>>>((const TI*)p->x, (const TI*)p->x2, p->pre_add, p->pre_add_stride, p->gamma, \
+                                                       p->beta, p->scale, p->shift, p->film_stride, p->stats, p->C1, p->C2, p->S,  \
+                                                       p->groups, chunks, p->act, (TO*)p->y)
+  if (p->in_dtype == RHO_F32 && p->out_dtype == RHO_F32) RHO_GNA(float, float);
+  else if (p->in_dtype == RHO_F32 && p->out_dtype == RHO_BF16) RHO_GNA(float, bf16);
+  else if (p->in_dtype == RHO_BF16 && p->out_dtype == RHO_BF16) RHO_GNA(bf16, bf16);
+  else if (p->in_dtype == RHO_BF16 && p->out_dtype == RHO_F32) RHO_GNA(bf16, float);
+  else return fail(RHO_ERR_INVALID_ARG, "gn_apply: bad dtype");
+#undef RHO_GNA
+  RHO_CHECK_LAUNCH("gn_apply");
+  return RHO_OK;
+}
+
+size_t rho_gn_bwd_workspace_bytes(const rho_gn_bwd_params* p) {
+  if (!p) return 0;
+  const rho_gn_params& f = p->fwd;
+  const int C = f.C1 + f.C2;
+  int chunks = gn_chunks(f.N, f.S, C);
+  size_t partial = (size_t)f.N * chunks * C * 3;
+  size_t sums = (size_t)f.N * C * 3;
+  size_t gmean = (size_t)f.N * f.groups * 2;
+  return (partial + sums + gmean) * sizeof(float);
+}
+
+int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
+  RHO_REQUIRE(p, "gn_bwd: null params");
+  const rho_gn_params& f = p->fwd;
+  int rc = gn_validate(&f, "gn_bwd");
+  if (rc) return rc;
+  RHO_REQUIRE(p->dy && p->dx && f.gamma && f.beta, "gn_bwd: null tensor");
+  RHO_REQUIRE((f.C2 == 0) || p->dx2, "gn_bwd: dx2 required for concat input");
+  const int C = f.C1 + f.C2;
+  int chunks = gn_chunks(f.N, f.S, C);
+  size_t need = rho_gn_bwd_workspace_bytes(p);
+  if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "gn_bwd: workspace %zu < %zu", p->workspace_bytes, need);
+  float* partial = (float*)p->workspace;
+  float* sums = partial + (size_t)f.N * chunks * C * 3;
+  float* gmean = sums + (size_t)f.N * C * 3;
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(chunks, f.N);
+#define RHO_GNB1(TI, TO)                                                                                                          \
+  gn_bwd_pass1_kernel<TI, TO><<<grid, GN_THREADS, 0, st>>>((const TI*)f.x, (const TI*)f.x2, (const TO*)p->dy, f.pre_add,           \
+                                                           f.pre_add_stride, f.gamma, f.beta, f.scale, f.shift, f.film_stride,    \
+                                                           f.stats, f.C1, f.C2, f.S, f.groups, chunks, f.act, partial)
+#define RHO_GNB2(TI, TO)                                                                                                          \
+  gn_bwd_pass2_kernel<TI, TO><<<grid, GN_THREADS, 0, st>>>((const TI*)f.x, (const TI*)f.x2, (const TO*)p->dy, f.pre_add,           \
+                                                           f.pre_add_stride, f.gamma, f.beta, f.scale, f.shift, f.film_stride,    \
+                                                           f.stats, gmean, f.C1, f.C2, f.S, f.groups, chunks, f.act, (TI*)p->dx,   \
+                                                           (TI*)p->dx2)
+  const int key = f.in_dtype * 2 + f.out_dtype;
+  switch (key) {
+    case 0: RHO_GNB1(float, float); break;
+    case 1: RHO_GNB1(float, bf16); break;
+    case 2: RHO_GNB1(bf16, float); break;
+    case 3: RHO_GNB1(bf16, bf16); break;
+    default: return fail(RHO_ERR_INVALID_ARG, "gn_bwd: bad dtype");
+  }
+  RHO_CHECK_LAUNCH("gn_bwd_pass1");
+  gn_bwd_reduce_kernel<<<f.N, GN_THREADS, 0, st>>>(partial, chunks, C, f.groups, f.S, f.gamma, f.beta, f.scale, f.film_stride, f.stats,
+                                                   sums, gmean, p->dscale, p->dshift, p->dfilm_stride, p->dpre_add);
+  RHO_CHECK_LAUNCH("gn_bwd_reduce");
+  if (p->dgamma || p->dbeta) {
+    gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, f.N, C, f.scale, f.film_stride, p->dgamma, p->dbeta);
+    RHO_CHECK_LAUNCH("gn_bwd_param");
+  }
+  switch (key) {
+    case 0: RHO_GNB2(float, float); break;
+    case 1: RHO_GNB2(float, bf16); break;
+    case 2: RHO_GNB2(bf16, float); break;
+    case 3: RHO_GNB2(bf16, bf16); break;
+  }
+  RHO_CHECK_LAUNCH("gn_bwd_pass2");
+#undef RHO_GNB1
+#undef RHO_GNB2
+  return RHO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,565 @@
+"""Host-side wrappers of the C ABI (``include/rho_b200.h``): tensor plumbing + autograd glue.
+
+PyTorch is used here for device memory, streams and the autograd tape only; every arithmetic
+operation is a kernel of librho_b200.so.  Activations inside the model are **channels-last**
+tensors of shape ``(N, *spatial, C)`` (contiguous); the reference's ``(N, C, *spatial)`` layout only
+exists at the UNet boundary (:func:`nc_to_cl` / :func:`cl_to_nc`).
+
+There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+F32, BF16 = L.F32, L.BF16
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_ACT_BY_NAME = {
+    None: L.ACT_NONE, "Identity": L.ACT_NONE, "SiLU": L.ACT_SILU, "ReLU": L.ACT_RELU, "Tanh": L.ACT_TANH,
+    "Sigmoid": L.ACT_SIGMOID, "GELU": L.ACT_GELU,
+}
+
+
+def act_code(act) -> int:
+    """Maps a registry activation (``nn.SiLU()`` instance, class or name) to the kernel enum."""
+    if act is None or isinstance(act, int):
+        return L.ACT_NONE if act is None else act
+    name = act if isinstance(act, str) else (act.__name__ if isinstance(act, type) else type(act).__name__)
+    if name not in _ACT_BY_NAME:
+        raise L.RhoB200Error(f"activation {name!r} has no fused B200 kernel (supported: SiLU, ReLU, Tanh, Sigmoid, GELU)")
+    if name == "GELU" and getattr(act, "approximate", "none") != "none":
+        raise L.RhoB200Error("GELU(approximate='tanh') is not supported")
+    return _ACT_BY_NAME[name]
+
+
+def dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise L.RhoB200Error(f"unsupported dtype {t.dtype}; the B200 path computes in float32 or bfloat16") from None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.RhoB200Error("rho_diffusion (B200) has no CPU path: tensors must be on a CUDA device")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-device scratch buffer, grown on demand (stream-ordered reuse)."""
+    key = (device.index, torch.cuda.is_current_stream_capturing())
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------------
+def nc_to_cl(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """(N, C, *sp) -> channels-last (N, *sp, C) in ``out_dtype``."""
+    _need_cuda(x)
+    x = x.contiguous()
+    N, Cc, *sp = x.shape
+    S = 1
+    for s in sp:
+        S *= s
+    y = torch.empty((N, *sp, Cc), dtype=out_dtype, device=x.device)
+    L.check(L.lib().rho_nc_to_cl(x.data_ptr(), dt(x), y.data_ptr(), dt(y), N, Cc, S, stream()), "nc_to_cl")
+    return y
+
+
+def cl_to_nc(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    N, *sp, Cc = x.shape
+    S = 1
+    for s in sp:
+        S *= s
+    y = torch.empty((N, Cc, *sp), dtype=out_dtype, device=x.device)
+    L.check(L.lib().rho_cl_to_nc(x.data_ptr(), dt(x), y.data_ptr(), dt(y), N, Cc, S, stream()), "cl_to_nc")
+    return y
+
+
+class _LayoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, to_cl, out_dtype):
+        ctx.to_cl, ctx.in_dtype = to_cl, x.dtype
+        return nc_to_cl(x, out_dtype) if to_cl else cl_to_nc(x, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (cl_to_nc(g, ctx.in_dtype) if ctx.to_cl else nc_to_cl(g, ctx.in_dtype)), None, None
+
+
+def to_channels_last(x, out_dtype):
+    return _LayoutFn.apply(x, True, out_dtype)
+
+
+def to_channels_first(x, out_dtype):
+    return _LayoutFn.apply(x, False, out_dtype)
+
+
+def _pad3(t) -> Tuple[int, int, int]:
+    t = tuple(int(v) for v in t)
+    return (1,) * (3 - len(t)) + t
+
+
+# ------------------------------------------------------------------------------------------------
+# conv_nd
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvSpec:
+    """Geometry of one conv_nd call site (kernel, stride and fused-upsample factors per spatial dim)."""
+    dims: int
+    kernel: Tuple[int, ...]
+    stride: Tuple[int, ...]
+    up: Tuple[int, ...]
+
+    @staticmethod
+    def make(dims, kernel=3, stride=1, up=1):
+        def tup(v):
+            return tuple(v) if isinstance(v, (tuple, list)) else (v,) * dims
+        return ConvSpec(dims, tup(kernel), tup(stride), tup(up))
+
+
+_weights_epoch = 0
+_pack_cache = {}
+
+
+def bump_weights_epoch():
+    """Called by the fused optimizer after it has rewritten parameter memory behind autograd's back."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def packed_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[Cout, Cin, *k] fp32 (state-dict layout) -> [Cout, taps, Cin] in ``dtype``; cached per parameter version."""
+    key = (weight.data_ptr(), dtype)
+    ver = (weight._version, _weights_epoch, tuple(weight.shape))
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (Cout * Cin)
+    out = hit[1] if (hit is not None and hit[1].shape == (Cout, taps, Cin)) else torch.empty(
+        (Cout, taps, Cin), dtype=dtype, device=w.device)
+    L.check(L.lib().rho_conv_pack_weight(w.data_ptr(), out.data_ptr(), _DT[dtype], Cout, Cin, taps, stream()), "conv_pack_weight")
+    _pack_cache[key] = (ver, out)
+    return out
+
+
+def _conv_params(x, x2, wp, bias, residual, y, spec: ConvSpec, Cout, engine, y_f32) -> L.ConvParams:
+    N = x.shape[0]
+    D, H, W = _pad3(x.shape[1:-1])
+    kd, kh, kw = _pad3(spec.kernel)
+    sd, sh, sw = _pad3(spec.stride)
+    ud, uh, uw = _pad3(spec.up)
+    p = L.ConvParams()
+    p.N, p.D, p.H, p.W = N, D, H, W
+    p.C1, p.C2, p.Cout = x.shape[-1], (x2.shape[-1] if x2 is not None else 0), Cout
+    p.kd, p.kh, p.kw, p.sd, p.sh, p.sw, p.ud, p.uh, p.uw = kd, kh, kw, sd, sh, sw, ud, uh, uw
+    p.act_dtype, p.w_dtype, p.engine, p.y_f32 = dt(x), dt(wp), engine, int(y_f32)
+    p.x, p.x2, p.w_packed = ptr(x), ptr(x2), ptr(wp)
+    p.bias, p.residual, p.y = ptr(bias), ptr(residual), ptr(y)
+    return p
+
+
+def conv_out_shape(x_shape, spec: ConvSpec, Cout):
+    sp = x_shape[1:-1]
+    out = []
+    for s, k, st, u in zip(sp, spec.kernel, spec.stride, spec.up):
+        out.append((s * u + 2 * (k // 2) - k) // st + 1)
+    return (x_shape[0], *out, Cout)
+
+
+def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False):
+    _need_cuda(x, x2, wp, bias, residual)
+    assert x.is_contiguous() and (x2 is None or x2.is_contiguous()) and (residual is None or residual.is_contiguous())
+    out_dtype = torch.float32 if y_f32 else x.dtype
+    y = torch.empty(conv_out_shape(x.shape, spec, Cout), dtype=out_dtype, device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.dtype == x.dtype
+    p = _conv_params(x, x2, wp, bias, residual, y, spec, Cout, engine, y_f32)
+    L.check(L.lib().rho_conv_fwd(C.byref(p), stream()), "conv_fwd")
+    return y
+
+
+def conv_backward(x, x2, wp, dy, spec: ConvSpec, Cout, need_dx, need_dw, need_db, w_shape, engine=L.CONV_AUTO):
+    dy = dy.contiguous()
+    bp = L.ConvBwdParams()
+    bp.fwd = _conv_params(x, x2, wp, None, None, None, spec, Cout, engine, False)
+    bp.dy = ptr(dy)
+    nbytes = L.lib().rho_conv_bwd_workspace_bytes(C.byref(bp))
+    ws = workspace(nbytes, x.device)
+    bp.workspace, bp.workspace_bytes = ws.data_ptr(), ws.numel()
+    dx = dx2 = dw = db = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        dx2 = torch.empty_like(x2) if x2 is not None else None
+        bp.dx, bp.dx2 = ptr(dx), ptr(dx2)
+        L.check(L.lib().rho_conv_dgrad(C.byref(bp), stream()), "conv_dgrad")
+    if need_dw or need_db:
+        if need_dw:
+            dw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+        if need_db:
+            db = torch.empty((Cout,), dtype=torch.float32, device=x.device)
+        bp.dw, bp.dbias = ptr(dw), ptr(db)
+        L.check(L.lib().rho_conv_wgrad(C.byref(bp), stream()), "conv_wgrad")
+    return dx, dx2, dw, db
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv_nd(cat(x, x2)) + bias (+ residual); see rho_conv_fwd in include/rho_b200.h."""
+
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, residual, spec, compute_dtype, engine, y_f32):
+        wp = packed_weight(weight, compute_dtype)
+        Cout = weight.shape[0]
+        b = bias.detach().float() if bias is not None else None
+        y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32)
+        ctx.save_for_backward(x, x2, weight)
+        ctx.spec, ctx.compute_dtype, ctx.engine, ctx.has_bias, ctx.has_res = spec, compute_dtype, engine, bias is not None, residual is not None
+        ctx.y_f32 = y_f32
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, weight = ctx.saved_tensors
+        if dy.dtype != x.dtype:  # y_f32 head: gradient arrives in fp32
+            dy = cast(dy, x.dtype)
+        wp = packed_weight(weight, ctx.compute_dtype)
+        need_dx = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
+        dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, weight.shape[0], need_dx, ctx.needs_input_grad[2],
+                                        ctx.has_bias and ctx.needs_input_grad[3], tuple(weight.shape), ctx.engine)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        return dx, dx2, dw, db, dres, None, None, None, None
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dtype conversion (optionally fused with an elementwise add)."""
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    if add is not None:
+        add = add.contiguous()
+    L.check(L.lib().rho_add_cast(x.data_ptr(), dt(x), ptr(add), dt(add) if add is not None else 0, y.data_ptr(), dt(y), x.numel(),
+                                 stream()), "add_cast")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm32 (+FiLM / embedding add) + activation
+# ------------------------------------------------------------------------------------------------
+def _gn_params(x, x2, gamma, beta, film, pre_add, act, stats, y, groups, eps) -> L.GnParams:
+    p = L.GnParams()
+    N = x.shape[0]
+    S = 1
+    for s in x.shape[1:-1]:
+        S *= s
+    C1, C2 = x.shape[-1], (x2.shape[-1] if x2 is not None else 0)
+    Ct = C1 + C2
+    p.N, p.S, p.C1, p.C2, p.groups = N, S, C1, C2, groups
+    p.in_dtype, p.out_dtype, p.act, p.eps = dt(x), (dt(y) if y is not None else dt(x)), act, eps
+    p.x, p.x2 = ptr(x), ptr(x2)
+    if pre_add is not None:
+        p.pre_add, p.pre_add_stride = pre_add.data_ptr(), pre_add.stride(0)
+    p.gamma, p.beta = ptr(gamma), ptr(beta)
+    if film is not None:  # [N, 2C]: scale = [:, :C], shift = [:, C:]
+        p.scale = film.data_ptr()
+        p.shift = film.data_ptr() + Ct * 4
+        p.film_stride = film.stride(0)
+    p.stats, p.y = ptr(stats), ptr(y)
+    return p
+
+
+def gn_forward(x, x2, gamma, beta, film, pre_add, act, out_dtype, groups=32, eps=1e-5):
+    _need_cuda(x, x2, gamma, beta, film, pre_add)
+    assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
+    for t in (film, pre_add):
+        assert t is None or (t.dtype == torch.float32 and t.stride(-1) == 1)
+    N = x.shape[0]
+    Ct = x.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+    stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    y = torch.empty((*x.shape[:-1], Ct), dtype=out_dtype, device=x.device)
+    p = _gn_params(x, x2, gamma, beta, film, pre_add, act, stats, y, groups, eps)
+    ws = workspace(L.lib().rho_gn_workspace_bytes(C.byref(p)), x.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    L.check(L.lib().rho_gn_stats(C.byref(p), stream()), "gn_stats")
+    L.check(L.lib().rho_gn_apply(C.byref(p), stream()), "gn_apply")
+    return y, stats
+
+
+class GnActFn(torch.autograd.Function):
+    """act(FiLM(GroupNorm32(cat(x, x2) + pre_add))); see rho_gn_* in include/rho_b200.h."""
+
+    @staticmethod
+    def forward(ctx, x, x2, gamma, beta, film, pre_add, act, out_dtype, groups, eps):
+        g32, b32 = gamma.detach().float(), beta.detach().float()
+        y, stats = gn_forward(x, x2, g32, b32, film, pre_add, act, out_dtype, groups, eps)
+        ctx.save_for_backward(x, x2, g32, b32, film, pre_add, stats)
+        ctx.act, ctx.groups, ctx.eps = act, groups, eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, gamma, beta, film, pre_add, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        Ct = gamma.numel()
+        bp = L.GnBwdParams()
+        bp.fwd = _gn_params(x, x2, gamma, beta, film, pre_add, ctx.act, stats, None, ctx.groups, ctx.eps)
+        bp.fwd.out_dtype = dt(dy)
+        dx = torch.empty_like(x)
+        dx2 = torch.empty_like(x2) if x2 is not None else None
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
+        dfilm = torch.empty_like(film) if film is not None else None
+        dpre = torch.empty((x.shape[0], Ct), dtype=torch.float32, device=x.device) if pre_add is not None else None
+        bp.dy, bp.dx, bp.dx2, bp.dgamma, bp.dbeta = ptr(dy), ptr(dx), ptr(dx2), ptr(dgamma), ptr(dbeta)
+        if dfilm is not None:
+            bp.dscale = dfilm.data_ptr()
+            bp.dshift = dfilm.data_ptr() + Ct * 4
+            bp.dfilm_stride = dfilm.stride(0)
+        bp.dpre_add = ptr(dpre)
+        ws = workspace(L.lib().rho_gn_bwd_workspace_bytes(C.byref(bp)), x.device)
+        bp.workspace, bp.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(L.lib().rho_gn_bwd(C.byref(bp), stream()), "gn_bwd")
+        return dx, dx2, dgamma, dbeta, dfilm, dpre, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """QKVAttention[Legacy] on channels-last qkv [N, T, 3*heads*ch]; see rho_attention_fwd."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, order):
+        _need_cuda(qkv)
+        qkv = qkv.contiguous()
+        N, T, W3 = qkv.shape
+        ch = W3 // (3 * heads)
+        out = torch.empty((N, T, heads * ch), dtype=qkv.dtype, device=qkv.device)
+        need_lse = qkv.requires_grad
+        lse = torch.empty((N, heads, T), dtype=torch.float32, device=qkv.device) if need_lse else None
+        p = L.AttnParams()
+        p.N, p.T, p.heads, p.ch, p.order, p.dtype = N, T, heads, ch, order, dt(qkv)
+        p.qkv, p.out, p.lse = ptr(qkv), ptr(out), ptr(lse)
+        L.check(L.lib().rho_attention_fwd(C.byref(p), stream()), "attention_fwd")
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.dims = (N, T, heads, ch, order)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        N, T, heads, ch, order = ctx.dims
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        bp = L.AttnBwdParams()
+        f = bp.fwd
+        f.N, f.T, f.heads, f.ch, f.order, f.dtype = N, T, heads, ch, order, dt(qkv)
+        f.qkv, f.out, f.lse = ptr(qkv), ptr(out), ptr(lse)
+        bp.dout, bp.dqkv = ptr(dout), ptr(dqkv)
+        ws = workspace(L.lib().rho_attention_bwd_workspace_bytes(C.byref(bp)), qkv.device)
+        bp.workspace, bp.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(L.lib().rho_attention_bwd(C.byref(bp), stream()), "attention_bwd")
+        return dqkv, None, None
+
+
+def attention(qkv, heads, order):
+    return AttentionFn.apply(qkv, heads, order)
+
+
+# ------------------------------------------------------------------------------------------------
+# embedding path (fp32)
+# ------------------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, dim: int, omega: torch.Tensor) -> torch.Tensor:
+    _need_cuda(t, omega)
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    L.check(L.lib().rho_timestep_embedding(t.data_ptr(), t.shape[0], dim, omega.data_ptr(), out.data_ptr(), stream()),
+            "timestep_embedding")
+    return out
+
+
+def _linear_params(x, w, b, add, y, act_in) -> L.LinearParams:
+    p = L.LinearParams()
+    p.B, p.I, p.O, p.act_in = x.shape[0], x.shape[1], w.shape[0], act_in
+    p.x, p.x_stride, p.w, p.b = x.data_ptr(), x.stride(0), w.data_ptr(), ptr(b)
+    if add is not None:
+        p.add, p.add_stride = add.data_ptr(), add.stride(0)
+    if y is not None:
+        p.y, p.y_stride = y.data_ptr(), y.stride(0)
+    return p
+
+
+class LinearFn(torch.autograd.Function):
+    """y = W act_in(x) + b (+ add); nn.Linear of time_embed / emb_layers with the activation fused."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, add, act_in):
+        _need_cuda(x, weight)
+        x = x.float().contiguous()
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        a = add.float().contiguous() if add is not None else None
+        y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+        p = _linear_params(x, w, b, a, y, act_in)
+        L.check(L.lib().rho_linear_fwd(C.byref(p), stream()), "linear_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.act_in, ctx.has_bias, ctx.has_add = act_in, bias is not None, add is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        p = _linear_params(x, w, None, None, None, ctx.act_in)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.empty((w.shape[0],), dtype=torch.float32, device=x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        L.check(L.lib().rho_linear_bwd(C.byref(p), dy.data_ptr(), dy.stride(0), ptr(dx), dx.stride(0) if dx is not None else 0,
+                                       ptr(dw), ptr(db), stream()), "linear_bwd")
+        dadd = dy if (ctx.has_add and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dadd, None
+
+
+def linear(x, weight, bias=None, add=None, act_in=L.ACT_NONE):
+    return LinearFn.apply(x, weight, bias, add, act_in)
+
+
+class EmbeddingMatchFn(torch.autograd.Function):
+    """sum_i table_i[index of y[:, i] in values_i] (MultiEmbeddings.forward, models/conditioning.py:115-139)."""
+
+    @staticmethod
+    def forward(ctx, y, values_list, *tables):
+        _need_cuda(y, *tables)
+        y = y.float()
+        if y.dim() == 1:
+            y = y[:, None].expand(-1, len(tables))
+        y = y.contiguous()
+        B, dim = y.shape[0], tables[0].shape[1]
+        out = torch.empty((B, dim), dtype=torch.float32, device=y.device)
+        idxs = torch.empty((len(tables), B), dtype=torch.int32, device=y.device)
+        for i, (vals, tab) in enumerate(zip(values_list, tables)):
+            tab32 = tab.detach().float().contiguous()
+            L.check(L.lib().rho_embedding_match(y.data_ptr() + 4 * i, y.stride(0), B, vals.data_ptr(), vals.numel(), tab32.data_ptr(), dim,
+                                                out.data_ptr(), int(i > 0), idxs[i].data_ptr(), stream()), "embedding_match")
+        ctx.save_for_backward(idxs)
+        ctx.shapes = [tuple(t.shape) for t in tables]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idxs,) = ctx.saved_tensors
+        dout = dout.float().contiguous()
+        grads = []
+        for i, shp in enumerate(ctx.shapes):
+            if not ctx.needs_input_grad[2 + i]:
+                grads.append(None)
+                continue
+            g = torch.zeros(shp, dtype=torch.float32, device=dout.device)
+            L.check(L.lib().rho_embedding_match_bwd(idxs[i].data_ptr(), dout.shape[0], dout.data_ptr(), shp[1], g.data_ptr(), shp[0],
+                                                    stream()), "embedding_match_bwd")
+            grads.append(g)
+        return (None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# diffusion math
+# ------------------------------------------------------------------------------------------------
+def randn(shape, device, seed: int, offset: int = 0) -> torch.Tensor:
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    L.check(L.lib().rho_randn(out.data_ptr(), out.numel(), seed, offset, stream()), "randn")
+    return out
+
+
+def q_sample(x0, noise, t, alpha_bar):
+    _need_cuda(x0, noise, t, alpha_bar)
+    x0 = x0.float().contiguous()
+    noise = noise.float().contiguous()
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty_like(x0)
+    N = x0.shape[0]
+    L.check(L.lib().rho_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), alpha_bar.data_ptr(), alpha_bar.numel(), N,
+                                 x0.numel() // N, out.data_ptr(), stream()), "q_sample")
+    return out
+
+
+def p_sample_step(x, eps, z, t_scalar, alpha, beta, alpha_bar, noise_scale=0.8, clamp=(-1.0, 1.0), seed=0):
+    """In-place ancestral update of ``x`` (fp32); ``t_scalar`` is a 1-element int64 device tensor."""
+    p = L.PSampleParams()
+    p.x, p.eps, p.z, p.t = x.data_ptr(), eps.data_ptr(), ptr(z), t_scalar.data_ptr()
+    p.alpha, p.beta, p.alpha_bar, p.T = alpha.data_ptr(), beta.data_ptr(), alpha_bar.data_ptr(), alpha_bar.numel()
+    p.n, p.noise_scale, p.clamp_lo, p.clamp_hi, p.seed = x.numel(), noise_scale, clamp[0], clamp[1], seed
+    L.check(L.lib().rho_p_sample_step(C.byref(p), stream()), "p_sample_step")
+
+
+def advance_timestep(t_scalar, t_vec):
+    L.check(L.lib().rho_advance_timestep(t_scalar.data_ptr(), t_vec.data_ptr(), t_vec.numel(), stream()), "advance_timestep")
+
+
+class MseLossFn(torch.autograd.Function):
+    """nn.MSELoss(pred, target) (ddpm.py:280); the gradient is produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        _need_cuda(pred, target)
+        pred = pred.contiguous()
+        target = target.float().contiguous()
+        n = pred.numel()
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred) if pred.requires_grad else None
+        ws = workspace(L.lib().rho_mse_workspace_bytes(n), pred.device)
+        L.check(L.lib().rho_mse_loss(pred.data_ptr(), dt(pred), target.data_ptr(), n, loss.data_ptr(), ptr(dpred), 1.0, ws.data_ptr(),
+                                     ws.numel(), stream()), "mse_loss")
+        ctx.dpred = dpred
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        g = ctx.dpred
+        ctx.dpred = None
+        if g is None:
+            return None, None
+        # upstream scale (1.0 for loss.backward()) is applied on the device: no host sync
+        dloss = dloss.float().contiguous()
+        L.check(L.lib().rho_scale(g.data_ptr(), dt(g), g.numel(), dloss.data_ptr(), 1.0, stream()), "scale")
+        return g, None
+
+
+def adamw_ema_step(p, g, m, v, shadow, step, lr, betas, eps, weight_decay, ema_decay_t=0.0, grad_scale=1.0):
+    a = L.AdamWParams()
+    a.p, a.g, a.m, a.v, a.shadow, a.n = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ptr(shadow), p.numel()
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, betas[0], betas[1], eps, weight_decay
+    a.step, a.ema_decay_t, a.grad_scale = step, ema_decay_t, grad_scale
+    L.check(L.lib().rho_adamw_ema_step(C.byref(a), stream()), "adamw_ema_step")
+    bump_weights_epoch()
+
+
+def ema_update(shadow: torch.Tensor, p: torch.Tensor, one_minus_decay: float) -> None:
+    """shadow -= one_minus_decay * (shadow - p), in place (ema.py:52-57)."""
+    _need_cuda(shadow, p)
+    assert shadow.is_contiguous() and p.is_contiguous() and shadow.dtype == torch.float32 and p.dtype == torch.float32
+    L.check(L.lib().rho_ema_update(shadow.data_ptr(), p.data_ptr(), shadow.numel(), one_minus_decay, stream()), "ema_update")

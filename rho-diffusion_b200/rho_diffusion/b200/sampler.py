@@ -1,0 +1,92 @@
+"""The ancestral sampling loop as a replayed CUDA graph (replaces the host-driven loop of ddpm.py:195-227).
+
+One graph = one UNet evaluation + the fused p_sample update (in-kernel Philox noise keyed by the step index) +
+the timestep decrement.  The step index and the (B,) timestep vector live in device memory and are advanced by
+a kernel inside the graph, so the same graph is replayed for every step; nothing is launched from Python in
+between and there is no host synchronisation inside the loop.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def shard_range(total: int, world: int, rank: int):
+    """Contiguous batch shard of rank ``rank`` (sampling shards the batch, no communication)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class AncestralSampler:
+    def __init__(self, backbone, shape, device, alpha, beta, alpha_bar, cond_example=None, use_cuda_graph=True,
+                 external_noise=False, noise_scale=0.8, clamp=(-1.0, 1.0)):
+        self.backbone = backbone
+        self.shape = tuple(shape)
+        self.device = device
+        self.alpha, self.beta, self.alpha_bar = alpha.contiguous(), beta.contiguous(), alpha_bar.contiguous()
+        self.T = int(alpha_bar.numel())
+        self.noise_scale, self.clamp = noise_scale, clamp
+        self.use_graph = bool(use_cuda_graph)
+        self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
+        self.tt = torch.zeros((self.shape[0],), dtype=torch.int64, device=device)
+        self.t_scalar = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.cond = cond_example.clone() if cond_example is not None else None
+        self.z = torch.zeros(self.shape, dtype=torch.float32, device=device) if external_noise else None
+        self.seed_holder = 0
+        self.graph = None
+        self._graph_seed = None
+
+    def _step(self, seed):
+        eps = self.backbone(self.x, self.tt, self.cond) if self.cond is not None else self.backbone(self.x, self.tt)
+        ops.p_sample_step(self.x, eps, self.z, self.t_scalar, self.alpha, self.beta, self.alpha_bar, self.noise_scale, self.clamp,
+                          seed)
+        ops.advance_timestep(self.t_scalar, self.tt)
+
+    def _capture(self, seed):
+        # warm-up on a side stream (packs weights, sets kernel attributes, sizes the workspace), then capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.t_scalar.fill_(1)
+            self.tt.fill_(1)
+            self._step(seed)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        self.t_scalar.fill_(1)
+        self.tt.fill_(1)
+        with torch.cuda.graph(g):
+            self._step(seed)
+        self.graph, self._graph_seed = g, seed
+
+    def run(self, x_init, cond=None, seed=0, noises=None, t_checkpoints=None, num_steps=None, progress=False):
+        T = self.T if num_steps is None else int(num_steps)
+        if self.use_graph and (self.graph is None or (self.z is None and self._graph_seed != seed)):
+            self._capture(seed)
+        self.x.copy_(x_init.reshape(self.shape).to(torch.float32))
+        if self.cond is not None:
+            self.cond.copy_(cond)
+        self.tt.fill_(T - 1)
+        self.t_scalar.fill_(T - 1)
+        buffer = None
+        n_ckpt = 0
+        if t_checkpoints is not None:
+            n_ckpt = len(t_checkpoints)
+            buffer = torch.zeros((self.shape[0], n_ckpt, *self.shape[1:]), dtype=torch.float32, device=self.device)
+        per_ckpt = max(T // 10, 1)
+        idx = 0
+        for t in range(T - 1, -1, -1):
+            if self.z is not None:
+                if t > 1:
+                    self.z.copy_(noises[t].to(self.device))
+                else:
+                    self.z.zero_()
+            if self.use_graph:
+                self.graph.replay()
+            else:
+                self._step(seed)
+            if buffer is not None and t % per_ckpt == 0 and idx < n_ckpt:
+                buffer[:, idx].copy_(self.x)
+                idx += 1
+        return {"buffer": buffer, "denoised": self.x.clone()}

@@ -1,0 +1,250 @@
+"""End-to-end parity of the CUDA path against golden outputs of the UNMODIFIED reference (tests/golden/, made by
+oracle/make_golden.py) and against the CPU oracle: full UNet forward (n = 1, 2, 3; all conditioning paths; both
+attention orders), DDPM training step (loss + gradients), AdamW / EMA, and the sampling trajectory with shared
+noise -- eager and through the replayed CUDA graph."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden  # noqa: E402
+from oracle import torch_oracle as O  # noqa: E402
+from oracle.cases import TIMESTEPS, UNET_CASES, cond_values  # noqa: E402
+from oracle.synth import synth_input, synth_state_dict  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def build(case, dtype=torch.float32):
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.models.conditioning import MultiEmbeddings
+    from rho_diffusion.models.unet_v2 import UNet
+    spec = UNET_CASES[case]
+    g = load_golden(f"unet_{case}.pt")
+    kwargs = dict(spec["kwargs"])
+    if spec["cond"] == "multi":
+        kwargs["cond_fn"] = MultiEmbeddings(parameter_space=OrderedDict(spec["parameter_space"]),
+                                            embedding_dim=4 * kwargs["model_channels"])
+    model = UNet(**kwargs)
+    model.load_state_dict(synth_state_dict(g["manifest"], seed=777), strict=True)   # reference checkpoint layout
+    model = set_compute_dtype(model.to(DEV).eval(), dtype)
+    x = synth_input(case + ".x", spec["x_shape"])
+    t = torch.tensor(TIMESTEPS[case], dtype=torch.long)
+    y = None
+    if spec["cond"] == "same_shape":
+        y = synth_input(case + ".y", (spec["x_shape"][0], 4 * kwargs["model_channels"]), kind="rand")
+    elif spec["cond"] == "multi":
+        y = torch.tensor(cond_values(case), dtype=torch.float32)
+    return model, g, x, t, y
+
+
+def nrm_err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return float((got - ref).norm() / ref.norm()), float((got - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("case", list(UNET_CASES))
+def test_unet_forward_fp32_matches_reference(case):
+    model, g, x, t, y = build(case)
+    with torch.inference_mode():
+        out = model(x.to(DEV), t.to(DEV), y.to(DEV)) if y is not None else model(x.to(DEV), t.to(DEV))
+    assert out.shape == g["out"].shape and out.dtype == torch.float32
+    l2, linf = nrm_err(out, g["out"])
+    print(f"{case}: fp32 rel L2 {l2:.2e} max {linf:.2e}")
+    assert l2 < 1e-5 and linf < 2e-5
+
+
+@pytest.mark.parametrize("case", list(UNET_CASES))
+def test_unet_forward_bf16_within_tolerance(case):
+    model, g, x, t, y = build(case, torch.bfloat16)
+    with torch.inference_mode():
+        out = model(x.to(DEV), t.to(DEV), y.to(DEV)) if y is not None else model(x.to(DEV), t.to(DEV))
+    l2, linf = nrm_err(out, g["out"])
+    print(f"{case}: bf16 rel L2 {l2:.2e} max {linf:.2e}")
+    assert l2 < 2e-2
+
+
+def test_per_block_taps_fp32():
+    """Per-layer parity: every block output of the 3-D FiLM case against the reference's activations."""
+    from rho_diffusion.layers import ExecCtx
+    from rho_diffusion.b200 import ops
+    model, g, x, t, y = build("film3d")
+    ctx = ExecCtx(dtype=torch.float32)
+    with torch.inference_mode():
+        emb = model._embedding(t.to(DEV), y.to(DEV))
+        h = ops.to_channels_last(x.to(DEV), torch.float32)
+        hs, seen = [], {}
+        for i, m in enumerate(model.input_blocks):
+            h = m.forward_cl(h, emb, ctx)
+            hs.append(h)
+            seen[f"input_blocks.{i}"] = h
+        h = model.middle_block.forward_cl(h, emb, ctx)
+        seen["middle_block"] = h
+        for i, m in enumerate(model.output_blocks):
+            h = m.forward_cl((h, hs.pop()), emb, ctx)
+            seen[f"output_blocks.{i}"] = h
+    checked = 0
+    for name, act in seen.items():
+        a = ops.cl_to_nc(act, torch.float32).cpu()
+        st = g["tap_stats"][name]
+        assert abs(float(a.double().mean()) - float(st[0])) < 1e-5 * max(1.0, float(st[2])), name
+        assert abs(float(a.double().std()) - float(st[1])) < 1e-5 * max(1.0, float(st[2])), name
+        if name in g["taps"]:
+            assert nrm_err(a, g["taps"][name])[1] < 2e-5, name
+            checked += 1
+    assert checked >= 3
+
+
+def make_ddpm(dtype=torch.float32):
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    g = load_golden("ddpm_film3d.pt")
+    spec = UNET_CASES["film3d"]
+    ddpm = DDPM("UNetv2", dict(spec["kwargs"]), LinearSchedule(g["T"], 1e-3, 0.02), "MSELoss", timesteps=g["T"], optimizer="AdamW",
+                opt_kwargs={"lr": 1e-4})
+    ddpm.backbone.load_state_dict(synth_state_dict(g["manifest"], seed=777))
+    ddpm = set_compute_dtype(ddpm.to(DEV), dtype)
+    x0 = synth_input("ddpm.x0", spec["x_shape"], kind="rand")
+    y = synth_input("film3d.y", (spec["x_shape"][0], 128), kind="rand")
+    return ddpm, g, x0, y
+
+
+def test_ddpm_forward_process_and_training_step_fp32():
+    ddpm, g, x0, y = make_ddpm()
+    q = g["q_sample"]
+    x_t, noise = ddpm.forward_process(x0.to(DEV), q["t"].to(DEV), noise=q["noise"].to(DEV))
+    assert (x_t.cpu() - q["x_t"]).abs().max() < 1e-6
+    tr = g["train"]
+    ddpm.train()
+    loss = ddpm.training_step([x0.to(DEV), y.to(DEV)], t=tr["t_idx"], noise=tr["noise"].to(DEV))
+    assert float(loss) == pytest.approx(float(tr["loss"]), rel=1e-5)
+    loss.backward()
+    named = dict(ddpm.backbone.named_parameters())
+    worst = 0.0
+    for k, stat in tr["grad_stats"].items():
+        gnorm = float(named[k].grad.double().norm())
+        worst = max(worst, abs(gnorm - float(stat[0])) / max(float(stat[0]), 1e-6))
+    print("worst grad-norm rel err", worst)
+    assert worst < 2e-4
+    for k, gref in tr["grads"].items():
+        got = named[k].grad.flatten()[:4096].cpu()
+        assert float((got - gref).norm() / gref.norm().clamp_min(1e-12)) < 1e-4, k
+
+
+def test_fused_adamw_matches_reference_step():
+    from rho_diffusion.b200 import optimize
+    ddpm, g, x0, y = make_ddpm()
+    tr = g["train"]
+    opt = ddpm.configure_optimizers(4)["optimizer"]          # lr * sqrt(4), as recorded in the golden
+    assert opt.param_groups[0]["lr"] == pytest.approx(g["opt"]["lr"])
+    ddpm, fused = optimize(ddpm, optimizer=opt, dtype=torch.float32, ema_decay=0.9999)
+    assert ddpm.backbone.state_dict().keys() == g["manifest"].keys()
+    ddpm.train()
+    fused.zero_grad()
+    loss = ddpm.training_step([x0.to(DEV), y.to(DEV)], t=tr["t_idx"], noise=tr["noise"].to(DEV))
+    loss.backward()
+    fused.step()
+    named = dict(ddpm.backbone.named_parameters())
+    for k, after in g["opt"]["after_step"].items():
+        got = named[k].detach().flatten()[:4096].cpu()
+        assert (got - after).abs().max() < 2e-6, k
+    # the step really went through the flat buffer (params are views into it) and a second forward sees new weights
+    assert named["out.2.weight"].data_ptr() >= fused.flat_p.data_ptr()
+    loss2 = ddpm.training_step([x0.to(DEV), y.to(DEV)], t=tr["t_idx"], noise=tr["noise"].to(DEV))
+    assert float(loss2) != float(loss)
+    sd = fused.shadow_state_dict(ddpm.backbone)
+    assert sd.keys() == ddpm.backbone.state_dict().keys()
+
+
+def test_ema_module_matches_reference():
+    from rho_diffusion.ema import ExponentialMovingAverage
+    ddpm, g, _, _ = make_ddpm()
+    # shadow := post-AdamW weights is not reproducible here; check the recurrence from known starts instead
+    ema = ExponentialMovingAverage(ddpm.backbone, decay=0.9999)
+    ddpm.backbone.load_state_dict(synth_state_dict(g["manifest"], seed=778))
+    ema.update()
+    ema.update()
+    assert ema.current_ema_frac == pytest.approx(g["ema"]["frac"])
+    k = "out.2.weight"
+    s0 = synth_state_dict({k: g["manifest"][k]}, seed=777)[k]
+    p = synth_state_dict({k: g["manifest"][k]}, seed=778)[k]
+    want = O.ema_update(O.ema_update(s0, p, 1), p, 2)
+    assert (dict(ema.ema_model.named_parameters())[k].cpu() - want).abs().max() < 1e-7
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_reverse_process_shared_noise_matches_reference(graph):
+    ddpm, g, _, y = make_ddpm()
+    ddpm.eval()
+    rv = g["reverse"]
+    T = g["T"]
+    noises = {T - 1 - i: z for i, z in enumerate(rv["z"])}
+    res = ddpm.reverse_process(torch.zeros(rv["x_init"].shape, device=DEV), conditions=y.to(DEV), x_init=rv["x_init"].to(DEV),
+                               noises=noises, use_cuda_graph=graph, t_checkpoints=[0, 1, 2])
+    den = res["denoised"].cpu()
+    err = float((den - rv["denoised"]).abs().max())
+    print("trajectory max abs err", err, "graph" if graph else "eager")
+    assert err < 2e-4
+    assert res["buffer"].shape[1] == 3
+    assert den.min() >= -1 and den.max() <= 1
+
+
+def test_reverse_process_graph_in_kernel_noise_is_deterministic_and_bounded():
+    ddpm, g, _, y = make_ddpm(torch.bfloat16)
+    ddpm.eval()
+    shape = g["reverse"]["x_init"].shape
+    from rho_diffusion.b200.sampler import AncestralSampler
+    alpha, beta, abar = ddpm._tables(torch.device(DEV, 0))
+    s = AncestralSampler(ddpm.backbone, shape, torch.device(DEV, 0), alpha, beta, abar, cond_example=y.to(DEV))
+    from rho_diffusion.b200 import ops
+    x_init = ops.randn(shape, DEV, seed=5)
+    a = s.run(x_init, y.to(DEV), seed=11)["denoised"]
+    b = s.run(x_init, y.to(DEV), seed=11)["denoised"]
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all() and a.min() >= -1 and a.max() <= 1
+    e = AncestralSampler(ddpm.backbone, shape, torch.device(DEV, 0), alpha, beta, abar, cond_example=y.to(DEV), use_cuda_graph=False)
+    c = e.run(x_init, y.to(DEV), seed=11)["denoised"]
+    assert (a - c).abs().max() < 1e-5      # same kernels, same order: graph replay == eager launches
+
+
+def test_training_loss_curve_tracks_oracle():
+    """Short shared-noise training run (fp32): the loss after each of 5 AdamW steps follows the CPU oracle driven by
+    torch autograd + the restated AdamW (the full 1k-step curve is a bench-time check)."""
+    from rho_diffusion.b200 import optimize
+    ddpm, g, x0, y = make_ddpm()
+    spec = UNET_CASES["film3d"]
+    uspec = O.UNetSpec(**spec["kwargs"])
+    sched = O.linear_schedule(g["T"], 1e-3, 0.02)
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth_state_dict(g["manifest"], seed=777).items()}
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    opt = ddpm.configure_optimizers(1)["optimizer"]
+    ddpm, fused = optimize(ddpm, optimizer=opt, dtype=torch.float32)
+    ddpm.train()
+    gen = torch.Generator().manual_seed(3)
+    for step in range(1, 6):
+        t = torch.randint(0, g["T"], (x0.shape[0],), generator=gen)
+        noise = torch.randn(x0.shape, generator=gen)
+        # oracle
+        x_t = O.q_sample(sched, x0, t, noise)
+        loss_ref = O.mse_loss(O.unet_forward(sd, uspec, x_t, t, y), noise)
+        grads = torch.autograd.grad(loss_ref, list(sd.values()))
+        with torch.no_grad():
+            for (k, p), gr in zip(sd.items(), grads):
+                p_new, m[k], v2[k] = O.adamw_step(p, gr, m[k], v2[k], step, lr=1e-4)
+                p.copy_(p_new)
+        # CUDA
+        fused.zero_grad()
+        loss = ddpm.training_step([x0.to(DEV), y.to(DEV)], t=t, noise=noise.to(DEV))
+        loss.backward()
+        fused.step()
+        print(step, float(loss), float(loss_ref))
+        assert float(loss) == pytest.approx(float(loss_ref), rel=5e-4)

@@ -1,0 +1,305 @@
+"""Per-kernel parity tests: every C-ABI op vs the CPU oracle (plain PyTorch fp32 on CPU) on seeded inputs.
+
+fp32 path: 1e-5 relative (north star), bf16 path: 2e-2.  Integer work (Philox words, embedding indices) is
+bit-exact.  All calls go through the C ABI (ctypes -> librho_b200.so)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rho_diffusion.b200 import ops as _ops
+    return _ops
+
+
+DEV = "cuda"
+
+
+def rel_err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+def randn(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def cl(x):  # (N, C, *sp) cpu -> channels-last cuda
+    return x.permute(0, *range(2, x.dim()), 1).contiguous().to(DEV)
+
+
+def nc(x):  # channels-last cuda -> (N, C, *sp) cpu
+    return x.float().cpu().permute(0, x.dim() - 1, *range(1, x.dim() - 1)).contiguous()
+
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_layout_roundtrip(ops):
+    for shape in [(2, 3, 24, 16), (2, 1, 8, 16, 16), (3, 32, 65), (1, 64, 5, 7, 9)]:
+        x = randn(*shape, seed=1).to(DEV)
+        y = ops.nc_to_cl(x, torch.float32)
+        assert torch.equal(nc(y), x.cpu())
+        assert torch.equal(ops.cl_to_nc(y, torch.float32).cpu(), x.cpu())
+        yb = ops.nc_to_cl(x, torch.bfloat16)
+        assert torch.equal(nc(yb), x.cpu().bfloat16().float())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,c2,film,pre", [
+    ((2, 64, 8, 8), 0, False, False),
+    ((2, 32, 33), 0, True, False),          # 1 channel per group, ragged S
+    ((2, 128, 4, 6, 5), 64, True, False),   # concat 128+64 = 192: groups straddle the two sources
+    ((1, 96, 7, 9), 0, False, True),        # 3 channels per group, additive embedding
+    ((2, 1024, 6), 512, True, False),       # 1536 channels: multi-pass over the channel dimension
+])
+def test_groupnorm_act_fwd_bwd(ops, dtype, shape, c2, film, pre):
+    N, C1 = shape[0], shape[1]
+    C = C1 + c2
+    x1 = randn(*shape, seed=2) * 1.5 + 0.3
+    x2 = randn(N, c2, *shape[2:], seed=3) - 0.5 if c2 else None
+    gamma, beta = 1 + 0.1 * randn(C, seed=4), 0.1 * randn(C, seed=5)
+    e = 0.3 * randn(N, 2 * C, seed=6)
+    pa = 0.5 * randn(N, C, seed=7)
+    dy = randn(N, C, *shape[2:], seed=8)
+
+    # ---- oracle (CPU fp32; inputs rounded to the storage dtype first so both sides see the same values)
+    q = (lambda t: t.to(dtype).float())
+    leaves = [q(x1).requires_grad_(True)]
+    if c2:
+        leaves.append(q(x2).requires_grad_(True))
+    gr, br, er, par = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), e.clone().requires_grad_(True), pa.clone().requires_grad_(True)
+    xin = torch.cat(leaves, 1)
+    bshape = (N, C, *([1] * (len(shape) - 2)))
+    if pre:
+        xin = xin + par.view(bshape)
+    h = F.group_norm(xin, 32, gr, br, 1e-5)
+    if film:
+        h = h * (1 + er[:, :C].reshape(bshape)) + er[:, C:].reshape(bshape)
+    ref = F.silu(h)
+    ref.backward(q(dy))
+
+    # ---- CUDA
+    xs = [cl(t.detach()).to(dtype).requires_grad_(True) for t in leaves]
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    ed = e.to(DEV).requires_grad_(True) if film else None
+    pd = pa.to(DEV).requires_grad_(True) if pre else None
+    from rho_diffusion.b200 import _lib
+    y = ops.GnActFn.apply(xs[0], xs[1] if c2 else None, gd, bd, ed, pd, _lib.ACT_SILU, dtype, 32, 1e-5)
+    y.backward(cl(dy).to(dtype))
+    tol = TOL[dtype]
+    assert rel_err(nc(y), ref) < tol
+    gtol = tol * 4
+    assert rel_err(nc(xs[0].grad), leaves[0].grad) < gtol
+    if c2:
+        assert rel_err(nc(xs[1].grad), leaves[1].grad) < gtol
+    assert rel_err(gd.grad, gr.grad) < gtol and rel_err(bd.grad, br.grad) < gtol
+    if film:
+        assert rel_err(ed.grad, er.grad) < gtol
+    if pre:
+        assert rel_err(pd.grad, par.grad) < gtol
+
+
+CONV_CASES = [
+    # (dims, N, Cin1, Cin2, Cout, spatial, k, stride, up, residual)
+    (2, 2, 3, 0, 32, (24, 16), 3, 1, 1, False),        # reference fixture: 3 input channels (odd), unaligned
+    (2, 2, 32, 0, 3, (12, 8), 3, 1, 1, False),         # 3 output channels
+    (3, 1, 1, 0, 32, (4, 8, 8), 3, 1, 1, False),       # first conv of the 3-D configs
+    (3, 1, 64, 0, 64, (4, 8, 8), 3, 1, 1, True),       # ResBlock out conv + identity residual
+    (3, 2, 64, 32, 64, (3, 6, 6), 3, 1, 1, False),     # concat input (up path)
+    (3, 1, 64, 32, 32, (3, 6, 6), 1, 1, 1, False),     # 1x1x1 skip conv on a concat input
+    (3, 1, 32, 0, 32, (4, 8, 8), 3, (1, 2, 2), 1, False),   # Downsample, 3-D keeps depth
+    (2, 2, 32, 0, 32, (8, 10), 3, 2, 1, False),        # Downsample 2-D
+    (1, 2, 32, 0, 64, (33,), 3, 2, 1, False),          # Downsample 1-D, odd length
+    (3, 1, 32, 0, 32, (3, 4, 5), 3, 1, (1, 2, 2), False),   # Upsample (nearest) fused into the conv, 3-D
+    (2, 1, 64, 0, 32, (5, 6), 3, 1, 2, False),         # Upsample 2-D
+    (1, 2, 128, 0, 384, (16,), 1, 1, 1, False),        # attention qkv projection (Conv1d k=1)
+    (1, 2, 128, 0, 128, (16,), 1, 1, 1, True),         # attention proj_out + residual
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
+def test_conv_fwd_bwd(ops, dtype, case):
+    dims, N, C1, C2, Cout, sp, k, stride, up, use_res = case
+    conv = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[dims]
+    q = (lambda t: t.to(dtype).float())
+    x1 = q(randn(N, C1, *sp, seed=10)).requires_grad_(True)
+    x2 = q(randn(N, C2, *sp, seed=11)).requires_grad_(True) if C2 else None
+    Cin = C1 + C2
+    w = (randn(Cout, Cin, *([k] * dims), seed=12) / math.sqrt(Cin * k ** dims)).requires_grad_(True)
+    b = (0.1 * randn(Cout, seed=13)).requires_grad_(True)
+    xin = torch.cat([x1, x2], 1) if C2 else x1
+    upt = up if isinstance(up, tuple) else (up,) * dims
+    if any(u != 1 for u in upt):
+        xin = F.interpolate(xin, tuple(s * u for s, u in zip(sp, upt)), mode="nearest")
+    wq = q(w) if dtype == torch.bfloat16 else w
+    ref = conv(xin, wq, b, stride=stride, padding=k // 2)
+    res = q(randn(*ref.shape, seed=14)) if use_res else None
+    if use_res:
+        ref = ref + res
+    dy = q(randn(*ref.shape, seed=15))
+    ref.backward(dy)
+
+    spec = ops.ConvSpec.make(dims, k, stride, up)
+    xd = cl(x1.detach()).to(dtype).requires_grad_(True)
+    x2d = cl(x2.detach()).to(dtype).requires_grad_(True) if C2 else None
+    wd, bd = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+    resd = cl(res).to(dtype).requires_grad_(True) if use_res else None
+    y = ops.ConvFn.apply(xd, x2d, wd, bd, resd, spec, dtype, 0, False)
+    assert tuple(nc(y).shape) == tuple(ref.shape)
+    y.backward(cl(dy).to(dtype))
+    tol = TOL[dtype]
+    assert rel_err(nc(y), ref) < tol
+    assert rel_err(nc(xd.grad), x1.grad) < 4 * tol
+    if C2:
+        assert rel_err(nc(x2d.grad), x2.grad) < 4 * tol
+    assert rel_err(wd.grad, w.grad) < 4 * tol   # (bf16: gradient at the rounded weight values)
+    assert rel_err(bd.grad, b.grad) < 4 * tol
+    if use_res:
+        assert rel_err(nc(resd.grad), dy) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,T,heads,ch,order", [
+    (2, 6, 1, 256, 0),      # reference fixture: heads=1, ch=256, T=6
+    (2, 100, 4, 16, 1),     # ragged T, new order
+    (1, 512, 4, 32, 0),
+    (1, 130, 2, 64, 1),
+    (1, 96, 4, 128, 1),     # config A head dim
+])
+def test_attention_fwd_bwd(ops, dtype, N, T, heads, ch, order):
+    q = (lambda t: t.to(dtype).float())
+    qkv = q(randn(N, 3 * heads * ch, T, seed=20)).requires_grad_(True)   # reference layout (N, 3HC, T)
+    ref = O._attention(qkv, heads, bool(order))
+    dy = q(randn(*ref.shape, seed=21))
+    ref.backward(dy)
+    qd = qkv.detach().permute(0, 2, 1).contiguous().to(DEV).to(dtype).requires_grad_(True)   # (N, T, 3HC)
+    out = ops.attention(qd, heads, order)
+    out.backward(dy.permute(0, 2, 1).contiguous().to(DEV).to(dtype))
+    tol = TOL[dtype]
+    assert rel_err(out.float().cpu().permute(0, 2, 1), ref) < tol
+    assert rel_err(qd.grad.float().cpu().permute(0, 2, 1), qkv.grad) < 4 * tol
+
+
+def test_embedding_path(ops):
+    from rho_diffusion.b200 import _lib
+    from rho_diffusion.models.common import omega_table
+    t = torch.tensor([0, 1, 2, 17, 499, 999])
+    for dim in (32, 64, 128):
+        got = ops.timestep_embedding(t.to(DEV), dim, omega_table(dim).to(DEV))
+        assert (got.cpu() - O.timestep_embedding(t, dim)).abs().max() < 2e-6
+    # linear with fused input activation and add, fwd + bwd
+    x = randn(5, 48, seed=30).requires_grad_(True)
+    w = (randn(96, 48, seed=31) / 7).requires_grad_(True)
+    b = randn(96, seed=32).requires_grad_(True)
+    add = randn(5, 96, seed=33).requires_grad_(True)
+    ref = F.linear(F.silu(x), w, b) + add
+    dy = randn(5, 96, seed=34)
+    ref.backward(dy)
+    xd, wd, bd, ad = (v.detach().to(DEV).requires_grad_(True) for v in (x, w, b, add))
+    y = ops.linear(xd, wd, bd, ad, act_in=_lib.ACT_SILU)
+    y.backward(dy.to(DEV))
+    assert rel_err(y, ref) < 1e-5
+    for got, want in ((xd.grad, x.grad), (wd.grad, w.grad), (bd.grad, b.grad), (ad.grad, add.grad)):
+        assert rel_err(got, want) < 1e-5
+    # MultiEmbeddings: indices are exact, the sum matches the oracle
+    from collections import OrderedDict
+    from rho_diffusion.models.conditioning import MultiEmbeddings
+    from conftest import load_golden
+    from oracle.synth import synth_state_dict
+    g = load_golden("embeddings.pt")["multi_emb"]
+    me = MultiEmbeddings(parameter_space=OrderedDict(g["space"]), embedding_dim=16)
+    me.load_state_dict(synth_state_dict(g["manifest"], seed=5))
+    me = me.to(DEV)
+    out = me(g["y"].to(DEV))
+    assert (out.cpu() - g["out"]).abs().max() < 1e-6
+    out.backward(torch.ones_like(out))
+    gs = me.embedding_layers["s"].weight.grad.cpu()
+    assert torch.equal(gs, torch.ones(3, 16))          # rows 0.5, 1.0, 0.25 each hit exactly once
+    gt = me.embedding_layers["t"].weight.grad.cpu()
+    assert torch.equal(gt[:, 0], torch.tensor([2.0, 1.0]))
+
+
+def test_philox_bit_exact_and_normals(ops):
+    import ctypes as C
+    from rho_diffusion.b200 import _lib
+    groups, seed, offset = 4096, 0x1234567890ABCDEF, 7
+    out = torch.empty(groups * 4, dtype=torch.int32, device=DEV)
+    _lib.check(_lib.lib().rho_philox_raw(out.data_ptr(), groups, seed, offset, ops.stream()), "philox_raw")
+    got = out.cpu().numpy().view(np.uint32).reshape(groups, 4)
+    assert np.array_equal(got, O.philox4x32_10(groups, offset, seed))
+    # Random123 known-answer vector: counter = 0, key = 0
+    _lib.check(_lib.lib().rho_philox_raw(out.data_ptr(), 1, 0, 0, ops.stream()), "philox_raw")
+    assert [hex(v) for v in out[:4].cpu().numpy().view(np.uint32)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    n = 100003
+    z = ops.randn((n,), DEV, seed=42, offset=3).cpu().numpy()
+    ref = O.philox_normal(n, 3, 42)
+    assert np.abs(z - ref).max() < 2e-5
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+
+
+def test_q_sample_p_sample_mse(ops):
+    sched = O.linear_schedule(100, 1e-3, 0.02)
+    dev = {k: v.to(DEV) for k, v in sched.items()}
+    x0, eps = randn(3, 1, 5, 7, 9, seed=40), randn(3, 1, 5, 7, 9, seed=41)   # 315 elements/sample: unaligned
+    t = torch.tensor([0, 57, 99])
+    got = ops.q_sample(x0.to(DEV), eps.to(DEV), t.to(DEV), dev["alpha_bar_t"])
+    assert (got.cpu() - O.q_sample(sched, x0, t, eps)).abs().max() < 1e-6
+    # ancestral update with external noise, all step classes (t = 0: identity, t = 1: no noise, t > 1)
+    z = randn(3, 1, 5, 7, 9, seed=42)
+    for step in (0, 1, 2, 50, 99):
+        x = x0.clone().to(DEV)
+        ts = torch.tensor([step], device=DEV)
+        ops.p_sample_step(x, eps.to(DEV), z.to(DEV), ts, dev["alpha_t"], dev["beta_t"], dev["alpha_bar_t"])
+        zz = z if step > 1 else torch.zeros_like(z)
+        assert (x.cpu() - O.p_sample_step(sched, x0, eps, zz, step)).abs().max() < 2e-6, step
+    # in-kernel Philox noise == external noise generated by rho_randn with (seed, offset = t)
+    x_a, x_b = x0.clone().to(DEV), x0.clone().to(DEV)
+    ts = torch.tensor([50], device=DEV)
+    zk = ops.randn(x0.shape, DEV, seed=99, offset=50)
+    ops.p_sample_step(x_a, eps.to(DEV), None, ts, dev["alpha_t"], dev["beta_t"], dev["alpha_bar_t"], seed=99)
+    ops.p_sample_step(x_b, eps.to(DEV), zk, ts, dev["alpha_t"], dev["beta_t"], dev["alpha_bar_t"])
+    assert torch.equal(x_a, x_b)
+    # timestep advance
+    tsc, tv = torch.tensor([7], device=DEV), torch.zeros(5, dtype=torch.int64, device=DEV)
+    ops.advance_timestep(tsc, tv)
+    assert int(tsc) == 6 and tv.tolist() == [6] * 5
+    # MSE + gradient
+    for dtype in (torch.float32, torch.bfloat16):
+        pred = randn(4, 1000, seed=43).to(dtype)
+        tgt = randn(4, 1000, seed=44)
+        pr = pred.float().requires_grad_(True)
+        ref = O.mse_loss(pr, tgt)
+        (ref * 3.0).backward()
+        pd = pred.to(DEV).requires_grad_(True)
+        loss = ops.MseLossFn.apply(pd, tgt.to(DEV))
+        (loss * 3.0).backward()
+        assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, float(ref))
+        assert rel_err(pd.grad, pr.grad) < TOL[dtype]
+
+
+def test_adamw_ema_kernel(ops):
+    n = 10007
+    p, g = randn(n, seed=50), randn(n, seed=51) * 0.1
+    m, v, sh = torch.zeros(n), torch.zeros(n), randn(n, seed=52)
+    pd, gd, md, vd, sd = (t.clone().to(DEV) for t in (p, g, m, v, sh))
+    for step in (1, 2, 3):
+        p, m, v = O.adamw_step(p, g * 0.5, m, v, step, lr=2e-4, weight_decay=1e-2)
+        sh = O.ema_update(sh, p, step)
+        ops.adamw_ema_step(pd, gd, md, vd, sd, step, 2e-4, (0.9, 0.999), 1e-8, 1e-2, ema_decay_t=O.ema_decay(step), grad_scale=0.5)
+    assert (pd.cpu() - p).abs().max() < 1e-6
+    assert (sd.cpu() - sh).abs().max() < 1e-6
+    assert rel_err(md, m) < 1e-5 and rel_err(vd, v) < 1e-5

@@ -1,0 +1,167 @@
+"""CPU tests of the host-side mirror of the reference interface: registry, config, schedules, state-dict layout,
+C-ABI symbol export.  No kernel is launched here."""
+import ctypes
+import json
+import os
+import re
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle.cases import UNET_CASES
+
+import rho_diffusion  # noqa: F401
+from rho_diffusion.config import ConfigValidationError, ExperimentConfig
+from rho_diffusion.diffusion import schedule as S
+from rho_diffusion.models.conditioning import MultiEmbeddings
+from rho_diffusion.models.unet_v2 import UNet
+from rho_diffusion.registry import registry
+
+EXAMPLES = {
+    "sph": dict(experiment="ShpericalHarmonics",
+                model={"name": "UNetv2", "kwargs": {"dims": 3, "in_channels": 1, "out_channels": 1, "model_channels": 64,
+                                                    "num_res_blocks": 2, "data_shape": [32, 32, 32], "attention_resolutions": [16, 8],
+                                                    "use_scale_shift_norm": True, "num_heads": 4, "num_classes": 20,
+                                                    "activation": "SiLU", "use_new_attention_order": False,
+                                                    "cond_fn": "MultiEmbeddings"}},
+                dataset={"name": "SphericalHarmonicDataset", "kwargs": {"max_l": 5}},
+                optimizer={"name": "AdamW", "kwargs": {"lr": 0.0001}},
+                lr_scheduler={"name": "CosineAnnealingLR", "kwargs": {"T_max": 10, "eta_min": 0.00001}},
+                noise_schedule={"name": "LinearSchedule", "kwargs": {"num_steps": 1000, "beta_1": 0.001, "beta_T": 0.02}},
+                training={"device": "xpu", "np": 1, "loss_fn": "MSELoss", "batch_size": 32, "seed": 777, "benchmark_mode": True},
+                inference={"device": "xpu", "checkpoint": "model.pth", "parameter_space": {"l": [-1, 1], "m": [1, 2]}}),
+}
+
+
+def test_registry_names_and_errors():
+    # reference tests/models/test_unet.py:28-30 and tests/pipeline/test_schedule.py:49-53
+    assert registry.get("models", "UNetv2") is UNet
+    for name in S.__all__:
+        assert registry.get("schedules", name)
+    for cat, name in [("layers", "GroupNorm32"), ("layers", "conv_nd"), ("layers", "avg_pool_nd"), ("layers", "mean_flat"),
+                      ("layers", "RMSNorm"), ("layers", "MultiEmbeddings"), ("layers", "SinusoidalPositionEmbedding"),
+                      ("activations", "SiLU"), ("optimizers", "AdamW"), ("nn", "MSELoss")]:
+        assert registry.get(cat, name)
+    assert registry.categories == ["models", "activations", "layers", "datasets", "nn", "schedules", "optimizers"]
+    with pytest.raises(KeyError):
+        registry.get("models", "nope")
+    with pytest.raises(AssertionError):
+        registry.get("nope", "UNetv2")
+
+    @registry.register_dataset("toy")
+    class Toy:
+        pass
+
+    assert registry.get("datasets", "toy") is Toy
+
+
+def test_config_schema_and_pydantic_v1_bool_quirk(tmp_path):
+    p = tmp_path / "cfg.json"
+    p.write_text(json.dumps(EXAMPLES["sph"]))
+    cfg = ExperimentConfig.from_json(str(p))
+    kw = cfg.model.kwargs
+    # numbers survive as numbers, JSON booleans become *strings* under the pinned pydantic v1
+    assert kw["model_channels"] == 64 and isinstance(kw["model_channels"], int)
+    assert kw["attention_resolutions"] == [16, 8] and kw["data_shape"] == [32, 32, 32]
+    assert kw["use_new_attention_order"] == "False" and kw["use_scale_shift_norm"] == "True"
+    assert cfg.optimizer.kwargs["lr"] == pytest.approx(1e-4)
+    assert cfg.noise_schedule.kwargs == {"num_steps": 1000, "beta_1": 0.001, "beta_T": 0.02}
+    assert cfg.training.batch_size == 32 and cfg.training.ema_decay == 0.0 and cfg.training.max_epochs == 999
+    assert not hasattr(cfg.training, "benchmark_mode")          # unknown keys are ignored
+    assert cfg.inference.seed == 777 and cfg.inference.cache_file is None
+    native = ExperimentConfig.from_json(str(p), bool_mode="native")
+    assert native.model.kwargs["use_new_attention_order"] == 0 and not isinstance(native.model.kwargs["use_new_attention_order"], str)
+    # the string 'False' is truthy => the new attention order is selected, as in the reference
+    m = UNet(**{**kw, "model_channels": 32, "data_shape": [8, 8, 8]})
+    assert type(m.middle_block[1].attention).__name__ == "QKVAttention"
+    with pytest.raises(FileNotFoundError):
+        ExperimentConfig.from_json(str(tmp_path / "missing.json"))
+
+
+def test_config_invalid_is_rejected():
+    # shape of the reference's tests/config_invalid.json: list where str expected, kwargs null, missing section
+    bad = dict(EXAMPLES["sph"])
+    bad["experiment"] = ["a", "b"]
+    with pytest.raises(ConfigValidationError):
+        ExperimentConfig(**bad)
+    bad = dict(EXAMPLES["sph"])
+    bad["model"] = {"name": "UNetv2", "kwargs": None}
+    with pytest.raises(ConfigValidationError):
+        ExperimentConfig(**bad)
+    bad = dict(EXAMPLES["sph"])
+    del bad["dataset"]
+    with pytest.raises(ConfigValidationError):
+        ExperimentConfig(**bad)
+
+
+@pytest.mark.parametrize("name,make", [
+    ("linear_100_kat", lambda: S.LinearSchedule(100, 1e-4, 0.02)),
+    ("linear_1000", lambda: S.LinearSchedule(1000, 1e-3, 0.02)),
+    ("linear_500_default", lambda: S.LinearSchedule(500)),
+    ("cosine_50", lambda: S.CosineBetaSchedule(50)),
+    ("cosine_1000", lambda: S.CosineBetaSchedule(1000)),
+])
+def test_schedule_tables_match_reference_bit_exact(name, make):
+    g = load_golden("schedule.pt")[name]
+    s = make()
+    for k in ("beta_t", "alpha_t", "alpha_bar_t", "sigma_t", "offset_alpha_bar_t"):
+        got = s[k] if k != "offset_alpha_bar_t" else s.offset_alpha_bar_t
+        assert got.dtype == torch.float32
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(g[k], nan=-7.0)), k
+
+
+def test_schedule_known_answers_and_dtype_cast():
+    s = S.LinearSchedule(100, 1e-4, 0.02)  # reference tests/pipeline/test_schedule.py:28-46
+    assert len(s.beta_t) == 100 and s.beta_t[0] == 0.001 and s.beta_t[-1] == 0.2
+    assert s.alpha_t[0] == 0.999 and s.alpha_t[-1] == 0.8 and s.sigma_t[0] == 0.0
+    assert float(s.sigma_t[-1]) == pytest.approx(0.4472, rel=1e-4)
+    s.dtype = torch.bfloat16
+    assert s["alpha_bar_t"].dtype == torch.bfloat16
+    with s:
+        assert s["alpha_bar_t"].dtype == torch.float32
+    assert len(S.CosineBetaSchedule(50)) == 51           # T+1 points, sigma_t[0] NaN
+    assert torch.isnan(S.CosineBetaSchedule(50).sigma_t[0])
+    with pytest.raises(NotImplementedError):
+        S.SigmoidSchedule(10)
+
+
+@pytest.mark.parametrize("case", list(UNET_CASES))
+def test_state_dict_layout_matches_reference(case):
+    """Checkpoint contract: same keys, same shapes as the reference model => reference model.pth loads strict."""
+    spec = UNET_CASES[case]
+    g = load_golden(f"unet_{case}.pt")
+    kwargs = dict(spec["kwargs"])
+    if spec["cond"] == "multi":
+        kwargs["cond_fn"] = MultiEmbeddings(parameter_space=OrderedDict(spec["parameter_space"]),
+                                            embedding_dim=4 * kwargs["model_channels"])
+    model = UNet(**kwargs)
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert list(got.keys()) == list(g["manifest"].keys())
+    assert got == g["manifest"]
+    # zero-initialised modules as in the reference (layers.py:113-119)
+    assert float(model.out[2].weight.abs().sum()) == 0.0
+    assert float(model.middle_block[1].proj_out.weight.abs().sum()) == 0.0
+    assert float(model.middle_block[0].out_layers[3].weight.abs().sum()) == 0.0
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rho_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rho_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 30
+    from rho_diffusion.b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first (__graft_entry__.build())"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, missing
+    assert sorted(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ set(declared)
+    assert handle.rho_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly off-GPU, never compute on the CPU."""
+    from rho_diffusion.b200 import _lib
+    m = UNet(data_shape=8, in_channels=1, model_channels=32, out_channels=1, num_res_blocks=1)
+    with pytest.raises(_lib.RhoB200Error):
+        m(torch.zeros(1, 1, 8, 8), torch.zeros(1, dtype=torch.long))
