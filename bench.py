@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native rho-diffusion hot path.
+
+Metric (BASELINE.json): UNet denoise evals/s (batch x steps / s) of the 3-D 64^3 conditional UNet (attention at
+64x16x16, "config D" of SURVEY.md section 8) inside the DDPM ancestral sampling loop, plus train samples/s of the same
+model.  One "step" = one sampling step (UNet eval + fused ancestral update) over one batch of synthetic density fields.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--dtype bf16|fp32]
+
+For N > 1 launch with torchrun (one rank per GPU); sampling shards the batch across ranks with no communication
+(weak scaling: per-GPU batch fixed), the training leg all-reduces the flat gradient buffer over NCCL.
+``--impl reference`` times the CPU restatement of the reference (oracle/torch_oracle.py, kind "port": the reference
+is pure Python and /root/reference does not exist on the GPU box) on the host cores for the same workload.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "rho-diffusion_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+# ---- workload: config D -----------------------------------------------------------
+CONFIG_D = dict(dims=3, in_channels=1, out_channels=1, model_channels=64, num_res_blocks=2, data_shape=[64, 64, 64],
+                attention_resolutions=[4], use_scale_shift_norm=True, num_heads=4, num_classes=20, activation="SiLU",
+                use_new_attention_order=True)
+T_STEPS = 1000
+WORKLOAD = "3D conditional UNet 64^3 (mc64, nrb2, FiLM, 4 heads, attention at 64x16x16), DDPM ancestral sampling step, T=1000"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return world, rank, local
+
+
+def make_inputs(batch, seed):
+    from oracle.synth import synth_input
+    x = synth_input(f"bench.x.{seed}", (batch, 1, 64, 64, 64))
+    y = synth_input(f"bench.y.{seed}", (batch, 256), kind="rand")
+    return x, y
+
+
+def build_model(device, dtype, seed=777):
+    from oracle.synth import synth_state_dict
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    ddpm = DDPM("UNetv2", dict(CONFIG_D), LinearSchedule(T_STEPS, 1e-3, 0.02), "MSELoss", timesteps=T_STEPS, optimizer="AdamW",
+                opt_kwargs={"lr": 1e-4}, seed=seed)
+    manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+    ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))   # random-init weights of the architecture
+    return set_compute_dtype(ddpm.to(device), dtype), manifest
+
+
+# --------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference UNet eval (+ ancestral update) on the host cores."""
+    world, rank, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import torch_oracle as O
+    from oracle.synth import synth_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    batch = 1
+    x, y = make_inputs(batch, 0)
+    spec = O.UNetSpec(**CONFIG_D)
+    sched = O.linear_schedule(T_STEPS, 1e-3, 0.02)
+    # manifest without instantiating the CUDA package: walk the reference layout through the product's module tree on CPU
+    from rho_diffusion.models.unet_v2 import UNet
+    manifest = {k: tuple(v.shape) for k, v in UNet(**CONFIG_D).state_dict().items()}
+    sd = synth_state_dict(manifest, seed=777)
+    budget_s = float(os.environ.get("RHO_BENCH_CPU_BUDGET_S", "240"))
+    t_begin = time.perf_counter()
+    warm = min(args.warmup, 1)        # one untimed eval (allocator / thread-pool warm-up); CPU evals take seconds each
+    timed, elapsed = 0, 0.0
+    tt = torch.full((batch,), T_STEPS - 1, dtype=torch.long)
+    with torch.inference_mode():
+        for i in range(warm + args.steps):
+            if timed >= 1 and time.perf_counter() - t_begin > budget_s:
+                break
+            t0 = time.perf_counter()
+            eps = O.unet_forward(sd, spec, x, tt, y)
+            x = O.p_sample_step(sched, x, eps, torch.zeros_like(x), T_STEPS - 1)
+            if i >= warm:
+                timed += 1
+                elapsed += time.perf_counter() - t0
+    value = batch * timed / elapsed
+    sample = f"{timed} timed evals of batch {batch} (of {args.steps} requested; {budget_s:.0f} s CPU budget), fp32, torch-CPU oracle port"
+    line = {
+        "impl": "reference", "metric": "UNet denoise evals/s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "ms_per_step": 1000.0 * elapsed / timed, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "batch_per_step": batch},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(budget_s=30.0):
+    """One oracle eval at batch 1 on the host cores (bounded sample of the same workload)."""
+    from oracle import torch_oracle as O
+    from oracle.synth import synth_state_dict
+    from rho_diffusion.models.unet_v2 import UNet
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = make_inputs(1, 0)
+    manifest = {k: tuple(v.shape) for k, v in UNet(**CONFIG_D).state_dict().items()}
+    sd = synth_state_dict(manifest, seed=777)
+    spec = O.UNetSpec(**CONFIG_D)
+    tt = torch.full((1,), T_STEPS - 1, dtype=torch.long)
+    n, elapsed = 0, 0.0
+    with torch.inference_mode():
+        while n < 1 or (elapsed < budget_s / 3 and n < 3):
+            t0 = time.perf_counter()
+            O.unet_forward(sd, spec, x, tt, y)
+            elapsed += time.perf_counter() - t0
+            n += 1
+    return {"value": n / elapsed, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} UNet eval(s) of batch 1, config D, fp32, torch-CPU oracle port of the reference"}
+
+
+# --------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from rho_diffusion.b200 import _lib, ops, optimize
+    from rho_diffusion.b200.sampler import AncestralSampler
+
+    world, rank, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    B = args.batch
+    pk = peaks()
+
+    ddpm, _ = build_model(device, dtype, seed=777 + rank)
+    ddpm.eval()
+    x_host, y_host = make_inputs(B, rank)
+    x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
+    x_out_pin = torch.empty_like(x_pin).pin_memory()
+    alpha, beta, abar = ddpm._tables(device)
+    cond_dev = y_host.to(device)
+    sampler = AncestralSampler(ddpm.backbone, (B, 1, 64, 64, 64), device, alpha, beta, abar, cond_example=cond_dev, use_cuda_graph=True)
+
+    # ---- capture (counts the kernels of one step through the C-ABI launch counter)
+    with torch.inference_mode():
+        c0 = _lib.launch_count()
+        sampler._capture(seed=1234 + rank)
+        launches_per_step = (_lib.launch_count() - c0) // 2      # warm-up pass + capture pass
+        x_dev = x_host.to(device)
+        sampler.x.copy_(x_dev)
+        sampler.tt.fill_(T_STEPS - 1)
+        sampler.t_scalar.fill_(T_STEPS - 1)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident leg: K replays of the captured step (inputs already in HBM; the working set of one eval,
+        #      >1 GB of activations + 326 MB of bf16 weights, is far larger than the 126 MB L2, so no flush is needed)
+        for _ in range(args.warmup):
+            sampler.graph.replay()
+        barrier()
+        clocks = ClockSampler(local)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            sampler.graph.replay()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop()
+
+        # ---- end-to-end leg: host buffers in, host buffers out, every step (public sampler API)
+        def e2e_step():
+            sampler.x.copy_(x_pin, non_blocking=True)
+            sampler.cond.copy_(y_pin, non_blocking=True)
+            sampler.graph.replay()
+            x_out_pin.copy_(sampler.x, non_blocking=True)
+
+        sampler.tt.fill_(T_STEPS // 2)
+        sampler.t_scalar.fill_(T_STEPS // 2)
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+        # ---- per-kernel roofline pass: one eager eval with CUDA events around every conv / GN / attention launch
+        ops.profiler = ops.KernelProfiler()
+        tt = torch.full((B,), 500, dtype=torch.int64, device=device)
+        ddpm.backbone(x_dev, tt, cond_dev)
+        prof = ops.profiler.summary()
+        ops.profiler = None
+
+    # ---- training leg (samples/s): q_sample -> UNet fwd/bwd -> fused AdamW (+ flat-gradient all-reduce for N > 1)
+    train = None
+    if args.train_steps > 0:
+        Bt = args.train_batch
+        xt, yt = make_inputs(Bt, 100 + rank)
+        xt, yt = xt.to(device), yt.to(device)
+        opt = ddpm.configure_optimizers(world)["optimizer"]
+        ddpm, fused = optimize(ddpm, optimizer=opt, dtype=dtype)
+        ddpm.train()
+
+        def train_step():
+            fused.zero_grad()
+            loss = ddpm.training_step([xt, yt])
+            loss.backward()
+            fused.step()
+            return loss
+
+        for _ in range(min(args.warmup, 2)):
+            train_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.train_steps):
+            loss = train_step()
+        g1.record()
+        barrier()
+        ms_train = g0.elapsed_time(g1)
+        train = {"ms": ms_train, "batch": Bt, "steps": args.train_steps, "loss": float(loss)}
+
+    # ---- reduce over ranks (max time)
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    ms = max_over_ranks(ms)
+    ms_e2e = max_over_ranks(ms_e2e)
+    if train is not None:
+        train["ms"] = max_over_ranks(train["ms"])
+
+    if rank == 0:
+        conv = prof.get("conv", {"ms": 0.0, "flops": 0.0, "launches": 0})
+        attn = prof.get("attention", {"ms": 0.0, "flops": 0.0, "launches": 0})
+        gn = prof.get("gn_apply", {"ms": 0.0, "bytes": 0.0, "launches": 0})
+        total_prof_ms = sum(v["ms"] for v in prof.values())
+        conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"] if dtype == torch.bfloat16 else None
+        flops_per_eval = (conv["flops"] + attn["flops"]) / B
+        roofline = {
+            "kernel": "conv_nd implicit GEMM (forward)", "bound": "tensor", "achieved": conv_tflops, "peak": peak,
+            "unit": "TFLOP/s", "frac": (conv_tflops / peak) if peak else None, "traffic": None,
+            "peak_source": pk["source"] + " (bf16 sustained)" if peak else "n/a for the fp32 CUDA-core engine",
+            "launches_per_eval": conv["launches"], "share_of_eval_time": conv["ms"] / total_prof_ms if total_prof_ms else None,
+            "algorithmic_gflop_per_eval_per_sample": flops_per_eval / 1e9,
+            "others": {
+                "attention_tflops": attn["flops"] / (attn["ms"] * 1e-3) / 1e12 if attn["ms"] > 0 else 0.0,
+                "attention_share": attn["ms"] / total_prof_ms if total_prof_ms else None,
+                "gn_apply_gbs": gn["bytes"] / (gn["ms"] * 1e-3) / 1e9 if gn["ms"] > 0 else 0.0,
+                "gn_apply_frac_of_hbm_peak": (gn["bytes"] / (gn["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]) if gn["ms"] > 0 else None,
+                "gn_share": (gn["ms"] + prof.get("gn_stats", {"ms": 0.0})["ms"]) / total_prof_ms if total_prof_ms else None,
+            },
+        }
+        cpu = cpu_baseline_leg() if (world == 1 and not args.no_cpu_baseline) else None
+        value = world * B * args.steps / (ms * 1e-3)
+        e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": "UNet denoise evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": "working set per eval (>1 GB) exceeds the 126 MB L2; no explicit flush", "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(x_out_pin.numel() * 4)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clk, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if train is not None:
+            line["train"] = {"metric": "train samples/s", "value": world * train["batch"] * train["steps"] / (train["ms"] * 1e-3),
+                             "unit": "samples/s", "ms_per_step": train["ms"] / train["steps"], "batch_per_gpu": train["batch"],
+                             "steps": train["steps"], "last_loss": train["loss"], "collective": "NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("RHO_BENCH_BATCH", "2")), help="sampling batch per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--train-steps", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_STEPS", "3")))
+    ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "1")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl != "reference" and args.warmup < 3:
+        args.warmup = 3   # timing hygiene: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

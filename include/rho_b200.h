@@ -270,7 +270,7 @@ int rho_mse_loss(const void* pred, int pred_dtype, const float* target, int64_t 
 typedef struct rho_adamw_params {
   float* p; const float* g; float* m; float* v; float* shadow;
   int64_t n;
-  float lr, beta1, beta2, eps, weight_decay;
+  double lr, beta1, beta2, eps, weight_decay; /* doubles: 1 - beta2 must be formed in double, as torch does */
   int32_t step;              /* 1-based */
   float ema_decay_t;         /* d * (1 - exp(-step/2000)) */
   float grad_scale;

@@ -7,17 +7,22 @@
 
 namespace rho {
 
-__global__ void __launch_bounds__(256) adamw_ema_kernel(rho_adamw_params a, float bc1, float bc2_sqrt, float one_minus_d) {
+struct AdamScalars {
+  float decay, step_size, beta1, omb1, beta2, omb2, bc2_sqrt, eps, one_minus_d, grad_scale;
+};
+
+__global__ void __launch_bounds__(256) adamw_ema_kernel(rho_adamw_params a, AdamScalars k) {
   const int64_t n4 = a.n >> 2;
-  const float decay = 1.0f - a.lr * a.weight_decay;
-  const float step_size = a.lr / bc1;
+  const float one_minus_d = k.one_minus_d;
+  // torch.optim.AdamW (single-tensor form): p *= 1 - lr*wd; m.lerp_(g, 1-b1); v = b2*v + (1-b2)*g*g;
+  // p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).  All scalars are formed in double on the host, like torch.
   auto upd = [&](float& p, float g, float& m, float& v) {
-    g *= a.grad_scale;
-    p *= decay;
-    m = a.beta1 * m + (1.0f - a.beta1) * g;
-    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
-    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-    p -= step_size * (m / denom);
+    g *= k.grad_scale;
+    p *= k.decay;
+    m = m + (g - m) * k.omb1;
+    v = v * k.beta2 + k.omb2 * g * g;
+    const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+    p -= k.step_size * (m / denom);
   };
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float p[4], g[4], m[4], v[4];
@@ -67,10 +72,19 @@ extern "C" int rho_ema_update(float* shadow, const float* p, int64_t n, float on
 
 extern "C" int rho_adamw_ema_step(const rho_adamw_params* p, rho_stream_t stream) {
   RHO_REQUIRE(p && p->p && p->g && p->m && p->v && p->n > 0 && p->step >= 1, "adamw_ema_step: bad args");
-  const double bc1 = 1.0 - pow((double)p->beta1, (double)p->step);
-  const double bc2 = 1.0 - pow((double)p->beta2, (double)p->step);
+  const double bc1 = 1.0 - pow(p->beta1, (double)p->step);
+  const double bc2 = 1.0 - pow(p->beta2, (double)p->step);
+  AdamScalars k;
+  k.decay = (float)(1.0 - p->lr * p->weight_decay);
+  k.step_size = (float)(p->lr / bc1);
+  k.beta1 = (float)p->beta1; k.omb1 = (float)(1.0 - p->beta1);
+  k.beta2 = (float)p->beta2; k.omb2 = (float)(1.0 - p->beta2);
+  k.bc2_sqrt = (float)sqrt(bc2);
+  k.eps = (float)p->eps;
+  k.one_minus_d = 1.0f - p->ema_decay_t;
+  k.grad_scale = p->grad_scale;
   int blocks = (int)std::min<int64_t>(ceil_div(p->n / 4 + 1, 256), (int64_t)sm_count() * 8);
-  adamw_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p, (float)bc1, (float)sqrt(bc2), 1.0f - p->ema_decay_t);
+  adamw_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p, k);
   RHO_CHECK_LAUNCH("adamw_ema_step");
   return RHO_OK;
 }

@@ -142,7 +142,6 @@ class ConvSpec:
 
 
 _weights_epoch = 0
-_pack_cache = {}
 
 
 def bump_weights_epoch():
@@ -151,11 +150,15 @@ def bump_weights_epoch():
     _weights_epoch += 1
 
 
-def packed_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """[Cout, Cin, *k] fp32 (state-dict layout) -> [Cout, taps, Cin] in ``dtype``; cached per parameter version."""
-    key = (weight.data_ptr(), dtype)
-    ver = (weight._version, _weights_epoch, tuple(weight.shape))
-    hit = _pack_cache.get(key)
+def packed_weight(owner, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[Cout, Cin, *k] fp32 (state-dict layout) -> [Cout, taps, Cin] in ``dtype``.
+
+    The packed copy is cached ON the owning module (``owner``), keyed by the parameter's version counter, its
+    address and the optimizer epoch -- never in a global table, where a recycled device address of a different
+    model could alias a stale entry."""
+    cache = owner.__dict__.setdefault("_rho_packed", {})
+    ver = (weight._version, _weights_epoch, weight.data_ptr(), tuple(weight.shape))
+    hit = cache.get(dtype)
     if hit is not None and hit[0] == ver:
         return hit[1]
     w = weight.detach()
@@ -163,10 +166,10 @@ def packed_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         w = w.float().contiguous()
     Cout, Cin = w.shape[0], w.shape[1]
     taps = w.numel() // (Cout * Cin)
-    out = hit[1] if (hit is not None and hit[1].shape == (Cout, taps, Cin)) else torch.empty(
+    out = hit[1] if (hit is not None and hit[1].shape == (Cout, taps, Cin) and hit[1].device == w.device) else torch.empty(
         (Cout, taps, Cin), dtype=dtype, device=w.device)
     L.check(L.lib().rho_conv_pack_weight(w.data_ptr(), out.data_ptr(), _DT[dtype], Cout, Cin, taps, stream()), "conv_pack_weight")
-    _pack_cache[key] = (ver, out)
+    cache[dtype] = (ver, out)
     return out
 
 
@@ -194,7 +197,54 @@ def conv_out_shape(x_shape, spec: ConvSpec, Cout):
     return (x_shape[0], *out, Cout)
 
 
+class KernelProfiler:
+    """Optional per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline)."""
+
+    def __init__(self):
+        self.records = []   # (kind, name, algorithmic flops, algorithmic bytes, start event, end event)
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def end(self, kind, name, flops, nbytes, start):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.records.append((kind, name, flops, nbytes, start, ev))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, name, flops, nbytes, s, e in self.records:
+            d = out.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+profiler: Optional[KernelProfiler] = None
+
+
 def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False):
+    if profiler is not None:
+        ev = profiler.begin()
+        y = _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32)
+        taps = 1
+        for k in spec.kernel:
+            taps *= k
+        cin = x.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+        m = y.numel() // Cout
+        nbytes = x.numel() * x.element_size() + (x2.numel() * x2.element_size() if x2 is not None else 0) + y.numel() * y.element_size() \
+            + wp.numel() * wp.element_size() + (residual.numel() * residual.element_size() if residual is not None else 0)
+        profiler.end("conv", f"conv{spec.dims}d_k{spec.kernel[-1]}_{cin}->{Cout}", 2.0 * m * Cout * cin * taps, nbytes, ev)
+        return y
+    return _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32)
+
+
+def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False):
     _need_cuda(x, x2, wp, bias, residual)
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous()) and (residual is None or residual.is_contiguous())
     out_dtype = torch.float32 if y_f32 else x.dtype
@@ -231,30 +281,34 @@ def conv_backward(x, x2, wp, dy, spec: ConvSpec, Cout, need_dx, need_dw, need_db
 
 
 class ConvFn(torch.autograd.Function):
-    """y = conv_nd(cat(x, x2)) + bias (+ residual); see rho_conv_fwd in include/rho_b200.h."""
+    """y = conv_nd(cat(x, x2)) + bias (+ residual); see rho_conv_fwd in include/rho_b200.h.
+    ``wp`` is the packed copy of ``weight`` (:func:`packed_weight`); ``weight`` itself only receives the gradient."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, bias, residual, spec, compute_dtype, engine, y_f32):
-        wp = packed_weight(weight, compute_dtype)
+    def forward(ctx, x, x2, weight, wp, bias, residual, spec, engine, y_f32):
         Cout = weight.shape[0]
         b = bias.detach().float() if bias is not None else None
         y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32)
-        ctx.save_for_backward(x, x2, weight)
-        ctx.spec, ctx.compute_dtype, ctx.engine, ctx.has_bias, ctx.has_res = spec, compute_dtype, engine, bias is not None, residual is not None
-        ctx.y_f32 = y_f32
+        ctx.save_for_backward(x, x2, wp)
+        ctx.spec, ctx.engine, ctx.has_bias, ctx.has_res = spec, engine, bias is not None, residual is not None
+        ctx.w_shape = tuple(weight.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, x2, weight = ctx.saved_tensors
+        x, x2, wp = ctx.saved_tensors
         if dy.dtype != x.dtype:  # y_f32 head: gradient arrives in fp32
             dy = cast(dy, x.dtype)
-        wp = packed_weight(weight, ctx.compute_dtype)
         need_dx = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
-        dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, weight.shape[0], need_dx, ctx.needs_input_grad[2],
-                                        ctx.has_bias and ctx.needs_input_grad[3], tuple(weight.shape), ctx.engine)
-        dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
-        return dx, dx2, dw, db, dres, None, None, None, None
+        dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, ctx.w_shape[0], need_dx, ctx.needs_input_grad[2],
+                                        ctx.has_bias and ctx.needs_input_grad[4], ctx.w_shape, ctx.engine)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
+        return dx, dx2, dw, None, db, dres, None, None, None
+
+
+def conv(owner, x, x2, weight, bias, residual, spec, dtype, engine=L.CONV_AUTO, y_f32=False):
+    """conv_nd through the autograd tape; ``owner`` is the module that holds ``weight`` (packed-weight cache)."""
+    return ConvFn.apply(x, x2, weight, packed_weight(owner, weight, dtype), bias, residual, spec, engine, y_f32)
 
 
 def cast(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -305,6 +359,15 @@ def gn_forward(x, x2, gamma, beta, film, pre_add, act, out_dtype, groups=32, eps
     p = _gn_params(x, x2, gamma, beta, film, pre_add, act, stats, y, groups, eps)
     ws = workspace(L.lib().rho_gn_workspace_bytes(C.byref(p)), x.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    if profiler is not None:
+        in_bytes = x.numel() * x.element_size() + (x2.numel() * x2.element_size() if x2 is not None else 0)
+        ev = profiler.begin()
+        L.check(L.lib().rho_gn_stats(C.byref(p), stream()), "gn_stats")
+        profiler.end("gn_stats", "gn_stats", 0.0, in_bytes, ev)
+        ev = profiler.begin()
+        L.check(L.lib().rho_gn_apply(C.byref(p), stream()), "gn_apply")
+        profiler.end("gn_apply", "gn_apply", 0.0, in_bytes + y.numel() * y.element_size(), ev)
+        return y, stats
     L.check(L.lib().rho_gn_stats(C.byref(p), stream()), "gn_stats")
     L.check(L.lib().rho_gn_apply(C.byref(p), stream()), "gn_apply")
     return y, stats
@@ -360,12 +423,16 @@ class AttentionFn(torch.autograd.Function):
         N, T, W3 = qkv.shape
         ch = W3 // (3 * heads)
         out = torch.empty((N, T, heads * ch), dtype=qkv.dtype, device=qkv.device)
-        need_lse = qkv.requires_grad
+        need_lse = ctx.needs_input_grad[0]
         lse = torch.empty((N, heads, T), dtype=torch.float32, device=qkv.device) if need_lse else None
         p = L.AttnParams()
         p.N, p.T, p.heads, p.ch, p.order, p.dtype = N, T, heads, ch, order, dt(qkv)
         p.qkv, p.out, p.lse = ptr(qkv), ptr(out), ptr(lse)
+        ev = profiler.begin() if profiler is not None else None
         L.check(L.lib().rho_attention_fwd(C.byref(p), stream()), "attention_fwd")
+        if ev is not None:
+            profiler.end("attention", f"attn_T{T}_ch{ch}", 4.0 * N * heads * T * T * ch,
+                         (qkv.numel() + out.numel()) * qkv.element_size(), ev)
         ctx.save_for_backward(qkv, out, lse)
         ctx.dims = (N, T, heads, ch, order)
         return out
@@ -530,7 +597,7 @@ class MseLossFn(torch.autograd.Function):
         target = target.float().contiguous()
         n = pred.numel()
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        dpred = torch.empty_like(pred) if pred.requires_grad else None
+        dpred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
         ws = workspace(L.lib().rho_mse_workspace_bytes(n), pred.device)
         L.check(L.lib().rho_mse_loss(pred.data_ptr(), dt(pred), target.data_ptr(), n, loss.data_ptr(), ptr(dpred), 1.0, ws.data_ptr(),
                                      ws.numel(), stream()), "mse_loss")

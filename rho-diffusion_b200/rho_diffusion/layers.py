@@ -79,7 +79,7 @@ class _ConvMixin:
 
     def forward_cl(self, x, x2=None, residual=None, up=1, y_f32=False, ctx: ExecCtx = None):
         ctx = ctx or module_ctx(self)
-        return _ops().ConvFn.apply(x, x2, self.weight, self.bias, residual, self._spec(up), ctx.dtype, ctx.engine, y_f32)
+        return _ops().conv(self, x, x2, self.weight, self.bias, residual, self._spec(up), ctx.dtype, ctx.engine, y_f32)
 
     def forward(self, x):
         ops = _ops()

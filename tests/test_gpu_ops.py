@@ -158,7 +158,8 @@ def test_conv_fwd_bwd(ops, dtype, case):
     x2d = cl(x2.detach()).to(dtype).requires_grad_(True) if C2 else None
     wd, bd = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
     resd = cl(res).to(dtype).requires_grad_(True) if use_res else None
-    y = ops.ConvFn.apply(xd, x2d, wd, bd, resd, spec, dtype, 0, False)
+    holder = torch.nn.Module()
+    y = ops.conv(holder, xd, x2d, wd, bd, resd, spec, dtype, 0, False)
     assert tuple(nc(y).shape) == tuple(ref.shape)
     y.backward(cl(dy).to(dtype))
     tol = TOL[dtype]
@@ -281,10 +282,10 @@ def test_q_sample_p_sample_mse(ops):
     for dtype in (torch.float32, torch.bfloat16):
         pred = randn(4, 1000, seed=43).to(dtype)
         tgt = randn(4, 1000, seed=44)
-        pr = pred.float().requires_grad_(True)
+        pr = pred.float().clone().requires_grad_(True)
         ref = O.mse_loss(pr, tgt)
         (ref * 3.0).backward()
-        pd = pred.to(DEV).requires_grad_(True)
+        pd = pred.detach().clone().to(DEV).requires_grad_(True)
         loss = ops.MseLossFn.apply(pd, tgt.to(DEV))
         (loss * 3.0).backward()
         assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, float(ref))
@@ -302,4 +303,4 @@ def test_adamw_ema_kernel(ops):
         ops.adamw_ema_step(pd, gd, md, vd, sd, step, 2e-4, (0.9, 0.999), 1e-8, 1e-2, ema_decay_t=O.ema_decay(step), grad_scale=0.5)
     assert (pd.cpu() - p).abs().max() < 1e-6
     assert (sd.cpu() - sh).abs().max() < 1e-6
-    assert rel_err(md, m) < 1e-5 and rel_err(vd, v) < 1e-5
+    assert rel_err(md, m) < 2e-6 and rel_err(vd, v) < 2e-6
