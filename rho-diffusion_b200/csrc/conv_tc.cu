@@ -1,9 +1,459 @@
-// placeholder replaced below by the tcgen05 engine
+// conv_nd on the 5th-generation tensor cores: TMA-fed tcgen05 implicit GEMM with TMEM accumulators (sm_100a).
+//
+//   D[128 output positions x BLOCK_N out-channels] += A[128 x BLOCK_K] * B[BLOCK_N x BLOCK_K]^T   per (tap, channel block)
+//
+// * activations are channels-last bf16; an M tile is a box of 128 output positions (bn x bd x bh x bw, all powers of
+//   two) of the 5-D tensor (N, D, H, W, C).  For every filter tap the A tile is ONE 5-D TMA box load at the box origin
+//   shifted by the tap offset; out-of-bounds coordinates are zero-filled by the TMA unit, which is exactly "same"
+//   padding -- no im2col buffer, no halo code, no predication.  The box lands in shared memory row-major (one
+//   128-byte row of 64 channels per position) with the 128-byte swizzle the UMMA K-major descriptor expects.
+// * the skip concat (unet_v2.py:729) is a second tensor map: the K loop walks the channels of x, then of x2.
+// * B tiles come from the packed weights [Cout][taps*Cin] through a 2-D tensor map.
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> +bias (+residual) -> bf16 -> 16-byte stores).  smem ring of STAGES (A, B) pairs with
+//   full/empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it have retired.
+// * two CTAs per SM (<= 96 KB smem, <= 256 TMEM columns each) so that one CTA's epilogue overlaps the other's MMAs.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include "conv_geom.cuh"
+
 namespace rho {
-bool conv_fwd_tc_supported(const ConvGeom&, const rho_conv_params*) { return false; }
-int conv_fwd_tc(const ConvGeom&, const rho_conv_params*, cudaStream_t) { return fail(RHO_ERR_UNSUPPORTED, "tcgen05 engine not built"); }
+
+constexpr int TC_BM = 128;
+constexpr int TC_MAX_TAPS = 28;
+constexpr int TC_MAX_MAPS = 4;
+
+struct TcTap {
+  int16_t dn, dd, dh, dw;  // coordinate offsets of this tap (in the coordinate system of its tensor map)
+  int32_t map;             // which tensor-map set (parity class for strided inputs)
+  int32_t kofs;            // K offset (elements) of channel 0 of this tap in a packed weight row
+};
+
+struct TcParams {
+  int bn, bd, bh, bw;      // tile box (product 128)
+  int lbw, lbh, lbd;       // log2 of bw, bh, bd
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  int N, Gd, Gh, Gw;       // extents of the output grid this launch covers
+  int os_d, os_h, os_w, oo_d, oo_h, oo_w;   // output position = grid * os + oo
+  int Do, Ho, Wo;
+  int Cout;                // row pitch (channels) of the output tensor(s)
+  int C1, C2;              // K channels per source
+  int n_blocks;            // Cout / BLOCK_N
+  int out_split;           // > 0: output channels >= out_split go to y2 (pitch Cout - out_split), else y (pitch out_split)
+  int ntaps;
+  TcTap taps[TC_MAX_TAPS];
+};
+
+struct TcMaps {
+  CUtensorMap a[TC_MAX_MAPS][2];
+  CUtensorMap w;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand, swizzle = row bytes (128 / 64 / 32)
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  constexpr uint64_t layout = ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;             // stride byte offset: 8 rows
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ uint32_t umma_idesc() {
+  return (1u << 4)                      // D format: F32
+         | (1u << 7) | (1u << 10)      // A, B format: BF16
+         | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int BLOCK_K, int STAGES, typename TOut>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
+                                                      const float* __restrict__ bias, const bf16* __restrict__ residual,
+                                                      TOut* __restrict__ y, TOut* __restrict__ y2) {
+  constexpr int ROW_BYTES = BLOCK_K * 2;
+  constexpr int A_BYTES = TC_BM * ROW_BYTES;
+  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to 1024 (the launch adds 1 KB of slack)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % p.n_blocks;
+  int mt = blockIdx.x / p.n_blocks;
+  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th = mt % p.tiles_h; mt /= p.tiles_h;
+  const int td = mt % p.tiles_d; mt /= p.tiles_d;
+  const int tn = mt;
+  const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = tn * p.bn;
+  const int kb_per_tap = (p.C1 + p.C2) / BLOCK_K;
+  const int num_kb = p.ntaps * kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BLOCK_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const TcTap tap = p.taps[t];
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          const int c = kb * BLOCK_K;
+          const int src = c >= p.C1 ? 1 : 0;
+          const int cc = src ? c - p.C1 : c;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_5d(sa, &maps.a[tap.map][src], &full_bar[stage], cc, w0 + tap.dw, h0 + tap.dh, d0 + tap.dd, n0 + tap.dn);
+          tma_load_2d(sa + A_BYTES, &maps.w, &full_bar[stage], tap.kofs + c, nb * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = umma_desc<ROW_BYTES>(sa);
+        const uint64_t bdesc = umma_desc<ROW_BYTES>(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w % 4) .. +31 =====
+    const int et = threadIdx.x - 64;   // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) sbias[i] = bias ? bias[nb * BLOCK_N + i] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const int iw = r & (p.bw - 1), ih = (r >> p.lbw) & (p.bh - 1), id = (r >> (p.lbw + p.lbh)) & (p.bd - 1),
+              in = r >> (p.lbw + p.lbh + p.lbd);
+    const int gw = w0 + iw, gh = h0 + ih, gd = d0 + id, gn = n0 + in;
+    const bool valid = gw < p.Gw && gh < p.Gh && gd < p.Gd && gn < p.N;
+    const long long pos = (((long long)gn * p.Do + (gd * p.os_d + p.oo_d)) * p.Ho + (gh * p.os_h + p.oo_h)) * p.Wo + (gw * p.os_w + p.oo_w);
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);   // warp-collective: all lanes execute
+      if (valid) {
+        const int ch = nb * BLOCK_N + c0;   // first global output channel of this chunk
+        TOut* dst;
+        const bf16* res = nullptr;
+        if (p.out_split > 0 && ch >= p.out_split) dst = y2 + pos * (p.Cout - p.out_split) + (ch - p.out_split);
+        else dst = y + pos * (p.out_split > 0 ? p.out_split : p.Cout) + ch;
+        if (residual) res = residual + pos * p.Cout + ch;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[c0 + j + e];
+          if (res) {
+            float rr[4];
+            load4(res + j, rr);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += rr[e];
+          }
+          store4(dst + j, o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  });
+  return fn;
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+static int pick_block_k(int C1, int C2) {
+  for (int bk : {64, 32, 16}) {
+    if (C1 % bk == 0 && (C2 == 0 || C2 % bk == 0)) return bk;
+  }
+  return 0;
+}
+static int pick_block_n(int Cout) {
+  for (int bn : {256, 128, 64, 32}) {
+    if (Cout % bn == 0) return bn;
+  }
+  return 0;
+}
+
+static int encode_act_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bn, int bd, int bh, int bw, int bk,
+                          long long sW, long long sH) {
+  // dims (C, W, H, D, N) over a channels-last tensor; sW / sH allow strided (parity) views: element strides in W and H
+  auto enc = get_encode();
+  if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, 0, 0};
+  (void)gstr;
+  return RHO_OK;
+}
+
+struct ActView {
+  const void* base;
+  long long dim[5];      // C, W, H, D, N
+  long long stride[4];   // bytes, for W, H, D, N
+};
+
+static int encode_view(CUtensorMap* m, const ActView& v, const int box[5], int bk) {
+  auto enc = get_encode();
+  if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) { gdim[i] = (cuuint64_t)v.dim[i]; bdim[i] = (cuuint32_t)box[i]; }
+  for (int i = 0; i < 4; ++i) gstr[i] = (cuuint64_t)v.stride[i];
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(v.base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return RHO_OK;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* w, long long Ktot, int rows, int bk, int block_n) {
+  auto enc = get_encode();
+  if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t bdim[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return RHO_OK;
+}
+
+static void pick_tile(TcParams& p) {
+  int rem = TC_BM;
+  p.bw = std::min(rem, pow2_ceil(p.Gw)); rem /= p.bw;
+  p.bh = std::min(rem, pow2_ceil(p.Gh)); rem /= p.bh;
+  p.bd = std::min(rem, pow2_ceil(p.Gd)); rem /= p.bd;
+  p.bn = rem;
+  p.lbw = ilog2(p.bw); p.lbh = ilog2(p.bh); p.lbd = ilog2(p.bd);
+  p.tiles_w = (int)ceil_div(p.Gw, p.bw); p.tiles_h = (int)ceil_div(p.Gh, p.bh); p.tiles_d = (int)ceil_div(p.Gd, p.bd);
+  p.tiles_n = (int)ceil_div(p.N, p.bn);
+}
+
+template <int BLOCK_N, int BLOCK_K, typename TOut>
+static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (TC_BM + BLOCK_N) * BLOCK_K * 2;
+  // ring depth: fill ~96 KB so that two CTAs fit in one SM's 227 KB
+  constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2 : ((96 * 1024 / STAGE_BYTES) > 8 ? 8 : (96 * 1024 / STAGE_BYTES));
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, TOut>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_blocks;
+  if (tiles > 2147483647LL) return fail(RHO_ERR_UNSUPPORTED, "conv_tc: grid too large");
+  kern<<<(unsigned)tiles, 192, SMEM, st>>>(maps, p, bias, residual, y, y2);
+  RHO_CHECK_LAUNCH("conv_fwd_tcgen05");
+  return RHO_OK;
+}
+
+template <typename TOut>
+static int dispatch_tc(int bn, int bk, const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2,
+                       cudaStream_t st) {
+#define RHO_TC(BN, BK) \
+  if (bn == BN && bk == BK) return launch_tc<BN, BK, TOut>(maps, p, bias, residual, y, y2, st)
+  RHO_TC(256, 64); RHO_TC(128, 64); RHO_TC(64, 64); RHO_TC(32, 64);
+  RHO_TC(256, 32); RHO_TC(128, 32); RHO_TC(64, 32); RHO_TC(32, 32);
+#undef RHO_TC
+  return fail(RHO_ERR_UNSUPPORTED, "conv_tc: no kernel for BLOCK_N=%d BLOCK_K=%d", bn, bk);
+}
+
+static bool tc_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RHO_DISABLE_TCGEN05");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p) {
+  if (tc_disabled()) return false;
+  if (p->act_dtype != RHO_BF16 || p->w_dtype != RHO_BF16 || p->y_f32) return false;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.ud != 1 || g.uh != 1 || g.uw != 1) return false;   // strided / upsampled: SIMT for now
+  const int bk = pick_block_k(g.C1, g.C2);
+  if (bk < 32) return false;
+  if (pick_block_n(g.Cout) == 0) return false;
+  if (g.taps > TC_MAX_TAPS) return false;
+  if (g.N > 32767 || g.D > 32767 || g.H > 32767 || g.W > 32767) return false;
+  return get_encode() != nullptr;
+}
+
+int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
+  const int bk = pick_block_k(g.C1, g.C2), bn = pick_block_n(g.Cout);
+  TcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.N = g.N; tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
+  tp.os_d = tp.os_h = tp.os_w = 1;
+  tp.Do = g.Do; tp.Ho = g.Ho; tp.Wo = g.Wo;
+  tp.Cout = g.Cout; tp.C1 = g.C1; tp.C2 = g.C2;
+  tp.n_blocks = g.Cout / bn;
+  pick_tile(tp);
+  tp.ntaps = g.taps;
+  for (int t = 0; t < g.taps; ++t) {
+    const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+    tp.taps[t].dn = 0;
+    tp.taps[t].dd = (int16_t)(kd - g.pd); tp.taps[t].dh = (int16_t)(kh - g.ph); tp.taps[t].dw = (int16_t)(kw - g.pw);
+    tp.taps[t].map = 0;
+    tp.taps[t].kofs = t * g.Cin;
+  }
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
+  auto view = [&](const void* base, int C) {
+    ActView v;
+    v.base = base;
+    v.dim[0] = C; v.dim[1] = g.W; v.dim[2] = g.H; v.dim[3] = g.D; v.dim[4] = g.N;
+    v.stride[0] = (long long)C * 2; v.stride[1] = v.stride[0] * g.W; v.stride[2] = v.stride[1] * g.H; v.stride[3] = v.stride[2] * g.D;
+    return v;
+  };
+  int rc = encode_view(&maps.a[0][0], view(p->x, g.C1), box, bk);
+  if (rc) return rc;
+  if (g.C2) {
+    rc = encode_view(&maps.a[0][1], view(p->x2, g.C2), box, bk);
+    if (rc) return rc;
+  }
+  rc = encode_weight_map(&maps.w, p->w_packed, g.Ktot, g.Cout, bk, bn);
+  if (rc) return rc;
+  return dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
+}
+
 bool conv_dgrad_tc_supported(const ConvGeom&, const rho_conv_bwd_params*) { return false; }
-int conv_dgrad_tc(const ConvGeom&, const rho_conv_bwd_params*, cudaStream_t) { return fail(RHO_ERR_UNSUPPORTED, "tcgen05 engine not built"); }
+int conv_dgrad_tc(const ConvGeom&, const rho_conv_bwd_params*, cudaStream_t) { return fail(RHO_ERR_UNSUPPORTED, "conv_dgrad_tc: not built"); }
 size_t conv_dgrad_tc_workspace(const ConvGeom&, const rho_conv_bwd_params*) { return 0; }
+
 }  // namespace rho

@@ -166,8 +166,11 @@ def packed_weight(owner, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tens
         w = w.float().contiguous()
     Cout, Cin = w.shape[0], w.shape[1]
     taps = w.numel() // (Cout * Cin)
-    out = hit[1] if (hit is not None and hit[1].shape == (Cout, taps, Cin) and hit[1].device == w.device) else torch.empty(
-        (Cout, taps, Cin), dtype=dtype, device=w.device)
+    if hit is not None and hit[1].shape == (Cout, taps, Cin) and hit[1].device == w.device:
+        out = hit[1]
+    else:
+        with torch.inference_mode(False):   # cached across inference and training: must not be an inference tensor
+            out = torch.empty((Cout, taps, Cin), dtype=dtype, device=w.device)
     L.check(L.lib().rho_conv_pack_weight(w.data_ptr(), out.data_ptr(), _DT[dtype], Cout, Cin, taps, stream()), "conv_pack_weight")
     cache[dtype] = (ver, out)
     return out

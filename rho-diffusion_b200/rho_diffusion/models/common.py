@@ -23,7 +23,8 @@ def sinosoidal_position_embedding(t: torch.Tensor, dim: int, wavelength: int = 1
 
     key = (dim, wavelength, t.device)
     if key not in _omega_cache:
-        _omega_cache[key] = omega_table(dim, wavelength).to(t.device)
+        with torch.inference_mode(False):
+            _omega_cache[key] = omega_table(dim, wavelength).to(t.device)
     return ops.timestep_embedding(t, dim, _omega_cache[key])
 
 

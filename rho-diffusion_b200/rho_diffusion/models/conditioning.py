@@ -46,8 +46,9 @@ class MultiEmbeddings(nn.Module):
         if tabs is None:
             if self.parameter_space is None:
                 raise RuntimeError("MultiEmbeddings.forward needs a parameter_space to map values to indices")
-            tabs = [torch.tensor([float(v) for v in self.parameter_space[key]], dtype=torch.float32, device=device)
-                    for key in self.embedding_layers.keys()]
+            with torch.inference_mode(False):
+                tabs = [torch.tensor([float(v) for v in self.parameter_space[key]], dtype=torch.float32, device=device)
+                        for key in self.embedding_layers.keys()]
             self._value_tables[device] = tabs
         return tabs
 

@@ -127,6 +127,12 @@ CONV_CASES = [
     (2, 1, 64, 0, 32, (5, 6), 3, 1, 2, False),         # Upsample 2-D
     (1, 2, 128, 0, 384, (16,), 1, 1, 1, False),        # attention qkv projection (Conv1d k=1)
     (1, 2, 128, 0, 128, (16,), 1, 1, 1, True),         # attention proj_out + residual
+    # tcgen05 engine shapes (bf16): several M tiles and N blocks, ragged spatial dims, 64/32-wide K blocks, concat
+    (3, 2, 128, 0, 256, (5, 9, 20), 3, 1, 1, True),
+    (2, 3, 64, 64, 512, (24, 16), 3, 1, 1, False),
+    (1, 2, 256, 0, 64, (100,), 3, 1, 1, False),
+    (3, 1, 96, 32, 96, (4, 6, 16), 3, 1, 1, False),
+    (2, 1, 512, 256, 256, (8, 8), 1, 1, 1, False),
 ]
 
 
@@ -171,6 +177,26 @@ def test_conv_fwd_bwd(ops, dtype, case):
     assert rel_err(bd.grad, b.grad) < 4 * tol
     if use_res:
         assert rel_err(nc(resd.grad), dy) < 1e-6
+
+
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 11, 13, 14, 15, 16, 17)])
+def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
+    """The bf16 shapes above must run on the tcgen05 engine (forced: an unsupported shape would raise), and agree with
+    the CUDA-core engine on the same inputs to fp32-accumulation rounding."""
+    from rho_diffusion.b200 import _lib
+    dims, N, C1, C2, Cout, sp, k, stride, up, use_res = case
+    x1 = cl(randn(N, C1, *sp, seed=10)).bfloat16()
+    x2 = cl(randn(N, C2, *sp, seed=11)).bfloat16() if C2 else None
+    w = (randn(Cout, C1 + C2, *([k] * dims), seed=12) / math.sqrt((C1 + C2) * k ** dims)).to(DEV)
+    b = (0.1 * randn(Cout, seed=13)).to(DEV)
+    spec = ops.ConvSpec.make(dims, k, stride, up)
+    holder = torch.nn.Module()
+    wp = ops.packed_weight(holder, w, torch.bfloat16)
+    res = torch.randn(ops.conv_out_shape(x1.shape, spec, Cout), device=DEV).bfloat16() if use_res else None
+    y_tc = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_TCGEN05)
+    y_simt = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_SIMT)
+    assert rel_err(y_tc, y_simt) < 1e-2          # both round the same fp32 sums to bf16 (different summation order)
+    assert float((y_tc.float() - y_simt.float()).abs().mean() / y_simt.float().abs().mean()) < 1e-3
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
