@@ -263,10 +263,21 @@ def run_b200(args):
         ms_e2e = f0.elapsed_time(f1)
 
         # ---- per-kernel roofline pass: one eager eval with CUDA events around every conv / GN / attention launch
-        ops.profiler = ops.KernelProfiler()
         tt = torch.full((B,), 500, dtype=torch.int64, device=device)
+        ddpm.backbone(x_dev, tt, cond_dev)      # untimed: fills this stream's allocator pool (no cudaMalloc in the timed pass)
+        torch.cuda.synchronize()
+        ops.profiler = ops.KernelProfiler()
         ddpm.backbone(x_dev, tt, cond_dev)
         prof = ops.profiler.summary()
+        if args.launch_table and rank == 0:
+            rows = {}
+            for kind, name, flops, nbytes, s0, s1 in ops.profiler.records:
+                r = rows.setdefault((kind, name), [0, 0.0, 0.0, 0.0])
+                r[0] += 1; r[1] += s0.elapsed_time(s1); r[2] += flops; r[3] += nbytes
+            with open(args.launch_table, "w") as fh:
+                fh.write("kind,name,launches,total_ms,tflops,gbs\n")
+                for (kind, name), r in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+                    fh.write(f"{kind},{name},{r[0]},{r[1]:.4f},{r[2] / (r[1] * 1e-3) / 1e12 if r[1] else 0:.2f},{r[3] / (r[1] * 1e-3) / 1e9 if r[1] else 0:.1f}\n")
         ops.profiler = None
 
     # ---- training leg (samples/s): q_sample -> UNet fwd/bwd -> fused AdamW (+ flat-gradient all-reduce for N > 1)
@@ -369,6 +380,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_STEPS", "3")))
     ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch-table", default=None, help="write a per-kernel-shape table (CUDA-event times of one eager eval) to this CSV")
     args = ap.parse_args()
     if args.impl != "reference" and args.warmup < 3:
         args.warmup = 3   # timing hygiene: at least 3 warm-up steps

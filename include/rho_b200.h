@@ -90,6 +90,8 @@ typedef struct rho_conv_params {
   const void* x;
   const void* x2;
   const void* w_packed;      /* from rho_conv_pack_weight */
+  const void* w_aux;         /* optional: from rho_conv_pack_weight_aux (pre-summed weights of the fused-upsample
+                                decomposition used by the tcgen05 engine); NULL selects the CUDA-core gather instead */
   const float* bias;         /* [Cout] or NULL */
   const void* residual;      /* [N,Do,Ho,Wo,Cout] or NULL */
   void* y;                   /* [N,Do,Ho,Wo,Cout] */
@@ -100,6 +102,10 @@ typedef struct rho_conv_params {
 /* packed forward weights: [Cout][taps][Cin] (K-major rows, K = tap*Cin + ci, tap = (kd*KH + kh)*KW + kw).
  * `w` is the reference state_dict tensor, fp32 [Cout, Cin, kd, kh, kw]. */
 int rho_conv_pack_weight(const float* w, void* packed, int packed_dtype, int32_t Cout, int32_t Cin, int32_t taps, rho_stream_t stream);
+/* engine-specific second packing (see w_aux): bytes needed for this geometry (0: none exists), and the packing itself.
+ * `w` is the fp32 state_dict tensor; sums are formed in fp32 and rounded once. */
+size_t rho_conv_aux_weight_bytes(const rho_conv_params* p);
+int rho_conv_pack_weight_aux(const rho_conv_params* p, const float* w, void* aux, rho_stream_t stream);
 size_t rho_conv_workspace_bytes(const rho_conv_params* p);
 int rho_conv_fwd(const rho_conv_params* p, rho_stream_t stream);
 /* which engine rho_conv_fwd would use for p (RHO_CONV_SIMT or RHO_CONV_TCGEN05) */

@@ -7,12 +7,17 @@ int conv_fwd_simt(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
 int conv_dgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 int conv_wgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 size_t conv_wgrad_simt_workspace(const ConvGeom& g);
+// conv_small.cu
+bool conv_small_supported(const ConvGeom& g, const rho_conv_params* p);
+int conv_small_fwd(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
 // conv_tc.cu
 bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p);
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
 bool conv_dgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
 int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 size_t conv_dgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
+size_t conv_aux_weight_bytes(const ConvGeom& g, const rho_conv_params* p);
+int conv_pack_weight_aux(const ConvGeom& g, const rho_conv_params* p, const float* w, void* out, cudaStream_t st);
 
 static int validate_fwd(const rho_conv_params* p, ConvGeom& g) {
   int rc = make_geom(p, g);
@@ -35,6 +40,20 @@ int rho_conv_engine_for(const rho_conv_params* p) {
   return conv_fwd_tc_supported(g, p) ? RHO_CONV_TCGEN05 : RHO_CONV_SIMT;
 }
 
+size_t rho_conv_aux_weight_bytes(const rho_conv_params* p) {
+  ConvGeom g;
+  if (make_geom(p, g)) return 0;
+  return conv_aux_weight_bytes(g, p);
+}
+
+int rho_conv_pack_weight_aux(const rho_conv_params* p, const float* w, void* aux, rho_stream_t stream) {
+  ConvGeom g;
+  int rc = make_geom(p, g);
+  if (rc) return rc;
+  RHO_REQUIRE(w && aux, "conv_pack_weight_aux: null pointer");
+  return conv_pack_weight_aux(g, p, w, aux, as_stream(stream));
+}
+
 size_t rho_conv_workspace_bytes(const rho_conv_params* p) {
   (void)p;
   return 0;
@@ -47,6 +66,8 @@ int rho_conv_fwd(const rho_conv_params* p, rho_stream_t stream) {
   const bool tc_ok = conv_fwd_tc_supported(g, p);
   if (p->engine == RHO_CONV_TCGEN05 && !tc_ok) return fail(RHO_ERR_UNSUPPORTED, "conv_fwd: tcgen05 engine does not take this shape");
   if (p->engine != RHO_CONV_SIMT && tc_ok) return conv_fwd_tc(g, p, as_stream(stream));
+  // degenerate first / last layers (Cin <= 4 or Cout <= 4): HBM-bound direct convolution
+  if (p->engine == RHO_CONV_AUTO && p->act_dtype == p->w_dtype && conv_small_supported(g, p)) return conv_small_fwd(g, p, as_stream(stream));
   return conv_fwd_simt(g, p, as_stream(stream));
 }
 

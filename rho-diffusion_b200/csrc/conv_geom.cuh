@@ -42,4 +42,52 @@ inline int make_geom(const rho_conv_params* p, ConvGeom& g) {
   return RHO_OK;
 }
 
+struct RowPos {
+  int n, d, h, w;
+  bool valid;
+};
+
+__device__ __forceinline__ RowPos decode_out(const ConvGeom& g, long long m) {
+  RowPos r;
+  r.valid = m < g.M;
+  long long t = r.valid ? m : 0;
+  r.w = (int)(t % g.Wo); t /= g.Wo;
+  r.h = (int)(t % g.Ho); t /= g.Ho;
+  r.d = (int)(t % g.Do); t /= g.Do;
+  r.n = (int)t;
+  return r;
+}
+__device__ __forceinline__ RowPos decode_in(const ConvGeom& g, long long m) {
+  RowPos r;
+  r.valid = m < g.Min;
+  long long t = r.valid ? m : 0;
+  r.w = (int)(t % g.W); t /= g.W;
+  r.h = (int)(t % g.H); t /= g.H;
+  r.d = (int)(t % g.D); t /= g.D;
+  r.n = (int)t;
+  return r;
+}
+
+// forward gather: input position (pre-upsample) feeding output `r` through tap (kd,kh,kw); -1 if padding
+__device__ __forceinline__ long long fwd_src(const ConvGeom& g, const RowPos& r, int tap) {
+  int kw = tap % g.kw, kh = (tap / g.kw) % g.kh, kd = tap / (g.kw * g.kh);
+  int pd = r.d * g.sd + kd - g.pd, ph = r.h * g.sh + kh - g.ph, pw = r.w * g.sw + kw - g.pw;
+  if (!r.valid || pd < 0 || pd >= g.Du || ph < 0 || ph >= g.Hu || pw < 0 || pw >= g.Wu) return -1;
+  int id = pd / g.ud, ih = ph / g.uh, iw = pw / g.uw;
+  return (((long long)r.n * g.D + id) * g.H + ih) * g.W + iw;
+}
+
+// dgrad gather: output position whose tap `tap` reads upsampled child `child` of input position `r`; -1 if none
+__device__ __forceinline__ long long dgrad_src(const ConvGeom& g, const RowPos& r, int vt) {
+  int tap = vt % g.taps, child = vt / g.taps;
+  int kw = tap % g.kw, kh = (tap / g.kw) % g.kh, kd = tap / (g.kw * g.kh);
+  int cw = child % g.uw, ch = (child / g.uw) % g.uh, cd = child / (g.uw * g.uh);
+  int td = r.d * g.ud + cd + g.pd - kd, th = r.h * g.uh + ch + g.ph - kh, tw = r.w * g.uw + cw + g.pw - kw;
+  if (!r.valid || td < 0 || th < 0 || tw < 0) return -1;
+  if ((td % g.sd) | (th % g.sh) | (tw % g.sw)) return -1;
+  int od = td / g.sd, oh = th / g.sh, ow = tw / g.sw;
+  if (od >= g.Do || oh >= g.Ho || ow >= g.Wo) return -1;
+  return (((long long)r.n * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+}
+
 }  // namespace rho

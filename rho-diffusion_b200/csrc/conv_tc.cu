@@ -305,17 +305,6 @@ static int pick_block_n(int Cout) {
   return 0;
 }
 
-static int encode_act_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bn, int bd, int bh, int bw, int bk,
-                          long long sW, long long sH) {
-  // dims (C, W, H, D, N) over a channels-last tensor; sW / sH allow strided (parity) views: element strides in W and H
-  auto enc = get_encode();
-  if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-  cuuint64_t gstr[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, 0, 0};
-  (void)gstr;
-  return RHO_OK;
-}
-
 struct ActView {
   const void* base;
   long long dim[5];      // C, W, H, D, N
@@ -401,51 +390,225 @@ static bool tc_disabled() {
   return v == 1;
 }
 
-bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p) {
+// ---- decomposition plans --------------------------------------------------------------------------------
+// A fused nearest-x2 upsample turns the 3-tap filter of an upsampled dim into, per OUTPUT parity p, a 2-tap filter on
+// the un-upsampled input:  p = 0: {x[i-1]*w0, x[i]*(w1+w2)},  p = 1: {x[i]*(w0+w1), x[i+1]*w2}.  One launch per parity
+// class with pre-summed weights ("aux" pack): 12 instead of 27 taps in 3-D (H, W upsampled), 4 instead of 9 in 2-D.
+struct DimTaps {
+  int n;            // reduced taps
+  int off[3];       // input offset of each
+  int cnt[3];       // how many original taps are summed
+  int src[3][2];    // which
+};
+static DimTaps dim_taps(int k, int up, int parity) {
+  DimTaps d;
+  memset(&d, 0, sizeof(d));
+  if (k == 1) { d.n = 1; d.off[0] = 0; d.cnt[0] = 1; d.src[0][0] = 0; return d; }
+  if (up == 1) {
+    d.n = 3;
+    for (int i = 0; i < 3; ++i) { d.off[i] = i - 1; d.cnt[i] = 1; d.src[i][0] = i; }
+    return d;
+  }
+  d.n = 2;
+  if (parity == 0) { d.off[0] = -1; d.cnt[0] = 1; d.src[0][0] = 0; d.off[1] = 0; d.cnt[1] = 2; d.src[1][0] = 1; d.src[1][1] = 2; }
+  else { d.off[0] = 0; d.cnt[0] = 2; d.src[0][0] = 0; d.src[0][1] = 1; d.off[1] = 1; d.cnt[1] = 1; d.src[1][0] = 2; }
+  return d;
+}
+
+struct AuxTable {
+  int nclass, rt, taps, Cin, Cout;
+  int cnt[4][12];
+  int src[4][12][4];
+  int16_t off[4][12][3];   // (dd, dh, dw)
+  int par[4][3];           // output parity per class (d, h, w)
+};
+
+static bool build_up_table(const ConvGeom& g, AuxTable& t) {
+  memset(&t, 0, sizeof(t));
+  if (g.ud != 1) return false;               // the UNet never upsamples depth (unet_v2.py:124-129)
+  const int cls_h = g.uh == 2 ? 2 : 1, cls_w = g.uw == 2 ? 2 : 1;
+  t.nclass = cls_h * cls_w;
+  t.taps = g.taps; t.Cin = g.Cin; t.Cout = g.Cout;
+  for (int c = 0; c < t.nclass; ++c) {
+    const int ph = g.uh == 2 ? c / cls_w : 0, pw = g.uw == 2 ? c % cls_w : 0;
+    t.par[c][0] = 0; t.par[c][1] = ph; t.par[c][2] = pw;
+    const DimTaps dd = dim_taps(g.kd, 1, 0), dh = dim_taps(g.kh, g.uh, ph), dw = dim_taps(g.kw, g.uw, pw);
+    const int rt = dd.n * dh.n * dw.n;
+    if (rt > 12) return false;
+    t.rt = rt;
+    int r = 0;
+    for (int a = 0; a < dd.n; ++a)
+      for (int b = 0; b < dh.n; ++b)
+        for (int e = 0; e < dw.n; ++e, ++r) {
+          t.off[c][r][0] = (int16_t)dd.off[a]; t.off[c][r][1] = (int16_t)dh.off[b]; t.off[c][r][2] = (int16_t)dw.off[e];
+          int n = 0;
+          for (int ia = 0; ia < dd.cnt[a]; ++ia)
+            for (int ib = 0; ib < dh.cnt[b]; ++ib)
+              for (int ie = 0; ie < dw.cnt[e]; ++ie) {
+                if (n >= 4) return false;
+                t.src[c][r][n++] = (dd.src[a][ia] * g.kh + dh.src[b][ib]) * g.kw + dw.src[e][ie];
+              }
+          t.cnt[c][r] = n;
+        }
+  }
+  return true;
+}
+
+// aux[class][co][r*Cin + ci] = sum_{k in src(class, r)} w[co][ci][k]   (w: fp32 state-dict layout)
+__global__ void pack_aux_kernel(AuxTable t, const float* __restrict__ w, bf16* __restrict__ aux) {
+  const long long per_class = (long long)t.Cout * t.rt * t.Cin;
+  const long long total = per_class * t.nclass;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / per_class);
+    long long rem = i % per_class;
+    const int co = (int)(rem / ((long long)t.rt * t.Cin));
+    rem %= (long long)t.rt * t.Cin;
+    const int r = (int)(rem / t.Cin), ci = (int)(rem % t.Cin);
+    float s = 0.f;
+    for (int n = 0; n < t.cnt[c][r]; ++n) s += w[((long long)co * t.Cin + ci) * t.taps + t.src[c][r][n]];
+    aux[i] = __float2bfloat16_rn(s);
+  }
+}
+
+static bool tc_common_ok(const ConvGeom& g, const rho_conv_params* p) {
   if (tc_disabled()) return false;
   if (p->act_dtype != RHO_BF16 || p->w_dtype != RHO_BF16 || p->y_f32) return false;
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.ud != 1 || g.uh != 1 || g.uw != 1) return false;   // strided / upsampled: SIMT for now
-  const int bk = pick_block_k(g.C1, g.C2);
-  if (bk < 32) return false;
-  if (pick_block_n(g.Cout) == 0) return false;
+  if (pick_block_k(g.C1, g.C2) < 32 || pick_block_n(g.Cout) == 0) return false;
   if (g.taps > TC_MAX_TAPS) return false;
   if (g.N > 32767 || g.D > 32767 || g.H > 32767 || g.W > 32767) return false;
   return get_encode() != nullptr;
+}
+
+static bool is_plain(const ConvGeom& g) { return g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1; }
+static bool is_strided(const ConvGeom& g) { return g.sd == 1 && (g.sh == 2 || g.sw == 2) && g.ud == 1 && g.uh == 1 && g.uw == 1; }
+static bool is_upsampled(const ConvGeom& g) { return g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && (g.uh == 2 || g.uw == 2); }
+
+bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p) {
+  if (!tc_common_ok(g, p)) return false;
+  if (is_plain(g) || is_strided(g)) return true;
+  if (is_upsampled(g)) {
+    AuxTable t;
+    return p->w_aux != nullptr && build_up_table(g, t);
+  }
+  return false;
+}
+
+size_t conv_aux_weight_bytes(const ConvGeom& g, const rho_conv_params* p) {
+  if (!tc_common_ok(g, p) || !is_upsampled(g)) return 0;
+  AuxTable t;
+  if (!build_up_table(g, t)) return 0;
+  return (size_t)t.nclass * t.Cout * t.rt * t.Cin * sizeof(bf16);
+}
+
+int conv_pack_weight_aux(const ConvGeom& g, const rho_conv_params* p, const float* w, void* out, cudaStream_t st) {
+  AuxTable t;
+  if (!is_upsampled(g) || !build_up_table(g, t)) return fail(RHO_ERR_UNSUPPORTED, "conv_pack_weight_aux: no aux form for this geometry");
+  long long total = (long long)t.nclass * t.Cout * t.rt * t.Cin;
+  int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
+  pack_aux_kernel<<<blocks, 256, 0, st>>>(t, w, (bf16*)out);
+  RHO_CHECK_LAUNCH("conv_pack_weight_aux");
+  return RHO_OK;
+}
+
+static ActView plain_view(const void* base, const ConvGeom& g, int C) {
+  ActView v;
+  v.base = base;
+  v.dim[0] = C; v.dim[1] = g.W; v.dim[2] = g.H; v.dim[3] = g.D; v.dim[4] = g.N;
+  v.stride[0] = (long long)C * 2; v.stride[1] = v.stride[0] * g.W; v.stride[2] = v.stride[1] * g.H; v.stride[3] = v.stride[2] * g.D;
+  return v;
+}
+
+// view of the elements with parity (ph, pw) in the strided dims: coordinate j <-> input index 2*j + parity
+static ActView parity_view(const void* base, const ConvGeom& g, int C, int ph, int pw) {
+  ActView v = plain_view(base, g, C);
+  long long off = 0;
+  if (g.sw == 2) { v.dim[1] = (g.W - pw + 1) / 2; off += (long long)pw * C * 2; v.stride[0] *= 2; }
+  if (g.sh == 2) { v.dim[2] = (g.H - ph + 1) / 2; off += (long long)ph * g.W * C * 2; v.stride[1] *= 2; }
+  v.base = (const char*)base + off;
+  return v;
 }
 
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const int bk = pick_block_k(g.C1, g.C2), bn = pick_block_n(g.Cout);
   TcParams tp;
   memset(&tp, 0, sizeof(tp));
-  tp.N = g.N; tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
+  tp.N = g.N;
   tp.os_d = tp.os_h = tp.os_w = 1;
   tp.Do = g.Do; tp.Ho = g.Ho; tp.Wo = g.Wo;
   tp.Cout = g.Cout; tp.C1 = g.C1; tp.C2 = g.C2;
   tp.n_blocks = g.Cout / bn;
-  pick_tile(tp);
-  tp.ntaps = g.taps;
-  for (int t = 0; t < g.taps; ++t) {
-    const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
-    tp.taps[t].dn = 0;
-    tp.taps[t].dd = (int16_t)(kd - g.pd); tp.taps[t].dh = (int16_t)(kh - g.ph); tp.taps[t].dw = (int16_t)(kw - g.pw);
-    tp.taps[t].map = 0;
-    tp.taps[t].kofs = t * g.Cin;
-  }
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
-  auto view = [&](const void* base, int C) {
-    ActView v;
-    v.base = base;
-    v.dim[0] = C; v.dim[1] = g.W; v.dim[2] = g.H; v.dim[3] = g.D; v.dim[4] = g.N;
-    v.stride[0] = (long long)C * 2; v.stride[1] = v.stride[0] * g.W; v.stride[2] = v.stride[1] * g.H; v.stride[3] = v.stride[2] * g.D;
-    return v;
-  };
-  int rc = encode_view(&maps.a[0][0], view(p->x, g.C1), box, bk);
-  if (rc) return rc;
-  if (g.C2) {
-    rc = encode_view(&maps.a[0][1], view(p->x2, g.C2), box, bk);
+  int rc;
+
+  if (is_upsampled(g)) {
+    AuxTable t;
+    if (!build_up_table(g, t)) return fail(RHO_ERR_UNSUPPORTED, "conv_tc: upsample plan");
+    // one launch per output parity class; the class grid is the un-upsampled input grid
+    tp.Gd = g.D; tp.Gh = g.H; tp.Gw = g.W;
+    pick_tile(tp);
+    const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
+    rc = encode_view(&maps.a[0][0], plain_view(p->x, g, g.C1), box, bk);
     if (rc) return rc;
+    if (g.C2) { rc = encode_view(&maps.a[0][1], plain_view(p->x2, g, g.C2), box, bk); if (rc) return rc; }
+    const long long cls_stride = (long long)t.Cout * t.rt * t.Cin;
+    for (int c = 0; c < t.nclass; ++c) {
+      tp.os_d = 1; tp.os_h = g.uh; tp.os_w = g.uw;
+      tp.oo_d = 0; tp.oo_h = t.par[c][1]; tp.oo_w = t.par[c][2];
+      tp.ntaps = t.rt;
+      for (int r = 0; r < t.rt; ++r) {
+        tp.taps[r].dn = 0; tp.taps[r].dd = t.off[c][r][0]; tp.taps[r].dh = t.off[c][r][1]; tp.taps[r].dw = t.off[c][r][2];
+        tp.taps[r].map = 0; tp.taps[r].kofs = r * g.Cin;
+      }
+      rc = encode_weight_map(&maps.w, (const bf16*)p->w_aux + c * cls_stride, (long long)t.rt * g.Cin, g.Cout, bk, bn);
+      if (rc) return rc;
+      rc = dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
+      if (rc) return rc;
+    }
+    return RHO_OK;
+  }
+
+  tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
+  pick_tile(tp);
+  const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
+  if (is_plain(g)) {
+    rc = encode_view(&maps.a[0][0], plain_view(p->x, g, g.C1), box, bk);
+    if (rc) return rc;
+    if (g.C2) { rc = encode_view(&maps.a[0][1], plain_view(p->x2, g, g.C2), box, bk); if (rc) return rc; }
+    tp.ntaps = g.taps;
+    for (int t = 0; t < g.taps; ++t) {
+      const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+      tp.taps[t].dn = 0;
+      tp.taps[t].dd = (int16_t)(kd - g.pd); tp.taps[t].dh = (int16_t)(kh - g.ph); tp.taps[t].dw = (int16_t)(kw - g.pw);
+      tp.taps[t].map = 0;
+      tp.taps[t].kofs = t * g.Cin;
+    }
+  } else {
+    // stride 2 in H and/or W: input index 2*o + k - pad  ->  (parity, coordinate) of a strided view
+    //   k - pad = -1: parity 1, coordinate o - 1;   0: parity 0, coordinate o;   +1: parity 1, coordinate o
+    bool used[4] = {false, false, false, false};
+    int nt = 0;
+    for (int t = 0; t < g.taps; ++t) {
+      const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+      const int eh = kh - g.ph, ew = kw - g.pw;
+      int ph = 0, pw = 0, dh = eh, dw = ew;
+      if (g.sh == 2) { ph = eh & 1; dh = eh < 0 ? -1 : 0; }
+      if (g.sw == 2) { pw = ew & 1; dw = ew < 0 ? -1 : 0; }
+      // a parity class with no elements (dim of size 1) contributes nothing
+      if ((g.sh == 2 && (g.H - ph + 1) / 2 == 0) || (g.sw == 2 && (g.W - pw + 1) / 2 == 0)) continue;
+      const int m = ph * 2 + pw;
+      used[m] = true;
+      tp.taps[nt].dn = 0; tp.taps[nt].dd = (int16_t)(kd - g.pd); tp.taps[nt].dh = (int16_t)dh; tp.taps[nt].dw = (int16_t)dw;
+      tp.taps[nt].map = m; tp.taps[nt].kofs = t * g.Cin;
+      ++nt;
+    }
+    tp.ntaps = nt;
+    for (int m = 0; m < 4; ++m) {
+      if (!used[m]) continue;
+      rc = encode_view(&maps.a[m][0], parity_view(p->x, g, g.C1, m >> 1, m & 1), box, bk);
+      if (rc) return rc;
+      if (g.C2) { rc = encode_view(&maps.a[m][1], parity_view(p->x2, g, g.C2, m >> 1, m & 1), box, bk); if (rc) return rc; }
+    }
   }
   rc = encode_weight_map(&maps.w, p->w_packed, g.Ktot, g.Cout, bk, bn);
   if (rc) return rc;

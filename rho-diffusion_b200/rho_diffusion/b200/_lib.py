@@ -26,7 +26,7 @@ class ConvParams(C.Structure):
         ("sd", c_i32), ("sh", c_i32), ("sw", c_i32),
         ("ud", c_i32), ("uh", c_i32), ("uw", c_i32),
         ("act_dtype", c_i32), ("w_dtype", c_i32), ("engine", c_i32), ("y_f32", c_i32),
-        ("x", c_vp), ("x2", c_vp), ("w_packed", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
+        ("x", c_vp), ("x2", c_vp), ("w_packed", c_vp), ("w_aux", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_sz),
     ]
 
@@ -102,6 +102,8 @@ SIGNATURES = {
     "rho_add_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_i64, c_vp]),
     "rho_scale": (C.c_int, [c_vp, C.c_int, c_i64, c_vp, c_f32, c_vp]),
     "rho_conv_pack_weight": (C.c_int, [c_vp, c_vp, C.c_int, c_i32, c_i32, c_i32, c_vp]),
+    "rho_conv_aux_weight_bytes": (c_sz, [P(ConvParams)]),
+    "rho_conv_pack_weight_aux": (C.c_int, [P(ConvParams), c_vp, c_vp, c_vp]),
     "rho_conv_workspace_bytes": (c_sz, [P(ConvParams)]),
     "rho_conv_fwd": (C.c_int, [P(ConvParams), c_vp]),
     "rho_conv_engine_for": (C.c_int, [P(ConvParams)]),

@@ -176,7 +176,7 @@ def packed_weight(owner, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tens
     return out
 
 
-def _conv_params(x, x2, wp, bias, residual, y, spec: ConvSpec, Cout, engine, y_f32) -> L.ConvParams:
+def _conv_params(x, x2, wp, bias, residual, y, spec: ConvSpec, Cout, engine, y_f32, w_aux=None) -> L.ConvParams:
     N = x.shape[0]
     D, H, W = _pad3(x.shape[1:-1])
     kd, kh, kw = _pad3(spec.kernel)
@@ -187,7 +187,7 @@ def _conv_params(x, x2, wp, bias, residual, y, spec: ConvSpec, Cout, engine, y_f
     p.C1, p.C2, p.Cout = x.shape[-1], (x2.shape[-1] if x2 is not None else 0), Cout
     p.kd, p.kh, p.kw, p.sd, p.sh, p.sw, p.ud, p.uh, p.uw = kd, kh, kw, sd, sh, sw, ud, uh, uw
     p.act_dtype, p.w_dtype, p.engine, p.y_f32 = dt(x), dt(wp), engine, int(y_f32)
-    p.x, p.x2, p.w_packed = ptr(x), ptr(x2), ptr(wp)
+    p.x, p.x2, p.w_packed, p.w_aux = ptr(x), ptr(x2), ptr(wp), ptr(w_aux)
     p.bias, p.residual, p.y = ptr(bias), ptr(residual), ptr(y)
     return p
 
@@ -231,10 +231,10 @@ class KernelProfiler:
 profiler: Optional[KernelProfiler] = None
 
 
-def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False):
+def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None):
     if profiler is not None:
         ev = profiler.begin()
-        y = _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32)
+        y = _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux)
         taps = 1
         for k in spec.kernel:
             taps *= k
@@ -242,19 +242,20 @@ def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_
         m = y.numel() // Cout
         nbytes = x.numel() * x.element_size() + (x2.numel() * x2.element_size() if x2 is not None else 0) + y.numel() * y.element_size() \
             + wp.numel() * wp.element_size() + (residual.numel() * residual.element_size() if residual is not None else 0)
-        profiler.end("conv", f"conv{spec.dims}d_k{spec.kernel[-1]}_{cin}->{Cout}", 2.0 * m * Cout * cin * taps, nbytes, ev)
+        tag = ("_s2" if max(spec.stride) > 1 else "") + ("_up" if max(spec.up) > 1 else "")
+        profiler.end("conv", f"conv{spec.dims}d_k{spec.kernel[-1]}{tag}_{cin}->{Cout}", 2.0 * m * Cout * cin * taps, nbytes, ev)
         return y
-    return _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32)
+    return _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux)
 
 
-def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False):
+def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None):
     _need_cuda(x, x2, wp, bias, residual)
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous()) and (residual is None or residual.is_contiguous())
     out_dtype = torch.float32 if y_f32 else x.dtype
     y = torch.empty(conv_out_shape(x.shape, spec, Cout), dtype=out_dtype, device=x.device)
     if residual is not None:
         assert residual.shape == y.shape and residual.dtype == x.dtype
-    p = _conv_params(x, x2, wp, bias, residual, y, spec, Cout, engine, y_f32)
+    p = _conv_params(x, x2, wp, bias, residual, y, spec, Cout, engine, y_f32, w_aux)
     L.check(L.lib().rho_conv_fwd(C.byref(p), stream()), "conv_fwd")
     return y
 
@@ -288,10 +289,10 @@ class ConvFn(torch.autograd.Function):
     ``wp`` is the packed copy of ``weight`` (:func:`packed_weight`); ``weight`` itself only receives the gradient."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, wp, bias, residual, spec, engine, y_f32):
+    def forward(ctx, x, x2, weight, wp, bias, residual, spec, engine, y_f32, w_aux=None):
         Cout = weight.shape[0]
         b = bias.detach().float() if bias is not None else None
-        y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32)
+        y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32, w_aux)
         ctx.save_for_backward(x, x2, wp)
         ctx.spec, ctx.engine, ctx.has_bias, ctx.has_res = spec, engine, bias is not None, residual is not None
         ctx.w_shape = tuple(weight.shape)
@@ -306,12 +307,38 @@ class ConvFn(torch.autograd.Function):
         dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, ctx.w_shape[0], need_dx, ctx.needs_input_grad[2],
                                         ctx.has_bias and ctx.needs_input_grad[4], ctx.w_shape, ctx.engine)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
-        return dx, dx2, dw, None, db, dres, None, None, None
+        return dx, dx2, dw, None, db, dres, None, None, None, None
+
+
+def aux_weight(owner, weight, spec: ConvSpec, x, x2, wp, dtype):
+    """Second, engine-specific packing (pre-summed weights of the fused-upsample decomposition); None if the geometry
+    has none.  Cached on the owning module like :func:`packed_weight`."""
+    if dtype != torch.bfloat16 or max(spec.up) == 1:
+        return None
+    p = _conv_params(x, x2, wp, None, None, None, spec, weight.shape[0], L.CONV_AUTO, False)
+    nbytes = L.lib().rho_conv_aux_weight_bytes(C.byref(p))
+    if nbytes == 0:
+        return None
+    cache = owner.__dict__.setdefault("_rho_aux", {})
+    ver = (weight._version, _weights_epoch, weight.data_ptr(), spec, nbytes)
+    hit = cache.get("aux")
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    with torch.inference_mode(False):
+        out = hit[1] if (hit is not None and hit[1].numel() == nbytes // 2) else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    L.check(L.lib().rho_conv_pack_weight_aux(C.byref(p), w.data_ptr(), out.data_ptr(), stream()), "conv_pack_weight_aux")
+    cache["aux"] = (ver, out)
+    return out
 
 
 def conv(owner, x, x2, weight, bias, residual, spec, dtype, engine=L.CONV_AUTO, y_f32=False):
     """conv_nd through the autograd tape; ``owner`` is the module that holds ``weight`` (packed-weight cache)."""
-    return ConvFn.apply(x, x2, weight, packed_weight(owner, weight, dtype), bias, residual, spec, engine, y_f32)
+    wp = packed_weight(owner, weight, dtype)
+    aux = aux_weight(owner, weight, spec, x, x2, wp, dtype) if engine != L.CONV_SIMT else None
+    return ConvFn.apply(x, x2, weight, wp, bias, residual, spec, engine, y_f32, aux)
 
 
 def cast(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None) -> torch.Tensor:

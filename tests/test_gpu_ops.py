@@ -133,6 +133,9 @@ CONV_CASES = [
     (1, 2, 256, 0, 64, (100,), 3, 1, 1, False),
     (3, 1, 96, 32, 96, (4, 6, 16), 3, 1, 1, False),
     (2, 1, 512, 256, 256, (8, 8), 1, 1, 1, False),
+    (3, 2, 128, 0, 128, (3, 8, 16), 3, 1, (1, 2, 2), False),   # Upsample on the tensor cores (4 parity classes, 12 taps)
+    (3, 2, 64, 0, 64, (3, 10, 12), 3, (1, 2, 2), 1, False),    # Downsample on the tensor cores (parity tensor maps)
+    (1, 2, 64, 0, 64, (37,), 3, 2, 1, False),                  # odd length, stride 2
 ]
 
 
@@ -179,7 +182,7 @@ def test_conv_fwd_bwd(ops, dtype, case):
         assert rel_err(nc(resd.grad), dy) < 1e-6
 
 
-@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 11, 13, 14, 15, 16, 17)])
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20)])
 def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     """The bf16 shapes above must run on the tcgen05 engine (forced: an unsupported shape would raise), and agree with
     the CUDA-core engine on the same inputs to fp32-accumulation rounding."""
@@ -193,7 +196,9 @@ def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     holder = torch.nn.Module()
     wp = ops.packed_weight(holder, w, torch.bfloat16)
     res = torch.randn(ops.conv_out_shape(x1.shape, spec, Cout), device=DEV).bfloat16() if use_res else None
-    y_tc = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_TCGEN05)
+    aux = ops.aux_weight(holder, w, spec, x1, x2, wp, torch.bfloat16)
+    assert (aux is not None) == (max(spec.up) > 1)
+    y_tc = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_TCGEN05, w_aux=aux)
     y_simt = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_SIMT)
     assert rel_err(y_tc, y_simt) < 1e-2          # both round the same fp32 sums to bf16 (different summation order)
     assert float((y_tc.float() - y_simt.float()).abs().mean() / y_simt.float().abs().mean()) < 1e-3
