@@ -395,6 +395,10 @@ static int attn_bwd_t(const rho_attn_bwd_params* p, cudaStream_t st) {
   return RHO_OK;
 }
 
+// attention_tc.cu
+bool attention_fwd_tc_supported(const rho_attn_params* p);
+int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st);
+
 int attention_fwd_simt(const rho_attn_params* p, cudaStream_t st) {
   if (p->dtype == RHO_F32) return attn_fwd_t<float>(p, st);
   if (p->dtype == RHO_BF16) return attn_fwd_t<bf16>(p, st);
@@ -410,6 +414,7 @@ extern "C" {
 int rho_attention_fwd(const rho_attn_params* p, rho_stream_t stream) {
   int rc = attn_validate(p, "attention_fwd");
   if (rc) return rc;
+  if (attention_fwd_tc_supported(p)) return attention_fwd_tc(p, as_stream(stream));   // bf16, head dim 64 / 128: tcgen05
   return attention_fwd_simt(p, as_stream(stream));
 }
 

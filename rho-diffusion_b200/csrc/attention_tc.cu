@@ -1,0 +1,289 @@
+// QKVAttention / QKVAttentionLegacy (rho_diffusion/models/unet_v2.py:365-436) on the 5th-generation tensor cores:
+// flash-style forward with tcgen05 MMAs, TMEM accumulators and TMA-fed operands (sm_100a).
+//
+// One CTA = 128 query rows of one (sample, head); key tiles of 128.
+//   S = Q K^T      : tcgen05.mma 128x128x(ch)   -> TMEM columns [0,128)     (A = Q, B = K, both K-major from TMA)
+//   softmax        : thread r owns TMEM lane r = query row r, so the row max / row sum need NO shuffles:
+//                    pass 1 reads the row from TMEM for the max, pass 2 re-reads it, exponentiates (exp2, fp32),
+//                    and writes P as bf16 into shared memory in the 128-byte-swizzled K-major layout
+//   O += P V       : tcgen05.mma 128x(ch)x128   -> TMEM columns [128,128+ch) (A = P, B = V as an MN-major operand:
+//                    V is [keys x ch] row-major, exactly what channels-last qkv gives)
+//   when the running max moves, the owner threads rescale their O row in TMEM (tcgen05.ld / tcgen05.st).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax / correction /
+// epilogue.  Two CTAs per SM (<= 97 KB smem, 256 TMEM columns each): one CTA's exponentials (MUFU-bound) overlap the
+// other's MMAs and loads.  The T x T weight matrix never exists in HBM (the reference materialises 4.3 GB per
+// sample per block at T = 16384).
+#include "tc_common.cuh"
+
+namespace rho {
+
+constexpr int AT_BM = 128;   // queries per CTA
+constexpr int AT_BN = 128;   // keys per tile
+
+struct AttnTcParams {
+  int T, heads, ch, order;
+  int q_col, k_col, v_col;   // channel offsets of head 0's q / k / v slices (per-head stride below)
+  int head_stride;           // channels between consecutive heads' slices
+  int C;                     // heads * ch
+  float scale_log2;          // ch^-1/2 * log2(e)
+  float scale;               // ch^-1/2
+};
+
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t at_desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// MN-major operand in the 128B-swizzled canonical layout: rows = K (keys), 128 bytes = 64 contiguous N (channels)
+__device__ __forceinline__ uint64_t at_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-wide N atoms
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride between 8-row K atoms
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnTcParams p,
+                                                                      bf16* __restrict__ out, float* __restrict__ lse) {
+  constexpr int KB = CH / 64;                   // 64-channel K blocks of Q / K, N atoms of V
+  constexpr int TILE_BYTES = 128 * 128;         // one [128 rows x 64 ch] bf16 block
+  constexpr int Q_BYTES = KB * TILE_BYTES, K_BYTES = KB * TILE_BYTES, V_BYTES = KB * TILE_BYTES;
+  constexpr int K_STAGES = CH == 64 ? 2 : 1;
+  constexpr int P_BYTES = 2 * TILE_BYTES;       // [2 key blocks][128 rows][64 keys]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + K_STAGES * K_BYTES;
+  uint8_t* sP = sV + V_BYTES;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_ready, p_ready, o_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, n = blockIdx.z;
+  const int nt = (p.T + AT_BN - 1) / AT_BN;
+  const int qc = p.q_col + h * p.head_stride, kc = p.k_col + h * p.head_stride, vc = p.v_col + h * p.head_stride;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+    mbar_init(&s_ready, 1); mbar_init(&o_done, 1);
+    mbar_init(&p_ready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_base_s;          // S: columns [0, 128)
+  const uint32_t tmem_o = tmem_base_s + 128;    // O: columns [128, 128 + CH)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, Q_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sQ + kb * TILE_BYTES, &qkv_map, &q_full, qc + kb * 64, q0, n);
+      for (int j = 0; j < nt; ++j) {
+        const int ks = j % K_STAGES;
+        const uint32_t kphase = (uint32_t)(j / K_STAGES) & 1;
+        mbar_wait(&k_empty[ks], kphase ^ 1);
+        mbar_expect_tx(&k_full[ks], K_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sK + ks * K_BYTES + kb * TILE_BYTES, &qkv_map, &k_full[ks], kc + kb * 64, j * AT_BN, n);
+        mbar_wait(&v_empty, (uint32_t)(j & 1) ^ 1);
+        mbar_expect_tx(&v_full, V_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sV + kb * TILE_BYTES, &qkv_map, &v_full, vc + kb * 64, j * AT_BN, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptors: D fp32, A/B bf16, M = 128
+      const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                                ((uint32_t)(AT_BM >> 4) << 24);
+      auto issue_qk = [&](int j) {
+        const int ks = j % K_STAGES;
+        mbar_wait(&k_full[ks], (uint32_t)(j / K_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * TILE_BYTES));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + ks * K_BYTES + kb * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_qk, (kb | k) != 0);
+        }
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_ready);
+      };
+      mbar_wait(&q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&p_ready, (uint32_t)j & 1);     // P_j is in smem and the softmax threads are done reading S_j
+        mbar_wait(&v_full, (uint32_t)j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {          // two 64-key blocks of P
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sP + kb * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {           // 16 keys per MMA: two 8-row K atoms = 2048 bytes of V
+            const uint64_t b = at_desc_mnmajor(smem_u32(sV + (kb * 64 + k * 16) * 128), TILE_BYTES);
+            umma_f16(tmem_o, a + (uint64_t)(2 * k), b, idesc_pv, (j | kb | k) != 0);
+          }
+        }
+        umma_commit(&v_empty);
+        umma_commit(&o_done);
+        if (j + 1 < nt) issue_qk(j + 1);
+      }
+    }
+  } else {
+    // ===== softmax / correction / epilogue: thread <-> query row =====
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_ready, (uint32_t)j & 1);
+      tc_fence_after();
+      const int kvalid = p.T - j * AT_BN;         // keys >= kvalid are padding (only in the last tile)
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < AT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_addr + (uint32_t)c, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float s = (c + e < kvalid) ? __uint_as_float(v[e]) : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * p.scale_log2);   // m = -inf on the first tile -> 0
+      // ---- correction: rescale this row of O when the running max moved (PV_{j-1} has completed: s_ready(j) follows it)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < CH; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st32(tmem_o + lane_addr + (uint32_t)c, v);
+        }
+      }
+      l *= alpha;
+      m = m_new;
+      const float mb = m_new * p.scale_log2;
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 P into swizzled smem
+#pragma unroll 1
+      for (int c = 0; c < AT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_addr + (uint32_t)c, v);
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = (c + e < kvalid) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -mb)) : 0.f;
+          float p1 = (c + e + 1 < kvalid) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -mb)) : 0.f;
+          l += p0 + p1;
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        // 32 keys = 4 chunks of 16 bytes; key block kb = c / 64, chunk index within the 128-byte row = (c % 64) / 8 + i
+        uint8_t* rowp = sP + (c >> 6) * TILE_BYTES + r * 128;
+        const int ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = (ch0 + i) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+      tc_fence_before();          // order our tcgen05.ld/st before the MMAs the issuer launches after the barrier
+      fence_proxy_async_smem();   // make the P stores visible to the tensor core (async proxy)
+      mbar_arrive(&p_ready);
+    }
+    // ---- epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_done, (uint32_t)(nt - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + r;
+    const float inv = 1.0f / l;
+    bf16* orow = out + ((long long)n * p.T + q) * p.C + h * CH;
+#pragma unroll 1
+    for (int c = 0; c < CH; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
+      if (q < p.T) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          float o[4] = {__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv, __uint_as_float(v[e + 2]) * inv,
+                        __uint_as_float(v[e + 3]) * inv};
+          store4(orow + c + e, o);
+        }
+      }
+    }
+    if (lse && q < p.T) lse[((long long)n * p.heads + h) * p.T + q] = m * p.scale + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(256u));
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+bool attention_fwd_tc_supported(const rho_attn_params* p) {
+  const char* e = getenv("RHO_DISABLE_TCGEN05");
+  if (e && e[0] == '1') return false;
+  if (p->dtype != RHO_BF16) return false;
+  if (p->ch != 64 && p->ch != 128) return false;
+  if (p->T < 1 || p->N > 65535 || p->heads > 65535) return false;
+  return get_encode() != nullptr;
+}
+
+template <int CH>
+static int launch_attn_tc(const CUtensorMap& map, const AttnTcParams& ap, const rho_attn_params* p, cudaStream_t st) {
+  constexpr int KB = CH / 64;
+  constexpr int K_STAGES = CH == 64 ? 2 : 1;
+  constexpr size_t SMEM = (size_t)(KB + K_STAGES * KB + KB + 2) * 128 * 128 + 1024;
+  auto kern = attn_tc_kernel<CH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)ceil_div(p->T, AT_BM), p->heads, p->N);
+  kern<<<grid, 192, SMEM, st>>>(map, ap, (bf16*)p->out, p->lse);
+  RHO_CHECK_LAUNCH("attention_fwd_tcgen05");
+  return RHO_OK;
+}
+
+int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
+  auto enc = get_encode();
+  if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const int C = p->heads * p->ch;
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {(cuuint64_t)(3 * C), (cuuint64_t)p->T, (cuuint64_t)p->N};
+  cuuint64_t gstr[2] = {(cuuint64_t)(3 * C) * 2, (cuuint64_t)(3 * C) * 2 * (cuuint64_t)p->T};
+  cuuint32_t bdim[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->qkv), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
+  AttnTcParams ap;
+  ap.T = p->T; ap.heads = p->heads; ap.ch = p->ch; ap.order = p->order; ap.C = C;
+  if (p->order == 0) { ap.q_col = 0; ap.k_col = p->ch; ap.v_col = 2 * p->ch; ap.head_stride = 3 * p->ch; }
+  else { ap.q_col = 0; ap.k_col = C; ap.v_col = 2 * C; ap.head_stride = p->ch; }
+  ap.scale = 1.0f / sqrtf((float)p->ch);
+  ap.scale_log2 = ap.scale * 1.4426950408889634f;
+  if (p->ch == 64) return launch_attn_tc<64>(map, ap, p, st);
+  return launch_attn_tc<128>(map, ap, p, st);
+}
+
+}  // namespace rho

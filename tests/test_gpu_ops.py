@@ -201,7 +201,9 @@ def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     y_tc = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_TCGEN05, w_aux=aux)
     y_simt = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_SIMT)
     assert rel_err(y_tc, y_simt) < 1e-2          # both round the same fp32 sums to bf16 (different summation order)
-    assert float((y_tc.float() - y_simt.float()).abs().mean() / y_simt.float().abs().mean()) < 1e-3
+    # the fused-upsample path rounds the pre-summed weights (w1 + w2) to bf16 once instead of w1 and w2 separately
+    mean_tol = 5e-3 if max(spec.up) > 1 else 1e-3
+    assert float((y_tc.float() - y_simt.float()).abs().mean() / y_simt.float().abs().mean()) < mean_tol
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -211,6 +213,9 @@ def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     (1, 512, 4, 32, 0),
     (1, 130, 2, 64, 1),
     (1, 96, 4, 128, 1),     # config A head dim
+    (1, 1000, 4, 64, 0),    # tcgen05 engine (bf16): 8 key tiles, ragged last tile, legacy order
+    (2, 300, 2, 128, 1),    # tcgen05 engine (bf16): head dim 128, 3 key tiles
+    (1, 128, 1, 64, 1),     # exactly one tile
 ])
 def test_attention_fwd_bwd(ops, dtype, N, T, heads, ch, order):
     q = (lambda t: t.to(dtype).float())
