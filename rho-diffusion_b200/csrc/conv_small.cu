@@ -31,15 +31,27 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(ConvGeom g, const T
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
-    for (int t = 0; t < g.taps; ++t) {
-      const long long src = fwd_src(g, rp, t);
-      if (src < 0) continue;
-      for (int ci = 0; ci < g.Cin; ++ci) {
-        const float xv = to_f32(x[src * g.Cin + ci]);
-        const float4 w0 = *reinterpret_cast<const float4*>(&ws[(t * g.Cin + ci) * g.Cout + c0]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&ws[(t * g.Cin + ci) * g.Cout + c0 + 4]);
-        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    int t = 0;
+    for (int kd = 0; kd < g.kd; ++kd) {
+      const int pd = rp.d * g.sd + kd - g.pd;
+      const bool okd = pd >= 0 && pd < g.Du;
+      const long long bd = ((long long)rp.n * g.D + pd / g.ud) * g.H;
+      for (int kh = 0; kh < g.kh; ++kh) {
+        const int ph = rp.h * g.sh + kh - g.ph;
+        const bool okh = okd && ph >= 0 && ph < g.Hu;
+        const long long bh = (bd + ph / g.uh) * g.W;
+        for (int kw = 0; kw < g.kw; ++kw, ++t) {
+          const int pw = rp.w * g.sw + kw - g.pw;
+          if (!(okh && pw >= 0 && pw < g.Wu)) continue;
+          const long long src = bh + pw / g.uw;
+          for (int ci = 0; ci < g.Cin; ++ci) {
+            const float xv = to_f32(x[src * g.Cin + ci]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws[(t * g.Cin + ci) * g.Cout + c0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&ws[(t * g.Cin + ci) * g.Cout + c0 + 4]);
+            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          }
+        }
       }
     }
     const float lo[4] = {acc[0], acc[1], acc[2], acc[3]}, hi[4] = {acc[4], acc[5], acc[6], acc[7]};
@@ -57,20 +69,32 @@ __global__ void __launch_bounds__(256) conv_small_cout_kernel(ConvGeom g, const 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int half = g.Cin >> 1;                 // channel pairs per tap
-  const int pairs = g.taps * half;
   const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < g.M; m += warps_total) {
     const RowPos rp = decode_out(g, m);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < pairs; i += 32) {
-      const int t = i / half, cp = (i - t * half) * 2;
-      const long long src = fwd_src(g, rp, t);
-      if (src < 0) continue;
-      const float x0 = to_f32(x[src * g.Cin + cp]), x1 = to_f32(x[src * g.Cin + cp + 1]);
-      const int k = t * g.Cin + cp;
+    int t = 0;
+    for (int kd = 0; kd < g.kd; ++kd) {
+      const int pd = rp.d * g.sd + kd - g.pd;
+      const bool okd = pd >= 0 && pd < g.Du;
+      const long long bd = ((long long)rp.n * g.D + pd / g.ud) * g.H;
+      for (int kh = 0; kh < g.kh; ++kh) {
+        const int ph = rp.h * g.sh + kh - g.ph;
+        const bool okh = okd && ph >= 0 && ph < g.Hu;
+        const long long bh = (bd + ph / g.uh) * g.W;
+        for (int kw = 0; kw < g.kw; ++kw, ++t) {
+          const int pw = rp.w * g.sw + kw - g.pw;
+          if (!(okh && pw >= 0 && pw < g.Wu)) continue;       // warp-uniform
+          const TA* row = x + (bh + pw / g.uw) * g.Cin;
+          for (int cp = lane; cp < half; cp += 32) {          // one coalesced row read per tap
+            const float x0 = to_f32(row[2 * cp]), x1 = to_f32(row[2 * cp + 1]);
+            const int k = t * g.Cin + 2 * cp;
 #pragma unroll
-      for (int co = 0; co < 4; ++co)
-        if (co < g.Cout) acc[co] = fmaf(x0, ws[co * K + k], fmaf(x1, ws[co * K + k + 1], acc[co]));
+            for (int co = 0; co < 4; ++co)
+              if (co < g.Cout) acc[co] = fmaf(x0, ws[co * K + k], fmaf(x1, ws[co * K + k + 1], acc[co]));
+          }
+        }
+      }
     }
 #pragma unroll
     for (int co = 0; co < 4; ++co) {

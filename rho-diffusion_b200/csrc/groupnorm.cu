@@ -462,6 +462,185 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_pass2_kernel(const TI* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bf16 fast path: 16-byte vectors (8 channels per thread), 4 rows in flight per thread
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const bf16* __restrict__ p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = __low2float(h[j]); v[2 * j + 1] = __high2float(h[j]); }
+}
+__device__ __forceinline__ void store8(bf16* __restrict__ p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void gn_load8(const bf16* __restrict__ x, const bf16* __restrict__ x2, int C1, int C2, int64_t row, int c,
+                                         float (&v)[8]) {
+  if (c < C1) load8(x + row * C1 + c, v);
+  else load8(x2 + row * C2 + (c - C1), v);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                               const float* __restrict__ pre_add, int pre_stride, int C1, int C2,
+                                                               int64_t S, int G, int chunks, float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int rows = GN_THREADS / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per, p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const int row = tid / CV, cv = tid - row * CV;
+  const bool active = row < rows;
+  const int c = cv * 8;
+  __shared__ float sc_n[2048], sc_mean[2048], sc_m2[2048];
+  const bf16* xb = x + (int64_t)n * S * C1;
+  const bf16* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+  float K[8], s1[8], s2[8], pa[8];
+  float cnt = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { K[j] = 0.f; s1[j] = 0.f; s2[j] = 0.f; pa[j] = 0.f; }
+  if (active) {
+    if (pre_add) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pa[j] = pre_add[(int64_t)n * pre_stride + c + j];
+    }
+    int64_t p = p0 + row;
+    if (p < p1) {
+      float v[8];
+      gn_load8(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) K[j] = v[j] + pa[j];
+    }
+    for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) gn_load8(xb, x2b, C1, C2, p + (int64_t)u * rows, c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = (v[u][j] + pa[j]) - K[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+      cnt += 4.f;
+    }
+    for (; p < p1; p += rows) {
+      float v[8];
+      gn_load8(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = (v[j] + pa[j]) - K[j];
+        s1[j] += d;
+        s2[j] = fmaf(d, d, s2[j]);
+      }
+      cnt += 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = row * C + c + j;
+      sc_n[idx] = cnt;
+      sc_mean[idx] = cnt > 0.f ? K[j] + s1[j] / cnt : 0.f;
+      sc_m2[idx] = cnt > 0.f ? fmaxf(s2[j] - s1[j] * s1[j] / cnt, 0.f) : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int cc = tid; cc < C; cc += GN_THREADS) {
+    Moments a = {sc_n[cc], sc_mean[cc], sc_m2[cc]};
+    for (int r = 1; r < rows; ++r) {
+      Moments b = {sc_n[r * C + cc], sc_mean[r * C + cc], sc_m2[r * C + cc]};
+      a = merge(a, b);
+    }
+    sc_n[cc] = a.n; sc_mean[cc] = a.mean; sc_m2[cc] = a.m2;   // row 0 now holds the per-channel moments
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += GN_THREADS) {
+    Moments a = {sc_n[g * cpg], sc_mean[g * cpg], sc_m2[g * cpg]};
+    for (int j = 1; j < cpg; ++j) {
+      Moments b = {sc_n[g * cpg + j], sc_mean[g * cpg + j], sc_m2[g * cpg + j]};
+      a = merge(a, b);
+    }
+    float* o = partial + (((int64_t)n * chunks + chunk) * G + g) * 3;
+    o[0] = a.n; o[1] = a.mean; o[2] = a.m2;
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                               const float* __restrict__ pre_add, int pre_stride,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ scale, const float* __restrict__ shift,
+                                                               int film_stride, const float* __restrict__ stats, int C1, int C2,
+                                                               int64_t S, int G, int chunks, int act, bf16* __restrict__ y) {
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int rows = GN_THREADS / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per, p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const int row = tid / CV, cv = tid - row * CV;
+  if (row >= rows) return;
+  const int c = cv * 8;
+  const int cpg = C / G;
+  // y = act(x * a + b): a = rstd*gamma*(1+sc), b = ((pa - mean)*rstd*gamma + beta)*(1+sc) + sh
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float mean = stats[((int64_t)n * G + g) * 2], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+    const float ga = gamma[c + j] * rstd;
+    const float pa = pre_add ? pre_add[(int64_t)n * pre_stride + c + j] : 0.f;
+    const float f = scale ? 1.f + scale[(int64_t)n * film_stride + c + j] : 1.f;
+    const float sh = shift ? shift[(int64_t)n * film_stride + c + j] : 0.f;
+    a[j] = ga * f;
+    b[j] = ((pa - mean) * ga + beta[c + j]) * f + sh;
+  }
+  const bf16* xb = x + (int64_t)n * S * C1;
+  const bf16* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
+  bf16* yb = y + (int64_t)n * S * C;
+  int64_t p = p0 + row;
+  for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) gn_load8(xb, x2b, C1, C2, p + (int64_t)u * rows, c, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[u][j] = apply_act(fmaf(v[u][j], a[j], b[j]), act);
+      store8(yb + (p + (int64_t)u * rows) * C + c, v[u]);
+    }
+  }
+  for (; p < p1; p += rows) {
+    float v[8];
+    gn_load8(xb, x2b, C1, C2, p, c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(v[j], a[j], b[j]), act);
+    store8(yb + p * C + c, v);
+  }
+}
+
+static int gn_chunks8(int N, int64_t S, int C) {
+  const int rows = GN_THREADS / (C >> 3);
+  int64_t target = (int64_t)sm_count() * 8;
+  int64_t chunks = ceil_div(target, N);
+  int64_t max_chunks = ceil_div(S, (int64_t)rows * 8);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 8192) chunks = 8192;
+  return (int)chunks;
+}
+static bool gn_fast8(const rho_gn_params* p) {
+  const int C = p->C1 + p->C2;
+  return p->in_dtype == RHO_BF16 && (p->C1 % 8 == 0) && (p->C2 % 8 == 0) && C <= 2048 && (C >> 3) <= GN_THREADS;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -497,7 +676,7 @@ extern "C" {
 
 size_t rho_gn_workspace_bytes(const rho_gn_params* p) {
   if (!p) return 0;
-  int chunks = gn_chunks(p->N, p->S, p->C1 + p->C2);
+  int chunks = gn_fast8(p) ? gn_chunks8(p->N, p->S, p->C1 + p->C2) : gn_chunks(p->N, p->S, p->C1 + p->C2);
   return (size_t)p->N * chunks * p->groups * 3 * sizeof(float);
 }
 
@@ -505,13 +684,17 @@ int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream) {
   int rc = gn_validate(p, "gn_stats");
   if (rc) return rc;
   const int C = p->C1 + p->C2;
-  int chunks = gn_chunks(p->N, p->S, C);
+  const bool fast = gn_fast8(p);
+  int chunks = fast ? gn_chunks8(p->N, p->S, C) : gn_chunks(p->N, p->S, C);
   size_t need = (size_t)p->N * chunks * p->groups * 3 * sizeof(float);
   if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "gn_stats: workspace %zu < %zu", p->workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   dim3 grid(chunks, p->N);
   float* partial = (float*)p->workspace;
-  if (p->in_dtype == RHO_F32)
+  if (fast)
+    gn_stats8_kernel<<<grid, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->C1, p->C2, p->S,
+                                                  p->groups, chunks, partial);
+  else if (p->in_dtype == RHO_F32)
     gn_stats_kernel<float><<<grid, GN_THREADS, 0, st>>>((const float*)p->x, (const float*)p->x2, p->pre_add, p->pre_add_stride, p->C1,
                                                          p->C2, p->S, p->groups, chunks, partial);
   else if (p->in_dtype == RHO_BF16)
@@ -532,8 +715,17 @@ int rho_gn_apply(const rho_gn_params* p, rho_stream_t stream) {
   RHO_REQUIRE(p->y && p->gamma && p->beta, "gn_apply: null tensor");
   RHO_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "gn_apply: scale/shift must both be set");
   const int C = p->C1 + p->C2;
-  int chunks = gn_chunks(p->N, p->S, C);
   cudaStream_t st = as_stream(stream);
+  if (gn_fast8(p) && p->out_dtype == RHO_BF16) {
+    int chunks8 = gn_chunks8(p->N, p->S, C);
+    dim3 grid8(chunks8, p->N);
+    gn_apply8_kernel<<<grid8, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->gamma, p->beta,
+                                                   p->scale, p->shift, p->film_stride, p->stats, p->C1, p->C2, p->S, p->groups, chunks8,
+                                                   p->act, (bf16*)p->y);
+    RHO_CHECK_LAUNCH("gn_apply8");
+    return RHO_OK;
+  }
+  int chunks = gn_chunks(p->N, p->S, C);
   dim3 grid(chunks, p->N);
 #define RHO_GNA(TI, TO)                                                                                                        \
   gn_apply_kernel<TI, TO><<<grid, GN_THREADS, 0, st>>>((const TI*)p->x, (const TI*)p->x2, p->pre_add, p->pre_add_stride, p->gamma, \
