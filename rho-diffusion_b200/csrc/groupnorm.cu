@@ -146,20 +146,34 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
   }
 }
 
-__global__ void gn_stats_finalize_kernel(const float* __restrict__ partial, int NG, int G, int chunks, float eps,
-                                         float* __restrict__ stats) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (n, group): lanes merge a strided subset of the chunk partials, then a fixed xor-shuffle tree merges the
+// 32 lane results (same order every run: deterministic)
+__global__ void __launch_bounds__(128) gn_stats_finalize_kernel(const float* __restrict__ partial, int NG, int G, int chunks, float eps,
+                                                                float* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= NG) return;
-  int n = i / G, g = i % G;
+  const int n = i / G, g = i % G;
   Moments a = {0.f, 0.f, 0.f};
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     const float* o = partial + (((int64_t)n * chunks + k) * G + g) * 3;
     Moments b = {o[0], o[1], o[2]};
     a = merge(a, b);
   }
-  float var = a.n > 0.f ? a.m2 / a.n : 0.f;
-  stats[2 * i] = a.mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Moments b;
+    b.n = __shfl_xor_sync(0xffffffffu, a.n, off);
+    b.mean = __shfl_xor_sync(0xffffffffu, a.mean, off);
+    b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, off);
+    // merge in a lane-independent order so that every lane ends with bit-identical results
+    a = (lane & off) ? merge(b, a) : merge(a, b);
+  }
+  if (lane == 0) {
+    const float var = a.n > 0.f ? a.m2 / a.n : 0.f;
+    stats[2 * i] = a.mean;
+    stats[2 * i + 1] = rsqrtf(var + eps);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -704,7 +718,7 @@ int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream) {
     return fail(RHO_ERR_INVALID_ARG, "gn_stats: bad dtype");
   RHO_CHECK_LAUNCH("gn_stats");
   int NG = p->N * p->groups;
-  gn_stats_finalize_kernel<<<(NG + 127) / 128, 128, 0, st>>>(partial, NG, p->groups, chunks, p->eps, p->stats);
+  gn_stats_finalize_kernel<<<(NG * 32 + 127) / 128, 128, 0, st>>>(partial, NG, p->groups, chunks, p->eps, p->stats);
   RHO_CHECK_LAUNCH("gn_stats_finalize");
   return RHO_OK;
 }
