@@ -155,20 +155,37 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
       mbar_wait(&s_ready, (uint32_t)j & 1);
       tc_fence_after();
       const int kvalid = p.T - j * AT_BN;         // keys >= kvalid are padding (only in the last tile)
-      // ---- pass 1: row max
+      const bool full = kvalid >= AT_BN;          // warp-uniform
+      // ---- pass 1: row max (TMEM loads software-pipelined: chunk c+1 is in flight while chunk c is reduced)
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_addr + (uint32_t)c, v);
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32_async(tmem_s + lane_addr, va);
+        tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float s = (c + e < kvalid) ? __uint_as_float(v[e]) : -INFINITY;
-          mx = fmaxf(mx, s);
+        for (int c = 0; c < AT_BN; c += 64) {
+          tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 32), vb);
+          if (full) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c + e < kvalid) ? __uint_as_float(va[e]) : -INFINITY);
+          }
+          tmem_wait_ld();
+          if (c + 64 < AT_BN) tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 64), va);
+          if (full) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c + 32 + e < kvalid) ? __uint_as_float(vb[e]) : -INFINITY);
+          }
+          if (c + 64 < AT_BN) tmem_wait_ld();
         }
       }
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * p.scale_log2);   // m = -inf on the first tile -> 0
+      const float alpha = ex2_approx((m - m_new) * p.scale_log2);   // m = -inf on the first tile -> 0
       // ---- correction: rescale this row of O when the running max moved (PV_{j-1} has completed: s_ready(j) follows it)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
@@ -183,28 +200,40 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
       l *= alpha;
       m = m_new;
       const float mb = m_new * p.scale_log2;
-      // ---- pass 2: p = exp2(s*c - m*c), row sum, bf16 P into swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
+      // ---- pass 2: p = exp2(s*c - m*c) (one FFMA + one MUFU per element), row sum, bf16 P into swizzled smem
+      {
         uint32_t v[32];
-        tmem_ld32(tmem_s + lane_addr + (uint32_t)c, v);
-        uint32_t packed[16];
+        float ls0 = 0.f, ls1 = 0.f;
+        tmem_ld32_async(tmem_s + lane_addr, v);
+        tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = (c + e < kvalid) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -mb)) : 0.f;
-          float p1 = (c + e + 1 < kvalid) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -mb)) : 0.f;
-          l += p0 + p1;
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        // 32 keys = 4 chunks of 16 bytes; key block kb = c / 64, chunk index within the 128-byte row = (c % 64) / 8 + i
-        uint8_t* rowp = sP + (c >> 6) * TILE_BYTES + r * 128;
-        const int ch0 = (c & 63) >> 3;
+        for (int c = 0; c < AT_BN; c += 32) {
+          uint32_t packed[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = (ch0 + i) ^ (r & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -mb));
+            if (!full) {
+              p0 = (c + e < kvalid) ? p0 : 0.f;
+              p1 = (c + e + 1 < kvalid) ? p1 : 0.f;
+            }
+            ls0 += p0;
+            ls1 += p1;
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          if (c + 32 < AT_BN) tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 32), v);   // v is dead: reuse for the next chunk
+          // 32 keys = 4 chunks of 16 bytes; key block kb = c / 64, chunk index within the 128-byte row = (c % 64) / 8 + i
+          uint8_t* rowp = sP + (c >> 6) * TILE_BYTES + r * 128;
+          const int ch0 = (c & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = (ch0 + i) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          }
+          if (c + 32 < AT_BN) tmem_wait_ld();
         }
+        l += ls0 + ls1;
       }
       tc_fence_before();          // order our tcgen05.ld/st before the MMAs the issuer launches after the barrier
       fence_proxy_async_smem();   // make the P stores visible to the tensor core (async proxy)
