@@ -16,6 +16,10 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
 bool conv_dgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
 int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 size_t conv_dgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
+// conv_wgrad_tc.cu
+bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
+size_t conv_wgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
+int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 size_t conv_aux_weight_bytes(const ConvGeom& g, const rho_conv_params* p);
 int conv_pack_weight_aux(const ConvGeom& g, const rho_conv_params* p, const float* w, void* out, cudaStream_t st);
 
@@ -76,7 +80,9 @@ size_t rho_conv_bwd_workspace_bytes(const rho_conv_bwd_params* p) {
   if (!p || make_geom(&p->fwd, g)) return 0;
   size_t a = conv_wgrad_simt_workspace(g);
   size_t b = conv_dgrad_tc_workspace(g, p);
-  return a > b ? a : b;
+  size_t c = conv_wgrad_tc_workspace(g, p);
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 int rho_conv_dgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
@@ -99,6 +105,15 @@ int rho_conv_wgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
   if (rc) return rc;
   RHO_REQUIRE(p->dy, "conv_wgrad: null dy");
   RHO_REQUIRE(p->dw || p->dbias, "conv_wgrad: nothing to compute");
+  if (p->dw && p->fwd.engine != RHO_CONV_SIMT && conv_wgrad_tc_supported(g, p)) {
+    RHO_REQUIRE(p->fwd.x, "conv_wgrad: x required");
+    rc = conv_wgrad_tc(g, p, as_stream(stream));
+    if (rc || !p->dbias) return rc;
+    rho_conv_bwd_params q = *p;     // bias gradient: column sums of dy (deterministic two-stage reduction)
+    q.dw = nullptr;
+    return conv_wgrad_simt(g, &q, as_stream(stream));
+  }
+  if (p->fwd.engine == RHO_CONV_TCGEN05 && p->dw) return fail(RHO_ERR_UNSUPPORTED, "conv_wgrad: tcgen05 engine does not take this shape");
   return conv_wgrad_simt(g, p, as_stream(stream));
 }
 

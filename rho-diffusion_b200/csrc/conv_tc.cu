@@ -541,8 +541,118 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   return dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
 }
 
-bool conv_dgrad_tc_supported(const ConvGeom&, const rho_conv_bwd_params*) { return false; }
-int conv_dgrad_tc(const ConvGeom&, const rho_conv_bwd_params*, cudaStream_t) { return fail(RHO_ERR_UNSUPPORTED, "conv_dgrad_tc: not built"); }
-size_t conv_dgrad_tc_workspace(const ConvGeom&, const rho_conv_bwd_params*) { return 0; }
+// ---- dgrad on the tensor cores ---------------------------------------------------------------------------
+// dX = "same" convolution of dY with the spatially flipped, channel-transposed filter: the forward kernel is reused with
+//   source = dY (K channels = Cout), output channels = Cin (split into dx | dx2 for a concat input),
+//   weights = [Cin][taps][Cout] with tap index reversed (a pure permutation of the packed bf16 forward weights, so it is
+//   rebuilt in the workspace on every call).
+// Fused-upsample convs: dgrad at the upsampled resolution into a temporary, then a 2x2 (H, W) sum-pool -- the adjoint of
+// the nearest-neighbour gather.  Strided (Downsample) convs stay on the CUDA-core engine (3 small layers).
+__global__ void pack_dgrad_kernel(const bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes wd [ci][t][co]
+    const int co = (int)(i % Cout);
+    const int t = (int)((i / Cout) % taps);
+    const int ci = (int)(i / ((long long)Cout * taps));
+    wd[i] = wf[((long long)co * taps + (taps - 1 - t)) * Cin + ci];
+  }
+}
+
+// dx[n,d,h,w,c] = sum_{a<uh, b<uw} t[n,d,h*uh+a,w*uw+b,c]; channels [0,C1) -> dx, [C1,C) -> dx2
+__global__ void sum_pool_split_kernel(const bf16* __restrict__ t, bf16* __restrict__ dx, bf16* __restrict__ dx2, long long NDin, int H, int W,
+                                      int uh, int uw, int C, int C1) {
+  const int cv = C >> 2;
+  const long long total = NDin * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    long long pos = i / cv;
+    const int w = (int)(pos % W); pos /= W;
+    const int h = (int)(pos % H);
+    const long long nd = pos / H;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < uh; ++a)
+      for (int b = 0; b < uw; ++b) {
+        float v[4];
+        load4(t + (((nd * (H * uh) + (h * uh + a)) * (long long)(W * uw)) + (w * uw + b)) * C + c, v);
+        acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+      }
+    const long long o = (nd * H + h) * W + w;
+    if (c < C1) store4(dx + o * C1 + c, acc);
+    else store4(dx2 + o * (C - C1) + (c - C1), acc);
+  }
+}
+
+static bool dgrad_tc_shape_ok(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (tc_disabled()) return false;
+  if (p->fwd.act_dtype != RHO_BF16 || p->fwd.w_dtype != RHO_BF16) return false;
+  if (!(is_plain(g) || is_upsampled(g))) return false;
+  if (pick_block_k(g.Cout, 0) < 32 || pick_block_n(g.Cin) == 0) return false;
+  if (g.C2 > 0 && (g.C1 % 32 != 0)) return false;
+  if (g.taps > TC_MAX_TAPS) return false;
+  if (g.N > 32767 || g.Du > 32767 || g.Hu > 32767 || g.Wu > 32767) return false;
+  return get_encode() != nullptr;
+}
+
+bool conv_dgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) { return dgrad_tc_shape_ok(g, p); }
+
+size_t conv_dgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (!dgrad_tc_shape_ok(g, p)) return 0;
+  size_t w = align_up((size_t)g.Cout * g.Cin * g.taps * sizeof(bf16), 1024);
+  size_t t = is_upsampled(g) ? align_up((size_t)g.N * g.Du * g.Hu * g.Wu * g.Cin * sizeof(bf16), 1024) : 0;
+  return w + t;
+}
+
+int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  const size_t need = conv_dgrad_tc_workspace(g, p);
+  if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "conv_dgrad_tc: workspace %zu < %zu", p->workspace_bytes, need);
+  bf16* wd = (bf16*)p->workspace;
+  bf16* tmp = (bf16*)((char*)p->workspace + align_up((size_t)g.Cout * g.Cin * g.taps * sizeof(bf16), 1024));
+  {
+    long long total = (long long)g.Cout * g.Cin * g.taps;
+    int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
+    pack_dgrad_kernel<<<blocks, 256, 0, st>>>((const bf16*)p->fwd.w_packed, wd, g.Cout, g.Cin, g.taps);
+    RHO_CHECK_LAUNCH("pack_dgrad");
+  }
+  const bool up = is_upsampled(g);
+  const int bk = pick_block_k(g.Cout, 0), bn = pick_block_n(g.Cin);
+  TcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.N = g.N;
+  tp.Gd = g.Du; tp.Gh = g.Hu; tp.Gw = g.Wu;       // dgrad output grid = (upsampled) input grid = dY grid for stride 1
+  tp.os_d = tp.os_h = tp.os_w = 1;
+  tp.Do = g.Du; tp.Ho = g.Hu; tp.Wo = g.Wu;
+  tp.Cout = g.Cin; tp.C1 = g.Cout; tp.C2 = 0;
+  tp.n_blocks = g.Cin / bn;
+  tp.out_split = (!up && g.C2 > 0) ? g.C1 : 0;
+  pick_tile(tp);
+  tp.ntaps = g.taps;
+  for (int t = 0; t < g.taps; ++t) {
+    const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+    tp.taps[t].dn = 0;
+    tp.taps[t].dd = (int16_t)(kd - g.pd); tp.taps[t].dh = (int16_t)(kh - g.ph); tp.taps[t].dw = (int16_t)(kw - g.pw);
+    tp.taps[t].map = 0;
+    tp.taps[t].kofs = t * g.Cout;
+  }
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
+  ActView v;
+  v.base = p->dy;
+  v.dim[0] = g.Cout; v.dim[1] = g.Wo; v.dim[2] = g.Ho; v.dim[3] = g.Do; v.dim[4] = g.N;
+  v.stride[0] = (long long)g.Cout * 2; v.stride[1] = v.stride[0] * g.Wo; v.stride[2] = v.stride[1] * g.Ho; v.stride[3] = v.stride[2] * g.Do;
+  int rc = encode_view(&maps.a[0][0], v, box, bk);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps.w, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
+  if (rc) return rc;
+  if (!up) return dispatch_tc<bf16>(bn, bk, maps, tp, nullptr, nullptr, (bf16*)p->dx, (bf16*)p->dx2, st);
+  rc = dispatch_tc<bf16>(bn, bk, maps, tp, nullptr, nullptr, tmp, (bf16*)nullptr, st);
+  if (rc) return rc;
+  long long total = (long long)g.N * g.D * g.H * g.W * (g.Cin >> 2);
+  int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 16);
+  sum_pool_split_kernel<<<blocks, 256, 0, st>>>(tmp, (bf16*)p->dx, (bf16*)p->dx2, (long long)g.N * g.D, g.H, g.W, g.uh, g.uw, g.Cin, g.C1);
+  RHO_CHECK_LAUNCH("sum_pool_split");
+  return RHO_OK;
+}
 
 }  // namespace rho

@@ -1,0 +1,294 @@
+// conv_nd weight gradient on the 5th-generation tensor cores (bf16 activations, fp32 accumulation, sm_100a).
+//
+//   dW[co][tap][ci] = sum over output positions  dY[pos][co] * X[pos + tap offset][ci]
+//
+// Both operands are channels-last, i.e. the reduction index (position) is the *row* and the channels are contiguous:
+// exactly the MN-major canonical layout of tcgen05 (64 channels = one 128-byte swizzled row, 8 rows per atom).  The same
+// 5-D TMA boxes as the forward pass are used -- a box of 128 output positions of dY, and the box of X shifted by the
+// tap offset (out-of-bounds = zero = padding) -- and fed to the MMA without any transpose:
+//   D[m = (tap-or-ci-block atom, ci)][n = co] += A^T B,  A = X box(es) [128 pos x 64 ci] x 2 atoms,  B = dY box(es).
+// M = 128 is always two 64-channel atoms: two ci blocks of one tap when Cin >= 128, or the same ci block of TWO taps
+// when Cin = 64 (so 64-channel layers still fill the 128-row MMA).  Split-K over position tiles; the fp32 partials
+// [split][tap][ci][co] are reduced in a fixed order (deterministic) into the PyTorch layout [co][ci][tap].
+#include "conv_geom.cuh"
+#include "tc_common.cuh"
+
+namespace rho {
+
+struct WgParams {
+  int bn, bd, bh, bw, lbw, lbh, lbd;
+  int tiles_w, tiles_h, tiles_d, tiles_n, tiles_total;
+  int Cout, Cin, taps, C1;
+  int n_co_blocks;       // Cout / BN
+  int m_units;           // number of (atom pair) units = CTAs along M
+  int splits, tiles_per_split;
+  int16_t tap_dd[28], tap_dh[28], tap_dw[28];
+  // unit u -> two atoms: (tap, ci block) each; -1 tap = unused (duplicate)
+  int16_t unit_tap[2][256];
+  int16_t unit_cib[2][256];
+};
+
+struct WgMaps {
+  CUtensorMap x[2];   // x, x2 (concat partner)
+  CUtensorMap dy;
+};
+
+__device__ __forceinline__ uint64_t wg_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams p,
+                                                            float* __restrict__ partial) {
+  constexpr int BOX = 128 * 128;                 // bytes of one [128 pos x 64 ch] bf16 box
+  constexpr int A_BYTES = 2 * BOX, B_BYTES = (BN / 64) * BOX, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bid = blockIdx.x;
+  const int split = bid % p.splits; bid /= p.splits;
+  const int cob = bid % p.n_co_blocks;
+  const int unit = bid / p.n_co_blocks;
+  const int t0 = split * p.tiles_per_split;
+  const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+  const int nsteps = max(t1 - t0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        int r = t;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int td = r % p.tiles_d; r /= p.tiles_d;
+        const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = r * p.bn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int tap = p.unit_tap[a][unit], c = p.unit_cib[a][unit] * 64;
+          const int src = c >= p.C1 ? 1 : 0;
+          tma_load_5d(sa + a * BOX, &maps.x[src], &full_bar[stage], src ? c - p.C1 : c, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
+                      d0 + p.tap_dd[tap], n0);
+        }
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_5d(sa + A_BYTES + b * BOX, &maps.dy, &full_bar[stage], cob * BN + b * 64, w0, h0, d0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D fp32, A/B bf16, both MN-major, M = 128, N = BN
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < nsteps; ++s) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 16 positions per MMA: two 8-row atoms = 2048 bytes
+          const uint64_t a = wg_desc_mn(sa + k * 2048, BOX);
+          const uint64_t b = wg_desc_mn(sa + A_BYTES + k * 2048, BOX);
+          umma_f16(tmem_base, a, b, idesc, (s | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;            // accumulator row: atom = r / 64, ci within block = r % 64
+    const int a = r >> 6;
+    const int tap = p.unit_tap[a][unit];
+    const int ci = p.unit_cib[a][unit] * 64 + (r & 63);
+    const bool dup = a == 1 && p.unit_tap[0][unit] == p.unit_tap[1][unit] && p.unit_cib[0][unit] == p.unit_cib[1][unit];
+    float* dst = partial + ((((long long)split * p.taps + tap) * p.Cin + ci) * p.Cout) + cob * BN;
+    if (nsteps > 0) {
+      mbar_wait(&accum_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      if (nsteps > 0) tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+      else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (!dup) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(dst + c0 + e) =
+              make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+}
+
+// dw[co][ci][tap] = sum_split partial[split][tap][ci][co]
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps, float* __restrict__ dw) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes [tap][ci][co] (coalesced reads)
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int tap = (int)(i / ((long long)Cout * Cin));
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(long long)k * total + i];
+    dw[((long long)co * Cin + ci) * taps + tap] = s;
+  }
+}
+
+static int wg_pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int wg_ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+static int wg_block_n(int Cout) {
+  for (int bn : {256, 128, 64}) if (Cout % bn == 0) return bn;
+  return 0;
+}
+
+bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  const char* e = getenv("RHO_DISABLE_TCGEN05");
+  if (e && e[0] == '1') return false;
+  if (p->fwd.act_dtype != RHO_BF16) return false;
+  if (!(g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1)) return false;
+  if (g.Cin % 64 != 0 || g.C1 % 64 != 0 || wg_block_n(g.Cout) == 0) return false;
+  if (g.taps > 28) return false;
+  const int units = g.Cin >= 128 ? g.taps * (g.Cin / 128) : (g.taps + 1) / 2;
+  if (units > 256) return false;
+  if (g.N > 32767 || g.D > 32767 || g.H > 32767 || g.W > 32767) return false;
+  return get_encode() != nullptr;
+}
+
+static void wg_plan(const ConvGeom& g, WgParams& wp) {
+  memset(&wp, 0, sizeof(wp));
+  int rem = 128;
+  wp.bw = std::min(rem, wg_pow2_ceil(g.Wo)); rem /= wp.bw;
+  wp.bh = std::min(rem, wg_pow2_ceil(g.Ho)); rem /= wp.bh;
+  wp.bd = std::min(rem, wg_pow2_ceil(g.Do)); rem /= wp.bd;
+  wp.bn = rem;
+  wp.lbw = wg_ilog2(wp.bw); wp.lbh = wg_ilog2(wp.bh); wp.lbd = wg_ilog2(wp.bd);
+  wp.tiles_w = (int)ceil_div(g.Wo, wp.bw); wp.tiles_h = (int)ceil_div(g.Ho, wp.bh); wp.tiles_d = (int)ceil_div(g.Do, wp.bd);
+  wp.tiles_n = (int)ceil_div(g.N, wp.bn);
+  wp.tiles_total = wp.tiles_w * wp.tiles_h * wp.tiles_d * wp.tiles_n;
+  wp.Cout = g.Cout; wp.Cin = g.Cin; wp.taps = g.taps; wp.C1 = g.C1;
+  const int bn = wg_block_n(g.Cout);
+  wp.n_co_blocks = g.Cout / bn;
+  for (int t = 0; t < g.taps; ++t) {
+    const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+    wp.tap_dd[t] = (int16_t)(kd - g.pd); wp.tap_dh[t] = (int16_t)(kh - g.ph); wp.tap_dw[t] = (int16_t)(kw - g.pw);
+  }
+  int u = 0;
+  if (g.Cin >= 128) {
+    for (int t = 0; t < g.taps; ++t)
+      for (int cb = 0; cb < g.Cin / 128; ++cb, ++u) {
+        wp.unit_tap[0][u] = wp.unit_tap[1][u] = (int16_t)t;
+        wp.unit_cib[0][u] = (int16_t)(2 * cb); wp.unit_cib[1][u] = (int16_t)(2 * cb + 1);
+      }
+  } else {
+    for (int t = 0; t < g.taps; t += 2, ++u) {
+      wp.unit_tap[0][u] = (int16_t)t; wp.unit_tap[1][u] = (int16_t)std::min(t + 1, g.taps - 1);
+      wp.unit_cib[0][u] = wp.unit_cib[1][u] = 0;
+    }
+  }
+  wp.m_units = u;
+  long long ctas = (long long)wp.m_units * wp.n_co_blocks;
+  long long want = ceil_div((long long)sm_count() * 2, ctas);
+  long long max_splits = std::max<long long>(1, wp.tiles_total / 4);
+  long long s = std::max<long long>(1, std::min(want, max_splits));
+  if (s > 64) s = 64;
+  wp.tiles_per_split = (int)ceil_div(wp.tiles_total, s);
+  wp.splits = (int)ceil_div(wp.tiles_total, wp.tiles_per_split);
+}
+
+size_t conv_wgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (!conv_wgrad_tc_supported(g, p)) return 0;
+  WgParams wp;
+  wg_plan(g, wp);
+  return (size_t)wp.splits * g.Cout * g.Cin * g.taps * sizeof(float);
+}
+
+static int wg_encode(CUtensorMap* m, const void* base, int C, int W, int H, int D, int N, const WgParams& wp) {
+  auto enc = get_encode();
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H, (cuuint64_t)C * 2 * W * H * D};
+  cuuint32_t bdim[5] = {64, (cuuint32_t)wp.bw, (cuuint32_t)wp.bh, (cuuint32_t)wp.bd, (cuuint32_t)wp.bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad) failed: %d", (int)r);
+  return RHO_OK;
+}
+
+template <int BN, int STAGES>
+static int wg_launch(const WgMaps& maps, const WgParams& wp, float* partial, cudaStream_t st) {
+  constexpr size_t SMEM = (size_t)STAGES * (2 + BN / 64) * 128 * 128 + 1024;
+  auto kern = conv_wgrad_tc_kernel<BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  long long ctas = (long long)wp.m_units * wp.n_co_blocks * wp.splits;
+  kern<<<(unsigned)ctas, 192, SMEM, st>>>(maps, wp, partial);
+  RHO_CHECK_LAUNCH("conv_wgrad_tcgen05");
+  return RHO_OK;
+}
+
+int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  WgParams wp;
+  wg_plan(g, wp);
+  const size_t need = (size_t)wp.splits * g.Cout * g.Cin * g.taps * sizeof(float);
+  if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "conv_wgrad_tc: workspace %zu < %zu", p->workspace_bytes, need);
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = wg_encode(&maps.x[0], p->fwd.x, g.C1, g.W, g.H, g.D, g.N, wp);
+  if (rc) return rc;
+  if (g.C2) { rc = wg_encode(&maps.x[1], p->fwd.x2, g.C2, g.W, g.H, g.D, g.N, wp); if (rc) return rc; }
+  rc = wg_encode(&maps.dy, p->dy, g.Cout, g.Wo, g.Ho, g.Do, g.N, wp);
+  if (rc) return rc;
+  float* partial = (float*)p->workspace;
+  const int bn = wg_block_n(g.Cout);
+  if (bn == 256) rc = wg_launch<256, 2>(maps, wp, partial, st);
+  else if (bn == 128) rc = wg_launch<128, 3>(maps, wp, partial, st);
+  else rc = wg_launch<64, 4>(maps, wp, partial, st);
+  if (rc) return rc;
+  long long total = (long long)g.Cout * g.Cin * g.taps;
+  int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(partial, wp.splits, g.Cout, g.Cin, g.taps, p->dw);
+  RHO_CHECK_LAUNCH("wgrad_tc_reduce");
+  return RHO_OK;
+}
+
+}  // namespace rho
