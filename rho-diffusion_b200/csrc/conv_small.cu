@@ -106,6 +106,148 @@ __global__ void __launch_bounds__(256) conv_small_cout_kernel(ConvGeom g, const 
   }
 }
 
+
+// ---- fast paths (bf16 activations, stride 1, no upsample: the shapes every shipped config produces) ------------
+// small-Cout: L lanes share one output position, lane v owns the 16-byte channel octets v, v+L, ...: every warp load
+// instruction covers 32/L complete rows (full 128-byte lines when Cin = 64), every input row is fetched from L1/L2
+// once per tap by exactly one lane group, and the L partial sums meet in a log2(L)-step shuffle at the end.
+template <int L, typename TO>
+__global__ void __launch_bounds__(256) conv_small_cout_vec_kernel(ConvGeom g, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const float* __restrict__ bias, TO* __restrict__ y) {
+  extern __shared__ __align__(16) float ws_dyn[];   // [co][tap*Cin + ci]
+  const int K = g.taps * g.Cin;
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) ws_dyn[i] = to_f32(w[i]);
+  __syncthreads();
+  const int v = threadIdx.x % L;
+  const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const bool valid = m < g.M;
+  unsigned t = valid ? (unsigned)m : 0u;                      // host guarantees M < 2^31
+  const int ow = (int)(t % (unsigned)g.Wo); t /= (unsigned)g.Wo;
+  const int oh = (int)(t % (unsigned)g.Ho); t /= (unsigned)g.Ho;
+  const int od = (int)(t % (unsigned)g.Do);
+  const int n = (int)(t / (unsigned)g.Do);
+  const int octets = g.Cin >> 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int tap = 0;
+  for (int kd = 0; kd < g.kd; ++kd) {
+    const int pd = od + kd - g.pd;
+    const bool okd = valid && pd >= 0 && pd < g.D;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int ph = oh + kh - g.ph;
+      const bool okh = okd && ph >= 0 && ph < g.H;
+      const long long base = (((long long)n * g.D + pd) * g.H + ph) * g.W;
+      for (int kw = 0; kw < g.kw; ++kw, ++tap) {
+        const int pw = ow + kw - g.pw;
+        if (!(okh && pw >= 0 && pw < g.W)) continue;
+        const uint4* row = reinterpret_cast<const uint4*>(x + (base + pw) * g.Cin);
+        for (int o = v; o < octets; o += L) {
+          const uint4 q = __ldg(row + o);
+          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+          float xv[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { xv[2 * j] = __uint_as_float(u[j] << 16); xv[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u); }
+          const int k = tap * g.Cin + o * 8;
+#pragma unroll
+          for (int co = 0; co < 4; ++co) {
+            if (co < g.Cout) {
+              const float4 w0 = *reinterpret_cast<const float4*>(&ws_dyn[co * K + k]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&ws_dyn[co * K + k + 4]);
+              float a = acc[co];
+              a = fmaf(xv[0], w0.x, a); a = fmaf(xv[1], w0.y, a); a = fmaf(xv[2], w0.z, a); a = fmaf(xv[3], w0.w, a);
+              a = fmaf(xv[4], w1.x, a); a = fmaf(xv[5], w1.y, a); a = fmaf(xv[6], w1.z, a); a = fmaf(xv[7], w1.w, a);
+              acc[co] = a;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    if (co < g.Cout) {
+      float s = acc[co];
+#pragma unroll
+      for (int off = L >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (v == 0 && valid) y[m * g.Cout + co] = from_f32<TO>(s + (bias ? bias[co] : 0.f));
+    }
+  }
+}
+
+// small-Cin: 8 lanes share a run of PW = 4 consecutive output positions along W, each lane produces 8 output channels
+// for all four (the (kw + j) input column is loaded once and feeds up to three taps; each weight vector is read from
+// shared memory once per four positions).  A warp store instruction writes four complete 128-byte lines at Cout = 64.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_small_cin_row4_kernel(ConvGeom g, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const float* __restrict__ bias, bf16* __restrict__ y) {
+  extern __shared__ __align__(16) float ws_dyn[];   // [tap*Cin + ci][Cout]
+  const int K = g.taps * CIN;
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) {
+    const int co = i / K, k = i % K;
+    ws_dyn[k * g.Cout + co] = to_f32(w[i]);
+  }
+  __syncthreads();
+  const int groups = g.Cout >> 3;
+  const int wq = g.Wo >> 2;                                   // runs per output row
+  const long long total = (g.M >> 2) * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % groups) * 8;
+  unsigned t = (unsigned)(idx / groups);                      // run index; host guarantees M < 2^31
+  const int ow0 = (int)(t % (unsigned)wq) * 4; t /= (unsigned)wq;
+  const int oh = (int)(t % (unsigned)g.Ho); t /= (unsigned)g.Ho;
+  const int od = (int)(t % (unsigned)g.Do);
+  const int n = (int)(t / (unsigned)g.Do);
+  float acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float b = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][j] = b;
+  }
+  for (int kd = 0; kd < g.kd; ++kd) {
+    const int pd = od + kd - g.pd;
+    if (pd < 0 || pd >= g.D) continue;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int ph = oh + kh - g.ph;
+      if (ph < 0 || ph >= g.H) continue;
+      const bf16* row = x + ((((long long)n * g.D + pd) * g.H + ph) * g.W) * CIN;
+      const int tap0 = (kd * g.kh + kh) * g.kw;
+      // input columns ow0 - pw .. ow0 + 3 + (kw - 1 - pw)
+      for (int col = 0; col < 4 + g.kw - 1; ++col) {
+        const int pw = ow0 + col - g.pw;
+        if (pw < 0 || pw >= g.W) continue;
+        float xv[CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xv[ci] = to_f32(row[(long long)pw * CIN + ci]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kw = col - q;                             // tap that maps input column `col` to output q
+          if (kw < 0 || kw >= g.kw) continue;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float* wp = &ws_dyn[((tap0 + kw) * CIN + ci) * g.Cout + c0];
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+            acc[q][0] = fmaf(xv[ci], w0.x, acc[q][0]); acc[q][1] = fmaf(xv[ci], w0.y, acc[q][1]);
+            acc[q][2] = fmaf(xv[ci], w0.z, acc[q][2]); acc[q][3] = fmaf(xv[ci], w0.w, acc[q][3]);
+            acc[q][4] = fmaf(xv[ci], w1.x, acc[q][4]); acc[q][5] = fmaf(xv[ci], w1.y, acc[q][5]);
+            acc[q][6] = fmaf(xv[ci], w1.z, acc[q][6]); acc[q][7] = fmaf(xv[ci], w1.w, acc[q][7]);
+          }
+        }
+      }
+    }
+  }
+  const long long m0 = (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[q][2 * j], acc[q][2 * j + 1]);
+    *reinterpret_cast<uint4*>(y + (m0 + q) * g.Cout + c0) = o;
+  }
+}
+
 bool conv_small_supported(const ConvGeom& g, const rho_conv_params* p) {
   if (p->residual || g.C2 != 0) return false;
   if ((long long)g.taps * g.Cin * g.Cout > SC_MAX_W) return false;
@@ -129,8 +271,46 @@ static int launch_small(const ConvGeom& g, const rho_conv_params* p, cudaStream_
   return RHO_OK;
 }
 
+// bf16 fast paths: unit stride, no fused upsample, fewer than 2^31 output positions
+static bool small_fast_geom(const ConvGeom& g) {
+  return g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1 && g.M < (1ll << 31);
+}
+template <typename TO>
+static int launch_small_cout_vec(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
+  const int octets = g.Cin >> 3;
+  const int L = octets % 8 == 0 ? 8 : octets % 4 == 0 ? 4 : octets % 2 == 0 ? 2 : 1;
+  const size_t smem = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
+  const unsigned blocks = (unsigned)ceil_div(g.M * L, 256);
+#define RHO_SCV(LL) conv_small_cout_vec_kernel<LL, TO><<<blocks, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (TO*)p->y)
+  if (L == 8) RHO_SCV(8);
+  else if (L == 4) RHO_SCV(4);
+  else if (L == 2) RHO_SCV(2);
+  else RHO_SCV(1);
+#undef RHO_SCV
+  RHO_CHECK_LAUNCH("conv_small_cout_vec");
+  return RHO_OK;
+}
+static int launch_small_cin_row4(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
+  const size_t smem = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
+  const unsigned blocks = (unsigned)ceil_div((g.M >> 2) * (g.Cout >> 3), 256);
+#define RHO_SCR(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (bf16*)p->y)
+  switch (g.Cin) {
+    case 1: RHO_SCR(1); break;
+    case 2: RHO_SCR(2); break;
+    case 3: RHO_SCR(3); break;
+    default: RHO_SCR(4); break;
+  }
+#undef RHO_SCR
+  RHO_CHECK_LAUNCH("conv_small_cin_row4");
+  return RHO_OK;
+}
+
 int conv_small_fwd(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const int a = p->act_dtype, w = p->w_dtype, f = p->y_f32;
+  if (a == RHO_BF16 && w == RHO_BF16 && small_fast_geom(g)) {
+    if (g.Cout <= 4 && g.Cin % 8 == 0) return f ? launch_small_cout_vec<float>(g, p, st) : launch_small_cout_vec<bf16>(g, p, st);
+    if (g.Cin <= 4 && g.Cout % 8 == 0 && g.Wo % 4 == 0 && !f) return launch_small_cin_row4(g, p, st);
+  }
   if (a == RHO_F32 && w == RHO_F32) return launch_small<float, float, float>(g, p, st);
   if (a == RHO_BF16 && w == RHO_BF16 && !f) return launch_small<bf16, bf16, bf16>(g, p, st);
   if (a == RHO_BF16 && w == RHO_BF16 && f) return launch_small<bf16, bf16, float>(g, p, st);

@@ -499,99 +499,102 @@ __device__ __forceinline__ void gn_load8(const bf16* __restrict__ x, const bf16*
   else load8(x2 + row * C2 + (c - C1), v);
 }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_stats8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
-                                                               const float* __restrict__ pre_add, int pre_stride, int C1, int C2,
-                                                               int64_t S, int G, int chunks, float* __restrict__ partial) {
+// One CTA streams a contiguous slab of positions.  Every channel of a group is shifted by the SAME constant (the value
+// of the group's first channel at the slab's first position), so the per-thread shifted sums add up across rows and
+// across the channels of a group without Chan merges; the merge across slabs happens in gn_stats_finalize_kernel.
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_stats8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                                  const float* __restrict__ pre_add, int pre_stride, int C1, int C2,
+                                                                  int64_t S, int G, int chunks, float* __restrict__ partial) {
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int rows = GN_THREADS / CV;
+  const int cpg = C / G;
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int64_t per = (S + chunks - 1) / chunks;
   const int64_t p0 = (int64_t)chunk * per, p1 = min(S, p0 + per);
   const int tid = threadIdx.x;
   const int row = tid / CV, cv = tid - row * CV;
-  const bool active = row < rows;
+  const bool active = row < rows && p0 < p1;
   const int c = cv * 8;
-  __shared__ float sc_n[2048], sc_mean[2048], sc_m2[2048];
+  __shared__ float sm1[2048], sm2[2048];
   const bf16* xb = x + (int64_t)n * S * C1;
   const bf16* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
-  float K[8], s1[8], s2[8], pa[8];
-  float cnt = 0.f;
+  auto value_at = [&](int64_t p, int ch) -> float {
+    const float v = ch < C1 ? __bfloat162float(xb[p * C1 + ch]) : __bfloat162float(x2b[p * C2 + (ch - C1)]);
+    return v + (pre_add ? pre_add[(int64_t)n * pre_stride + ch] : 0.f);
+  };
+  float s1[8], s2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { K[j] = 0.f; s1[j] = 0.f; s2[j] = 0.f; pa[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (active) {
-    if (pre_add) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pa[j] = pre_add[(int64_t)n * pre_stride + c + j];
-    }
-    int64_t p = p0 + row;
-    if (p < p1) {
-      float v[8];
-      gn_load8(xb, x2b, C1, C2, p, c, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) K[j] = v[j] + pa[j];
-    }
-    for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
-      float v[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) gn_load8(xb, x2b, C1, C2, p + (int64_t)u * rows, c, v[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = (v[u][j] + pa[j]) - K[j];
-          s1[j] += d;
-          s2[j] = fmaf(d, d, s2[j]);
-        }
-      cnt += 4.f;
-    }
-    for (; p < p1; p += rows) {
-      float v[8];
-      gn_load8(xb, x2b, C1, C2, p, c, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = (v[j] + pa[j]) - K[j];
-        s1[j] += d;
-        s2[j] = fmaf(d, d, s2[j]);
-      }
-      cnt += 1.f;
-    }
+    float Kp[8];                      // shift minus the per-channel pre-add: d = (v + pa) - K = v - Kp
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int idx = row * C + c + j;
-      sc_n[idx] = cnt;
-      sc_mean[idx] = cnt > 0.f ? K[j] + s1[j] / cnt : 0.f;
-      sc_m2[idx] = cnt > 0.f ? fmaxf(s2[j] - s1[j] * s1[j] / cnt, 0.f) : 0.f;
+      const int gfirst = ((c + j) / cpg) * cpg;
+      Kp[j] = value_at(p0, gfirst) - (pre_add ? pre_add[(int64_t)n * pre_stride + c + j] : 0.f);
     }
+    const bf16* src = c < C1 ? xb + c : x2b + (c - C1);
+    const int64_t stride = c < C1 ? C1 : C2;
+    auto accum = [&](const uint4& q) {
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = __uint_as_float(u[j] << 16) - Kp[2 * j];
+        const float d1 = __uint_as_float(u[j] & 0xffff0000u) - Kp[2 * j + 1];
+        s1[2 * j] += d0; s2[2 * j] = fmaf(d0, d0, s2[2 * j]);
+        s1[2 * j + 1] += d1; s2[2 * j + 1] = fmaf(d1, d1, s2[2 * j + 1]);
+      }
+    };
+    int64_t p = p0 + row;
+    for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(src + (p + (int64_t)u * rows) * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accum(q[u]);
+    }
+    for (; p < p1; p += rows) accum(__ldg(reinterpret_cast<const uint4*>(src + p * stride)));
+  }
+  if (row < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sm1[row * C + c + j] = s1[j]; sm2[row * C + c + j] = s2[j]; }
   }
   __syncthreads();
   for (int cc = tid; cc < C; cc += GN_THREADS) {
-    Moments a = {sc_n[cc], sc_mean[cc], sc_m2[cc]};
-    for (int r = 1; r < rows; ++r) {
-      Moments b = {sc_n[r * C + cc], sc_mean[r * C + cc], sc_m2[r * C + cc]};
-      a = merge(a, b);
-    }
-    sc_n[cc] = a.n; sc_mean[cc] = a.mean; sc_m2[cc] = a.m2;   // row 0 now holds the per-channel moments
+    float a1 = sm1[cc], a2 = sm2[cc];
+    for (int r = 1; r < rows; ++r) { a1 += sm1[r * C + cc]; a2 += sm2[r * C + cc]; }
+    sm1[cc] = a1; sm2[cc] = a2;
   }
   __syncthreads();
-  const int cpg = C / G;
   for (int g = tid; g < G; g += GN_THREADS) {
-    Moments a = {sc_n[g * cpg], sc_mean[g * cpg], sc_m2[g * cpg]};
-    for (int j = 1; j < cpg; ++j) {
-      Moments b = {sc_n[g * cpg + j], sc_mean[g * cpg + j], sc_m2[g * cpg + j]};
-      a = merge(a, b);
-    }
+    float a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < cpg; ++j) { a1 += sm1[g * cpg + j]; a2 += sm2[g * cpg + j]; }
     float* o = partial + (((int64_t)n * chunks + chunk) * G + g) * 3;
-    o[0] = a.n; o[1] = a.mean; o[2] = a.m2;
+    if (p0 < p1) {
+      const float cnt = (float)((p1 - p0) * cpg);
+      o[0] = cnt;
+      o[1] = value_at(p0, g * cpg) + a1 / cnt;
+      o[2] = fmaxf(a2 - a1 * a1 / cnt, 0.f);
+    } else {
+      o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
+    }
   }
 }
 
-__global__ void __launch_bounds__(GN_THREADS) gn_apply8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
-                                                               const float* __restrict__ pre_add, int pre_stride,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               const float* __restrict__ scale, const float* __restrict__ shift,
-                                                               int film_stride, const float* __restrict__ stats, int C1, int C2,
-                                                               int64_t S, int G, int chunks, int act, bf16* __restrict__ y) {
+// SiLU through one MUFU: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx: 2^-11 relative, below bf16 resolution)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_apply8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                                  const float* __restrict__ pre_add, int pre_stride,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                  int film_stride, const float* __restrict__ stats, int C1, int C2,
+                                                                  int64_t S, int G, int chunks, int act, bf16* __restrict__ y) {
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int rows = GN_THREADS / CV;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply8_kernel(const bf16* __res
   if (row >= rows) return;
   const int c = cv * 8;
   const int cpg = C / G;
-  // y = act(x * a + b): a = rstd*gamma*(1+sc), b = ((pa - mean)*rstd*gamma + beta)*(1+sc) + sh
+  // y = act(x * a + b): a = rstd*gamma*(1+sc), b = ((pa - mean)*rstd*gamma + beta)*(1+sc) + sh   (halved for the SiLU form)
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -615,34 +618,45 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply8_kernel(const bf16* __res
     const float sh = shift ? shift[(int64_t)n * film_stride + c + j] : 0.f;
     a[j] = ga * f;
     b[j] = ((pa - mean) * ga + beta[c + j]) * f + sh;
+    if (SILU) { a[j] *= 0.5f; b[j] *= 0.5f; }
   }
-  const bf16* xb = x + (int64_t)n * S * C1;
-  const bf16* x2b = x2 ? x2 + (int64_t)n * S * C2 : nullptr;
-  bf16* yb = y + (int64_t)n * S * C;
+  const bf16* src = c < C1 ? x + (int64_t)n * S * C1 + c : x2 + (int64_t)n * S * C2 + (c - C1);
+  const int64_t stride = c < C1 ? C1 : C2;
+  bf16* dst = y + (int64_t)n * S * C + c;
+  auto transform = [&](const uint4& q) -> uint4 {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v0 = fmaf(__uint_as_float(u[j] << 16), a[2 * j], b[2 * j]);
+      float v1 = fmaf(__uint_as_float(u[j] & 0xffff0000u), a[2 * j + 1], b[2 * j + 1]);
+      if (SILU) {
+        v0 = fmaf(v0, tanh_approx(v0), v0);
+        v1 = fmaf(v1, tanh_approx(v1), v1);
+      } else {
+        v0 = apply_act(v0, act);
+        v1 = apply_act(v1, act);
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      ow[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return o;
+  };
   int64_t p = p0 + row;
   for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
-    float v[4][8];
+    uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) gn_load8(xb, x2b, C1, C2, p + (int64_t)u * rows, c, v[u]);
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(src + (p + (int64_t)u * rows) * stride));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[u][j] = apply_act(fmaf(v[u][j], a[j], b[j]), act);
-      store8(yb + (p + (int64_t)u * rows) * C + c, v[u]);
-    }
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(dst + (p + (int64_t)u * rows) * C) = transform(q[u]);
   }
-  for (; p < p1; p += rows) {
-    float v[8];
-    gn_load8(xb, x2b, C1, C2, p, c, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(v[j], a[j], b[j]), act);
-    store8(yb + p * C + c, v);
-  }
+  for (; p < p1; p += rows) *reinterpret_cast<uint4*>(dst + p * C) = transform(__ldg(reinterpret_cast<const uint4*>(src + p * stride)));
 }
 
 static int gn_chunks8(int N, int64_t S, int C) {
   const int rows = GN_THREADS / (C >> 3);
-  int64_t target = (int64_t)sm_count() * 8;
+  int64_t target = (int64_t)sm_count() * 4;          // one resident wave: 4 CTAs per SM
   int64_t chunks = ceil_div(target, N);
   int64_t max_chunks = ceil_div(S, (int64_t)rows * 8);
   if (chunks > max_chunks) chunks = max_chunks;
@@ -733,9 +747,14 @@ int rho_gn_apply(const rho_gn_params* p, rho_stream_t stream) {
   if (gn_fast8(p) && p->out_dtype == RHO_BF16) {
     int chunks8 = gn_chunks8(p->N, p->S, C);
     dim3 grid8(chunks8, p->N);
-    gn_apply8_kernel<<<grid8, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->gamma, p->beta,
-                                                   p->scale, p->shift, p->film_stride, p->stats, p->C1, p->C2, p->S, p->groups, chunks8,
-                                                   p->act, (bf16*)p->y);
+    if (p->act == RHO_ACT_SILU)
+      gn_apply8_kernel<true><<<grid8, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->gamma,
+                                                           p->beta, p->scale, p->shift, p->film_stride, p->stats, p->C1, p->C2, p->S,
+                                                           p->groups, chunks8, p->act, (bf16*)p->y);
+    else
+      gn_apply8_kernel<false><<<grid8, GN_THREADS, 0, st>>>((const bf16*)p->x, (const bf16*)p->x2, p->pre_add, p->pre_add_stride, p->gamma,
+                                                            p->beta, p->scale, p->shift, p->film_stride, p->stats, p->C1, p->C2, p->S,
+                                                            p->groups, chunks8, p->act, (bf16*)p->y);
     RHO_CHECK_LAUNCH("gn_apply8");
     return RHO_OK;
   }
