@@ -1,0 +1,472 @@
+// Backward of QKVAttention / QKVAttentionLegacy (rho_diffusion/models/unet_v2.py:365-436; reached through the
+// always-on checkpoint of AttentionBlock, unet_v2.py:334) on the 5th-generation tensor cores (sm_100a).
+//
+// With S = scale * Q K^T, P = exp(S - lse) (lse from the forward), delta = rowsum(dO o O):
+//     dV = P^T dO        dP = dO V^T        dS = P o (dP - delta)        dQ = scale * dS K        dK = scale * dS^T Q
+// Two deterministic kernels (no atomics), both recomputing P from the saved log-sum-exp:
+//   attn_bwd_dq_kernel : one CTA = 128 queries, loops over 64-key tiles.
+//        S  = Q K_j^T  (128x64)  -> TMEM [0,64)          dP = dO V_j^T (128x64) -> TMEM [64,128)
+//        thread r <-> query row r: dS row -> bf16 -> swizzled smem;   dQ += dS K_j  -> TMEM [128,128+ch)
+//   attn_bwd_dkv_kernel: one CTA = 128 keys, loops over 64-query tiles (the transposed problem, so that the thread
+//        <-> TMEM-lane mapping is again one thread per output row):
+//        S^T = K Q_i^T (128x64) -> TMEM [0,64)           dP^T = V dO_i^T        -> TMEM [64,128)
+//        P^T, dS^T rows -> bf16 -> smem;   dV += P^T dO_i -> TMEM,   dK += dS^T Q_i -> TMEM
+//        (lse / delta are per COLUMN here: staged per tile in shared memory and read as broadcasts)
+// Every operand is a TMA box of the channels-last qkv / dout tensors in the 128-byte-swizzled layout: a [rows x 64 ch]
+// tile serves as a K-major operand (Q K^T, dO V^T) and, unchanged, as an MN-major B operand (dS K, P^T dO, dS^T Q).
+// Out-of-range rows are zero-filled by TMA, which makes every padded contribution exactly 0 without masks.
+// Warp roles as in the forward: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = the 128
+// row-owner threads.  ch = 64: 256 TMEM columns and <= 100 KB smem per CTA -> two CTAs per SM, so one CTA's
+// exponentials (MUFU) overlap the other's MMAs.
+#include "tc_common.cuh"
+
+namespace rho {
+
+struct AttnBwdTcParams {
+  int T, heads, C;
+  int q_col, k_col, v_col, head_stride;
+  float scale, scale_log2;
+};
+
+constexpr int AB_ROWS = 128;   // rows (queries resp. keys) owned by a CTA
+constexpr int AB_COLS = 64;    // columns (keys resp. queries) per inner tile
+constexpr float AB_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// store 32 consecutive bf16 columns [c, c+32) of row r into a [128 rows][64 cols] 128B-swizzled K-major tile
+__device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int c, const uint32_t (&packed)[16]) {
+  uint8_t* rowp = tile + r * 128;
+  const int ch0 = c >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int chunk = (ch0 + i) ^ (r & 7);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dQ
+// ------------------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
+    attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv64,
+                       const __grid_constant__ CUtensorMap do128, const AttnBwdTcParams p, const float* __restrict__ lse,
+                       const float* __restrict__ delta, bf16* __restrict__ dqkv) {
+  constexpr int KB = CH / 64;
+  constexpr int ROW_TILE = AB_ROWS * 128;       // [128 rows x 64 ch] bf16
+  constexpr int COL_TILE = AB_COLS * 128;       // [64 rows x 64 ch] bf16
+  constexpr int Q_BYTES = KB * ROW_TILE, KV_BYTES = KB * COL_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + Q_BYTES;
+  uint8_t* sK = sdO + Q_BYTES;                  // [2 stages][KB][64 x 64]
+  uint8_t* sV = sK + 2 * KV_BYTES;
+  uint8_t* sdS = sV + 2 * KV_BYTES;             // [128][64]
+  __shared__ uint64_t q_full, kv_full[2], kv_empty[2], sdp_ready, ds_ready, dq_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AB_ROWS, h = blockIdx.y, n = blockIdx.z;
+  const int nt = (p.T + AB_COLS - 1) / AB_COLS;
+  const int qc = p.q_col + h * p.head_stride, kc = p.k_col + h * p.head_stride, vc = p.v_col + h * p.head_stride;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&sdp_ready, 1); mbar_init(&dq_done, 1);
+    mbar_init(&ds_ready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_base_s;            // S : [0, 64)
+  const uint32_t tmem_dp = tmem_base_s + 64;      // dP: [64, 128)
+  const uint32_t tmem_dq = tmem_base_s + 128;     // dQ: [128, 128 + CH)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, 2 * Q_BYTES);
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_3d(sQ + kb * ROW_TILE, &qkv128, &q_full, qc + kb * 64, q0, n);
+        tma_load_3d(sdO + kb * ROW_TILE, &do128, &q_full, h * CH + kb * 64, q0, n);
+      }
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(sK + s * KV_BYTES + kb * COL_TILE, &qkv64, &kv_full[s], kc + kb * 64, j * AB_COLS, n);
+          tma_load_3d(sV + s * KV_BYTES + kb * COL_TILE, &qkv64, &kv_full[s], vc + kb * 64, j * AB_COLS, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
+      const uint32_t idesc_dq = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                                ((uint32_t)(AB_ROWS >> 4) << 24);
+      auto issue_sdp = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * ROW_TILE));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + s * KV_BYTES + kb * COL_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sdO + kb * ROW_TILE));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sV + s * KV_BYTES + kb * COL_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_dp, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+        }
+        umma_commit(&sdp_ready);
+      };
+      mbar_wait(&q_full, 0);
+      issue_sdp(0);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&ds_ready, (uint32_t)j & 1);    // dS_j is in smem; the row owners are done reading S_j / dP_j
+        tc_fence_after();
+        const uint64_t a = at_desc_kmajor<128>(smem_u32(sdS));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {             // 16 keys per MMA = two 8-row atoms of the K tile
+          const uint64_t b = at_desc_mnmajor(smem_u32(sK + s * KV_BYTES + k * 16 * 128), COL_TILE);
+          umma_f16(tmem_dq, a + (uint64_t)(2 * k), b, idesc_dq, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        if (j + 1 < nt) issue_sdp(j + 1);         // its commit also covers dQ_j: dS may be overwritten after sdp_ready
+        else umma_commit(&dq_done);
+      }
+    }
+  } else {
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const int q = q0 + r;
+    const long long row_idx = ((long long)n * p.heads + h) * p.T + q;
+    const float lse2 = q < p.T ? lse[row_idx] * AB_LOG2E : 0.f;
+    const float dl = q < p.T ? delta[row_idx] : 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&sdp_ready, (uint32_t)j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < AB_COLS; c += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32_async(tmem_s + lane_addr + (uint32_t)c, vs);
+        tmem_ld32_async(tmem_dp + lane_addr + (uint32_t)c, vd);
+        tmem_wait_ld();
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -lse2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -lse2));
+          packed[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - dl), p1 * (__uint_as_float(vd[e + 1]) - dl));
+        }
+        store_row_chunk32(sdS, r, c, packed);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&ds_ready);
+    }
+    mbar_wait(&dq_done, 0);
+    tc_fence_after();
+    bf16* orow = dqkv + ((long long)n * p.T + q) * (3 * p.C) + qc;
+#pragma unroll 1
+    for (int c = 0; c < CH; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_dq + lane_addr + (uint32_t)c, v);
+      if (q < p.T) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[e]) * p.scale, __uint_as_float(v[e + 1]) * p.scale);
+          o.y = pack_bf16x2(__uint_as_float(v[e + 2]) * p.scale, __uint_as_float(v[e + 3]) * p.scale);
+          o.z = pack_bf16x2(__uint_as_float(v[e + 4]) * p.scale, __uint_as_float(v[e + 5]) * p.scale);
+          o.w = pack_bf16x2(__uint_as_float(v[e + 6]) * p.scale, __uint_as_float(v[e + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(orow + c + e) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(256u));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dK, dV
+// ------------------------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
+    attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv64,
+                        const __grid_constant__ CUtensorMap do64, const AttnBwdTcParams p, const float* __restrict__ lse,
+                        const float* __restrict__ delta, bf16* __restrict__ dqkv) {
+  constexpr int KB = CH / 64;
+  constexpr int ROW_TILE = AB_ROWS * 128;
+  constexpr int COL_TILE = AB_COLS * 128;
+  constexpr int K_BYTES = KB * ROW_TILE, QD_BYTES = KB * COL_TILE;
+  constexpr uint32_t TMEM_COLS = CH == 64 ? 256u : 512u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + K_BYTES;
+  uint8_t* sQ = sV + K_BYTES;                   // [2 stages][KB][64 x 64]
+  uint8_t* sdO = sQ + 2 * QD_BYTES;
+  uint8_t* sP = sdO + 2 * QD_BYTES;             // P^T  [128 keys][64 queries]
+  uint8_t* sdS = sP + ROW_TILE;                 // dS^T [128 keys][64 queries]
+  __shared__ uint64_t kv_full, qd_full[2], qd_empty[2], st_ready, pds_ready, acc_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sLD[2][128];   // per query tile: [0,64) lse*log2e, [64,128) delta
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * AB_ROWS, h = blockIdx.y, n = blockIdx.z;
+  const int ni = (p.T + AB_COLS - 1) / AB_COLS;
+  const int qc = p.q_col + h * p.head_stride, kc = p.k_col + h * p.head_stride, vc = p.v_col + h * p.head_stride;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
+    mbar_init(&st_ready, 1); mbar_init(&acc_done, 1);
+    mbar_init(&pds_ready, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_st = tmem_base_s;                 // S^T : [0, 64)
+  const uint32_t tmem_dpt = tmem_base_s + 64;           // dP^T: [64, 128)
+  const uint32_t tmem_dk = tmem_base_s + 128;           // dK  : [128, 128 + CH)
+  const uint32_t tmem_dv = tmem_base_s + 128 + CH;      // dV  : [128 + CH, 128 + 2 CH)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&kv_full, 2 * K_BYTES);
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_3d(sK + kb * ROW_TILE, &qkv128, &kv_full, kc + kb * 64, k0, n);
+        tma_load_3d(sV + kb * ROW_TILE, &qkv128, &kv_full, vc + kb * 64, k0, n);
+      }
+      for (int i = 0; i < ni; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qd_empty[s], ((uint32_t)(i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qd_full[s], 2 * QD_BYTES);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_3d(sQ + s * QD_BYTES + kb * COL_TILE, &qkv64, &qd_full[s], qc + kb * 64, i * AB_COLS, n);
+          tma_load_3d(sdO + s * QD_BYTES + kb * COL_TILE, &do64, &qd_full[s], h * CH + kb * 64, i * AB_COLS, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_st = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
+      const uint32_t idesc_acc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                                 ((uint32_t)(AB_ROWS >> 4) << 24);
+      auto issue_st = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(&qd_full[s], (uint32_t)(i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sK + kb * ROW_TILE));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sQ + s * QD_BYTES + kb * COL_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_st, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sV + kb * ROW_TILE));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sdO + s * QD_BYTES + kb * COL_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_dpt, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
+        }
+        umma_commit(&st_ready);
+      };
+      mbar_wait(&kv_full, 0);
+      issue_st(0);
+      for (int i = 0; i < ni; ++i) {
+        const int s = i & 1;
+        mbar_wait(&pds_ready, (uint32_t)i & 1);
+        tc_fence_after();
+        const uint64_t ap = at_desc_kmajor<128>(smem_u32(sP));
+        const uint64_t ads = at_desc_kmajor<128>(smem_u32(sdS));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {             // 16 queries per MMA
+          const uint64_t bdo = at_desc_mnmajor(smem_u32(sdO + s * QD_BYTES + k * 16 * 128), COL_TILE);
+          umma_f16(tmem_dv, ap + (uint64_t)(2 * k), bdo, idesc_acc, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t bq = at_desc_mnmajor(smem_u32(sQ + s * QD_BYTES + k * 16 * 128), COL_TILE);
+          umma_f16(tmem_dk, ads + (uint64_t)(2 * k), bq, idesc_acc, (i | k) != 0);
+        }
+        umma_commit(&qd_empty[s]);
+        if (i + 1 < ni) issue_st(i + 1);
+        else umma_commit(&acc_done);
+      }
+    }
+  } else {
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;               // key row
+    const int t = threadIdx.x - 64;               // 0..127: slot in sLD
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const long long col_base = ((long long)n * p.heads + h) * p.T;
+    auto fetch = [&](int i) -> float {            // this thread's entry of tile i's lse/delta staging
+      const int qq = i * AB_COLS + (t & 63);
+      if (qq >= p.T) return 0.f;
+      return t < 64 ? lse[col_base + qq] * AB_LOG2E : delta[col_base + qq];
+    };
+    sLD[0][t] = fetch(0);
+    named_bar_sync(1, 128);
+    for (int i = 0; i < ni; ++i) {
+      const float nxt = i + 1 < ni ? fetch(i + 1) : 0.f;
+      const float* ld = sLD[i & 1];
+      mbar_wait(&st_ready, (uint32_t)i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < AB_COLS; c += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32_async(tmem_st + lane_addr + (uint32_t)c, vs);
+        tmem_ld32_async(tmem_dpt + lane_addr + (uint32_t)c, vd);
+        tmem_wait_ld();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(ld + c + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(ld + 64 + c + e);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -l4.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -l4.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(vs[e + 2]), p.scale_log2, -l4.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(vs[e + 3]), p.scale_log2, -l4.w));
+          pp[e >> 1] = pack_bf16x2(p0, p1);
+          pp[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+          pd[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - d4.x), p1 * (__uint_as_float(vd[e + 1]) - d4.y));
+          pd[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(vd[e + 2]) - d4.z), p3 * (__uint_as_float(vd[e + 3]) - d4.w));
+        }
+        store_row_chunk32(sP, r, c, pp);
+        store_row_chunk32(sdS, r, c, pd);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&pds_ready);
+      sLD[(i + 1) & 1][t] = nxt;
+      named_bar_sync(1, 128);
+    }
+    mbar_wait(&acc_done, 0);
+    tc_fence_after();
+    const int key = k0 + r;
+    bf16* krow = dqkv + ((long long)n * p.T + key) * (3 * p.C) + kc;
+    bf16* vrow = dqkv + ((long long)n * p.T + key) * (3 * p.C) + vc;
+#pragma unroll 1
+    for (int c = 0; c < CH; c += 32) {
+      uint32_t v[32], w[32];
+      tmem_ld32_async(tmem_dk + lane_addr + (uint32_t)c, v);
+      tmem_ld32_async(tmem_dv + lane_addr + (uint32_t)c, w);
+      tmem_wait_ld();
+      if (key < p.T) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[e]) * p.scale, __uint_as_float(v[e + 1]) * p.scale);
+          o.y = pack_bf16x2(__uint_as_float(v[e + 2]) * p.scale, __uint_as_float(v[e + 3]) * p.scale);
+          o.z = pack_bf16x2(__uint_as_float(v[e + 4]) * p.scale, __uint_as_float(v[e + 5]) * p.scale);
+          o.w = pack_bf16x2(__uint_as_float(v[e + 6]) * p.scale, __uint_as_float(v[e + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(krow + c + e) = o;
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(w[e]), __uint_as_float(w[e + 1]));
+          u.y = pack_bf16x2(__uint_as_float(w[e + 2]), __uint_as_float(w[e + 3]));
+          u.z = pack_bf16x2(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
+          u.w = pack_bf16x2(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
+          *reinterpret_cast<uint4*>(vrow + c + e) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(TMEM_COLS));
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+bool attention_bwd_tc_supported(const rho_attn_bwd_params* p) {
+  const char* e = getenv("RHO_DISABLE_TCGEN05");
+  if (e && e[0] == '1') return false;
+  const rho_attn_params& f = p->fwd;
+  if (f.dtype != RHO_BF16) return false;
+  if (f.ch != 64 && f.ch != 128) return false;
+  if (f.T < 1 || f.N > 65535 || f.heads > 65535) return false;
+  return get_encode() != nullptr;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int channels, int T, int N, int box_rows) {
+  cuuint64_t gdim[3] = {(cuuint64_t)channels, (cuuint64_t)T, (cuuint64_t)N};
+  cuuint64_t gstr[2] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * (cuuint64_t)T};
+  cuuint32_t bdim[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "attention_bwd_tc: cuTensorMapEncodeTiled failed: %d", (int)r);
+  return RHO_OK;
+}
+
+template <int CH>
+static int launch_attn_bwd_tc(const rho_attn_bwd_params* p, const AttnBwdTcParams& ap, const float* delta, cudaStream_t st) {
+  constexpr int KB = CH / 64;
+  constexpr size_t SMEM_DQ = (size_t)(2 * KB * 16384 + 4 * KB * 8192 + 16384) + 1024;
+  constexpr size_t SMEM_DKV = (size_t)(2 * KB * 16384 + 4 * KB * 8192 + 2 * 16384) + 1024;
+  const rho_attn_params& f = p->fwd;
+  auto kq = attn_bwd_dq_kernel<CH>;
+  auto kkv = attn_bwd_dkv_kernel<CH>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  CUtensorMap qkv128, qkv64, do128, do64;
+  int rc = make_map(&qkv128, f.qkv, 3 * ap.C, f.T, f.N, 128);
+  if (!rc) rc = make_map(&qkv64, f.qkv, 3 * ap.C, f.T, f.N, 64);
+  if (!rc) rc = make_map(&do128, p->dout, ap.C, f.T, f.N, 128);
+  if (!rc) rc = make_map(&do64, p->dout, ap.C, f.T, f.N, 64);
+  if (rc) return rc;
+  dim3 grid((unsigned)ceil_div(f.T, AB_ROWS), f.heads, f.N);
+  kq<<<grid, 192, SMEM_DQ, st>>>(qkv128, qkv64, do128, ap, f.lse, delta, (bf16*)p->dqkv);
+  RHO_CHECK_LAUNCH("attention_bwd_dq_tcgen05");
+  kkv<<<grid, 192, SMEM_DKV, st>>>(qkv128, qkv64, do64, ap, f.lse, delta, (bf16*)p->dqkv);
+  RHO_CHECK_LAUNCH("attention_bwd_dkv_tcgen05");
+  return RHO_OK;
+}
+
+// delta must already hold rowsum(dO o O) as [N, heads, T] fp32
+int attention_bwd_tc(const rho_attn_bwd_params* p, const float* delta, cudaStream_t st) {
+  const rho_attn_params& f = p->fwd;
+  AttnBwdTcParams ap;
+  ap.T = f.T; ap.heads = f.heads; ap.C = f.heads * f.ch;
+  if (f.order == 0) { ap.q_col = 0; ap.k_col = f.ch; ap.v_col = 2 * f.ch; ap.head_stride = 3 * f.ch; }
+  else { ap.q_col = 0; ap.k_col = ap.C; ap.v_col = 2 * ap.C; ap.head_stride = f.ch; }
+  ap.scale = 1.0f / sqrtf((float)f.ch);
+  ap.scale_log2 = ap.scale * AB_LOG2E;
+  if (f.ch == 64) return launch_attn_bwd_tc<64>(p, ap, delta, st);
+  return launch_attn_bwd_tc<128>(p, ap, delta, st);
+}
+
+}  // namespace rho

@@ -366,6 +366,10 @@ static int attn_fwd_t(const rho_attn_params* p, cudaStream_t st) {
   return RHO_OK;
 }
 
+// attention_bwd_tc.cu
+bool attention_bwd_tc_supported(const rho_attn_bwd_params* p);
+int attention_bwd_tc(const rho_attn_bwd_params* p, const float* delta, cudaStream_t st);
+
 template <typename T>
 static int attn_bwd_t(const rho_attn_bwd_params* p, cudaStream_t st) {
   const rho_attn_params& f = p->fwd;
@@ -375,6 +379,7 @@ static int attn_bwd_t(const rho_attn_bwd_params* p, cudaStream_t st) {
   long long total = (long long)f.N * f.heads * f.T;
   attn_bwd_delta_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const T*)f.out, (const T*)p->dout, delta, f.T, f.heads, ch, total);
   RHO_CHECK_LAUNCH("attention_bwd_delta");
+  if (attention_bwd_tc_supported(p)) return attention_bwd_tc(p, delta, st);   // bf16, head dim 64 / 128: tcgen05
 #define RHO_AB(TS, CJ)                                                                                                   \
   do {                                                                                                                   \
     size_t smem = ((size_t)4 * TS * (ch + 4) + (size_t)2 * TS * (TS + 4) + 2 * TS) * sizeof(float);                      \

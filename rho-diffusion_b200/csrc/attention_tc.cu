@@ -29,27 +29,6 @@ struct AttnTcParams {
   float scale;               // ch^-1/2
 };
 
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t at_desc_kmajor(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
-  return d;
-}
-// MN-major operand in the 128B-swizzled canonical layout: rows = K (keys), 128 bytes = 64 contiguous N (channels)
-__device__ __forceinline__ uint64_t at_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-wide N atoms
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride between 8-row K atoms
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 template <int CH>
 __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnTcParams p,
                                                                       bf16* __restrict__ out, float* __restrict__ lse) {

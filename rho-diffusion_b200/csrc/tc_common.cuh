@@ -113,6 +113,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- UMMA shared-memory descriptors for 128-byte-swizzled tiles (rows of 128 bytes = 64 bf16) ------------------
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t at_desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// MN-major operand in the 128B-swizzled canonical layout: rows = K (keys), 128 bytes = 64 contiguous N (channels)
+__device__ __forceinline__ uint64_t at_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-wide N atoms
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride between 8-row K atoms
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
