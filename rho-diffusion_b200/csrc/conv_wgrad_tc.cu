@@ -10,6 +10,10 @@
 // M = 128 is always two 64-channel atoms: two ci blocks of one tap when Cin >= 128, or the same ci block of TWO taps
 // when Cin = 64 (so 64-channel layers still fill the 128-row MMA).  Split-K over position tiles; the fp32 partials
 // [split][tap][ci][co] are reduced in a fixed order (deterministic) into the PyTorch layout [co][ci][tap].
+// Strided (Downsample, unet_v2.py:153) and fused-upsample (Upsample, unet_v2.py:124-131) convs use the same kernel:
+//   stride 2 : the X box of tap t comes from the parity view (coordinate j <-> input 2j + parity) that tap reads;
+//   upsample : the reduction runs over the 4 output-parity classes; class (a, b) pairs the parity view of dY with
+//              the X box shifted by floor((a + dh) / 2), floor((b + dw) / 2) on the un-upsampled grid.
 #include "conv_geom.cuh"
 #include "tc_common.cuh"
 
@@ -22,15 +26,18 @@ struct WgParams {
   int n_co_blocks;       // Cout / BN
   int m_units;           // number of (atom pair) units = CTAs along M
   int splits, tiles_per_split;
-  int16_t tap_dd[28], tap_dh[28], tap_dw[28];
+  int ncls;              // reduction classes per position tile (output parities of a fused upsample; else 1)
+  int mode;              // 0 plain (x map = concat source), 1 strided (x map = parity view of the tap), 2 fused upsample
+  int8_t off_d[28][4], off_h[28][4], off_w[28][4];   // X box shift per (tap, class)
+  int8_t tap_xmap[28];
   // unit u -> two atoms: (tap, ci block) each; -1 tap = unused (duplicate)
   int16_t unit_tap[2][256];
   int16_t unit_cib[2][256];
 };
 
 struct WgMaps {
-  CUtensorMap x[2];   // x, x2 (concat partner)
-  CUtensorMap dy;
+  CUtensorMap x[4];   // plain: x, x2 (concat partner);  strided: parity views (ph * 2 + pw)
+  CUtensorMap dy[4];  // fused upsample: output-parity views (a * uw + b);  else dy[0]
 };
 
 __device__ __forceinline__ uint64_t wg_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -57,8 +64,8 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const int split = bid % p.splits; bid /= p.splits;
   const int cob = bid % p.n_co_blocks;
   const int unit = bid / p.n_co_blocks;
-  const int t0 = split * p.tiles_per_split;
-  const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+  const int t0 = split * p.tiles_per_split;                      // steps = (position tile, class), class fastest
+  const int t1 = min(p.tiles_total * p.ncls, t0 + p.tiles_per_split);
   const int nsteps = max(t1 - t0, 0);
 
   if (threadIdx.x == 0) {
@@ -80,7 +87,8 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t0; t < t1; ++t) {
-        int r = t;
+        const int cls = t % p.ncls;
+        int r = t / p.ncls;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
         const int td = r % p.tiles_d; r /= p.tiles_d;
@@ -92,12 +100,13 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
         for (int a = 0; a < 2; ++a) {
           const int tap = p.unit_tap[a][unit], c = p.unit_cib[a][unit] * 64;
           const int src = c >= p.C1 ? 1 : 0;
-          tma_load_5d(sa + a * BOX, &maps.x[src], &full_bar[stage], src ? c - p.C1 : c, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
-                      d0 + p.tap_dd[tap], n0);
+          const int xm = p.mode == 0 ? src : (p.mode == 1 ? p.tap_xmap[tap] : 0);
+          tma_load_5d(sa + a * BOX, &maps.x[xm], &full_bar[stage], src ? c - p.C1 : c, w0 + p.off_w[tap][cls], h0 + p.off_h[tap][cls],
+                      d0 + p.off_d[tap][cls], n0);
         }
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
-          tma_load_5d(sa + A_BYTES + b * BOX, &maps.dy, &full_bar[stage], cob * BN + b * 64, w0, h0, d0, n0);
+          tma_load_5d(sa + A_BYTES + b * BOX, &maps.dy[cls], &full_bar[stage], cob * BN + b * 64, w0, h0, d0, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -181,7 +190,12 @@ bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
   const char* e = getenv("RHO_DISABLE_TCGEN05");
   if (e && e[0] == '1') return false;
   if (p->fwd.act_dtype != RHO_BF16) return false;
-  if (!(g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1)) return false;
+  const bool plain = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1;
+  const bool strided = g.sd == 1 && (g.sh == 2 || g.sw == 2) && g.ud == 1 && g.uh == 1 && g.uw == 1;
+  const bool upsampled = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && (g.uh == 2 || g.uw == 2);
+  if (!(plain || strided || upsampled)) return false;
+  if (!plain && g.C2 != 0) return false;
+  if (strided && ((g.sh == 2 && g.H < 2) || (g.sw == 2 && g.W < 2))) return false;   // an empty parity view cannot be encoded
   if (g.Cin % 64 != 0 || g.C1 % 64 != 0 || wg_block_n(g.Cout) == 0) return false;
   if (g.taps > 28) return false;
   const int units = g.Cin >= 128 ? g.taps * (g.Cin / 128) : (g.taps + 1) / 2;
@@ -192,13 +206,19 @@ bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
 
 static void wg_plan(const ConvGeom& g, WgParams& wp) {
   memset(&wp, 0, sizeof(wp));
+  const bool up = g.uh == 2 || g.uw == 2;
+  const bool strided = g.sh == 2 || g.sw == 2;
+  wp.mode = up ? 2 : (strided ? 1 : 0);
+  wp.ncls = up ? g.uh * g.uw : 1;
+  // position tiles walk the output grid; for a fused upsample, the un-upsampled grid (= each output-parity class)
+  const int Gw = up ? g.W : g.Wo, Gh = up ? g.H : g.Ho, Gd = up ? g.D : g.Do;
   int rem = 128;
-  wp.bw = std::min(rem, wg_pow2_ceil(g.Wo)); rem /= wp.bw;
-  wp.bh = std::min(rem, wg_pow2_ceil(g.Ho)); rem /= wp.bh;
-  wp.bd = std::min(rem, wg_pow2_ceil(g.Do)); rem /= wp.bd;
+  wp.bw = std::min(rem, wg_pow2_ceil(Gw)); rem /= wp.bw;
+  wp.bh = std::min(rem, wg_pow2_ceil(Gh)); rem /= wp.bh;
+  wp.bd = std::min(rem, wg_pow2_ceil(Gd)); rem /= wp.bd;
   wp.bn = rem;
   wp.lbw = wg_ilog2(wp.bw); wp.lbh = wg_ilog2(wp.bh); wp.lbd = wg_ilog2(wp.bd);
-  wp.tiles_w = (int)ceil_div(g.Wo, wp.bw); wp.tiles_h = (int)ceil_div(g.Ho, wp.bh); wp.tiles_d = (int)ceil_div(g.Do, wp.bd);
+  wp.tiles_w = (int)ceil_div(Gw, wp.bw); wp.tiles_h = (int)ceil_div(Gh, wp.bh); wp.tiles_d = (int)ceil_div(Gd, wp.bd);
   wp.tiles_n = (int)ceil_div(g.N, wp.bn);
   wp.tiles_total = wp.tiles_w * wp.tiles_h * wp.tiles_d * wp.tiles_n;
   wp.Cout = g.Cout; wp.Cin = g.Cin; wp.taps = g.taps; wp.C1 = g.C1;
@@ -206,7 +226,22 @@ static void wg_plan(const ConvGeom& g, WgParams& wp) {
   wp.n_co_blocks = g.Cout / bn;
   for (int t = 0; t < g.taps; ++t) {
     const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
-    wp.tap_dd[t] = (int16_t)(kd - g.pd); wp.tap_dh[t] = (int16_t)(kh - g.ph); wp.tap_dw[t] = (int16_t)(kw - g.pw);
+    const int ed = kd - g.pd, eh = kh - g.ph, ew = kw - g.pw;
+    wp.tap_xmap[t] = 0;
+    for (int cls = 0; cls < wp.ncls; ++cls) {
+      int dh = eh, dw = ew;
+      if (up) {
+        const int a = g.uw == 2 ? cls / 2 : cls, b = cls % 2;      // class = a * uw + b
+        if (g.uh == 2) dh = (a + eh) >> 1;                          // floor((a + eh) / 2)
+        if (g.uw == 2) dw = ((g.uh == 2 ? b : cls) + ew) >> 1;
+      } else if (strided) {
+        int ph = 0, pw = 0;
+        if (g.sh == 2) { ph = eh & 1; dh = eh < 0 ? -1 : 0; }
+        if (g.sw == 2) { pw = ew & 1; dw = ew < 0 ? -1 : 0; }
+        wp.tap_xmap[t] = (int8_t)(ph * 2 + pw);
+      }
+      wp.off_d[t][cls] = (int8_t)ed; wp.off_h[t][cls] = (int8_t)dh; wp.off_w[t][cls] = (int8_t)dw;
+    }
   }
   int u = 0;
   if (g.Cin >= 128) {
@@ -224,11 +259,12 @@ static void wg_plan(const ConvGeom& g, WgParams& wp) {
   wp.m_units = u;
   long long ctas = (long long)wp.m_units * wp.n_co_blocks;
   long long want = ceil_div((long long)sm_count() * 2, ctas);
-  long long max_splits = std::max<long long>(1, wp.tiles_total / 4);
+  const long long steps = (long long)wp.tiles_total * wp.ncls;
+  long long max_splits = std::max<long long>(1, steps / 4);
   long long s = std::max<long long>(1, std::min(want, max_splits));
   if (s > 64) s = 64;
-  wp.tiles_per_split = (int)ceil_div(wp.tiles_total, s);
-  wp.splits = (int)ceil_div(wp.tiles_total, wp.tiles_per_split);
+  wp.tiles_per_split = (int)ceil_div(steps, s);
+  wp.splits = (int)ceil_div(steps, wp.tiles_per_split);
 }
 
 size_t conv_wgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) {
@@ -238,10 +274,14 @@ size_t conv_wgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) 
   return (size_t)wp.splits * g.Cout * g.Cin * g.taps * sizeof(float);
 }
 
-static int wg_encode(CUtensorMap* m, const void* base, int C, int W, int H, int D, int N, const WgParams& wp) {
+// view of a channels-last [N][D][H][W][C] bf16 tensor keeping, in H and W, the elements fh * j + ph resp. fw * j + pw
+static int wg_encode(CUtensorMap* m, const void* base, int C, int W, int H, int D, int N, const WgParams& wp, int fh = 1, int ph = 0,
+                     int fw = 1, int pw = 0) {
   auto enc = get_encode();
-  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H, (cuuint64_t)C * 2 * W * H * D};
+  const int Wv = (W - pw + fw - 1) / fw, Hv = (H - ph + fh - 1) / fh;
+  base = (const char*)base + ((long long)ph * W + pw) * C * 2;
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2 * fw, (cuuint64_t)C * 2 * W * fh, (cuuint64_t)C * 2 * W * H, (cuuint64_t)C * 2 * W * H * D};
   cuuint32_t bdim[5] = {64, (cuuint32_t)wp.bw, (cuuint32_t)wp.bh, (cuuint32_t)wp.bd, (cuuint32_t)wp.bn};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -273,10 +313,26 @@ int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "conv_wgrad_tc: workspace %zu < %zu", p->workspace_bytes, need);
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = wg_encode(&maps.x[0], p->fwd.x, g.C1, g.W, g.H, g.D, g.N, wp);
+  int rc = RHO_OK;
+  if (wp.mode == 1) {
+    for (int m = 0; m < 4 && !rc; ++m) {
+      const int ph = m >> 1, pw = m & 1;
+      if ((ph && g.sh != 2) || (pw && g.sw != 2)) continue;
+      rc = wg_encode(&maps.x[m], p->fwd.x, g.C1, g.W, g.H, g.D, g.N, wp, g.sh, ph, g.sw, pw);
+    }
+  } else {
+    rc = wg_encode(&maps.x[0], p->fwd.x, g.C1, g.W, g.H, g.D, g.N, wp);
+    if (!rc && g.C2) rc = wg_encode(&maps.x[1], p->fwd.x2, g.C2, g.W, g.H, g.D, g.N, wp);
+  }
   if (rc) return rc;
-  if (g.C2) { rc = wg_encode(&maps.x[1], p->fwd.x2, g.C2, g.W, g.H, g.D, g.N, wp); if (rc) return rc; }
-  rc = wg_encode(&maps.dy, p->dy, g.Cout, g.Wo, g.Ho, g.Do, g.N, wp);
+  if (wp.mode == 2) {
+    for (int cls = 0; cls < wp.ncls && !rc; ++cls) {
+      const int a = g.uw == 2 ? cls / 2 : cls, b = g.uh == 2 ? cls % 2 : cls;
+      rc = wg_encode(&maps.dy[cls], p->dy, g.Cout, g.Wo, g.Ho, g.Do, g.N, wp, g.uh, g.uh == 2 ? a : 0, g.uw, g.uw == 2 ? b : 0);
+    }
+  } else {
+    rc = wg_encode(&maps.dy[0], p->dy, g.Cout, g.Wo, g.Ho, g.Do, g.N, wp);
+  }
   if (rc) return rc;
   float* partial = (float*)p->workspace;
   const int bn = wg_block_n(g.Cout);

@@ -136,6 +136,11 @@ CONV_CASES = [
     (3, 2, 128, 0, 128, (3, 8, 16), 3, 1, (1, 2, 2), False),   # Upsample on the tensor cores (4 parity classes, 12 taps)
     (3, 2, 64, 0, 64, (3, 10, 12), 3, (1, 2, 2), 1, False),    # Downsample on the tensor cores (parity tensor maps)
     (1, 2, 64, 0, 64, (37,), 3, 2, 1, False),                  # odd length, stride 2
+    # tcgen05 weight-gradient engine on strided / fused-upsample convs (parity views of x resp. dy)
+    (2, 2, 64, 0, 128, (9, 12), 3, 2, 1, False),               # Downsample 2-D, odd height
+    (2, 1, 128, 0, 64, (5, 6), 3, 1, 2, False),                # Upsample 2-D (4 output-parity classes)
+    (1, 2, 64, 0, 64, (19,), 3, 1, 2, False),                  # Upsample 1-D (2 classes)
+    (3, 1, 256, 0, 256, (2, 4, 8), 3, 1, (1, 2, 2), False),    # Upsample 3-D, two ci blocks per tap
 ]
 
 

@@ -47,3 +47,8 @@ tot = sum(r[1] for r in rows.values())
 print(f"mode={mode} B={B} total device time {tot/1e3:.2f} ms")
 for k, r in sorted(rows.items(), key=lambda kv: -kv[1][1])[:28]:
     print(f"{r[1]/1e3:9.3f} ms {100*r[1]/tot:5.1f}% x{r[0]:4d}  {k}")
+
+print("-- individual launches of the CUDA-core conv engines (us) --")
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA and ("simt" in e.name or "small" in e.name):
+        print(f"{e.device_time:10.1f}  {e.name[:90]}")
