@@ -10,6 +10,9 @@ size_t conv_wgrad_simt_workspace(const ConvGeom& g);
 // conv_small.cu
 bool conv_small_supported(const ConvGeom& g, const rho_conv_params* p);
 int conv_small_fwd(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
+bool conv_small_wgrad_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
+size_t conv_small_wgrad_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
+int conv_small_wgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 // conv_tc.cu
 bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p);
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
@@ -81,8 +84,10 @@ size_t rho_conv_bwd_workspace_bytes(const rho_conv_bwd_params* p) {
   size_t a = conv_wgrad_simt_workspace(g);
   size_t b = conv_dgrad_tc_workspace(g, p);
   size_t c = conv_wgrad_tc_workspace(g, p);
+  size_t d = conv_small_wgrad_workspace(g, p);
   a = a > b ? a : b;
-  return a > c ? a : c;
+  a = a > c ? a : c;
+  return a > d ? a : d;
 }
 
 int rho_conv_dgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
@@ -114,6 +119,15 @@ int rho_conv_wgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
     return conv_wgrad_simt(g, &q, as_stream(stream));
   }
   if (p->fwd.engine == RHO_CONV_TCGEN05 && p->dw) return fail(RHO_ERR_UNSUPPORTED, "conv_wgrad: tcgen05 engine does not take this shape");
+  // degenerate first / last layers: HBM-bound streaming reduction
+  if (p->dw && p->fwd.engine == RHO_CONV_AUTO && conv_small_wgrad_supported(g, p)) {
+    RHO_REQUIRE(p->fwd.x, "conv_wgrad: x required");
+    rc = conv_small_wgrad(g, p, as_stream(stream));
+    if (rc || !p->dbias) return rc;
+    rho_conv_bwd_params q = *p;
+    q.dw = nullptr;
+    return conv_wgrad_simt(g, &q, as_stream(stream));
+  }
   return conv_wgrad_simt(g, p, as_stream(stream));
 }
 

@@ -305,6 +305,150 @@ static int launch_small_cin_row4(const ConvGeom& g, const rho_conv_params* p, cu
   return RHO_OK;
 }
 
+
+// ---- weight gradient of the two degenerate layers (bf16, unit stride) ------------------------------------------------
+//   first conv (Cin <= 4):  dW[co][tap][ci] = sum_pos dY[pos][co] * x[pos + off(tap)][ci]     wide = dY, narrow = x,  SIGN = +1
+//   last  conv (Cout <= 4): dW[co][tap][ci] = sum_q   x[q][ci]   * dY[q - off(tap)][co]       wide = x,  narrow = dY, SIGN = -1
+// Both stream the wide [M x CW] tensor once per (kd, narrow channel) with 16-byte loads and keep the KH*KW x 8 partial
+// sums of a thread in registers; the position lanes of a CTA meet in shuffles + one shared-memory pass, the CTAs in a
+// fixed-order second kernel (deterministic, no atomics).
+template <int SIGN, int KH, int KW>
+__global__ void __launch_bounds__(256) conv_small_wgrad_kernel(ConvGeom g, const bf16* __restrict__ wide, const bf16* __restrict__ narrow,
+                                                               int CW, int CN, int chunks, float* __restrict__ partial) {
+  constexpr int NT = KH * KW;
+  __shared__ float red[8][64 * 8];                 // [warp][octet-in-warp * 8 + channel] (octets per warp <= 32)
+  const int octets = CW >> 3;
+  const int P = 256 / octets;                      // position lanes per CTA (octets is a power of two <= 32: whole warps)
+  const int tid = threadIdx.x;
+  const int octet = tid % octets, lp = tid / octets;
+  const int kd = blockIdx.y, cn = blockIdx.z, chunk = blockIdx.x;
+  const int dd = SIGN * (kd - g.pd);
+  const unsigned M = (unsigned)g.M;
+  const unsigned per = (M + chunks - 1) / chunks;
+  const unsigned p0 = chunk * per, p1 = min(M, p0 + per);
+  float acc[NT][8];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  for (unsigned m = p0 + lp; m < p1; m += P) {
+    unsigned t = m;
+    const int w = (int)(t % (unsigned)g.W); t /= (unsigned)g.W;
+    const int h = (int)(t % (unsigned)g.H); t /= (unsigned)g.H;
+    const int d = (int)(t % (unsigned)g.D);
+    const int n = (int)(t / (unsigned)g.D);
+    const int nd = d + dd;
+    if (nd < 0 || nd >= g.D) continue;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(wide + (long long)m * CW) + octet);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { wv[2 * j] = __uint_as_float(u[j] << 16); wv[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u); }
+    const long long base = ((long long)n * g.D + nd) * g.H;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int nh = h + SIGN * (j / KW - KH / 2), nw = w + SIGN * (j % KW - KW / 2);
+      float nv = 0.f;
+      if (nh >= 0 && nh < g.H && nw >= 0 && nw < g.W) nv = __bfloat162float(narrow[((base + nh) * g.W + nw) * CN + cn]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(nv, wv[e], acc[j][e]);
+    }
+  }
+  // lanes with the same octet inside a warp: xor-shuffle over the position bits; then the 8 warps through shared memory
+  const int warp = tid >> 5, lane = tid & 31;
+  const int opw = octets < 32 ? octets : 32;       // octets per warp
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[j][e];
+      for (int off = 16; off >= opw; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[j][e] = v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (lane < opw) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[j][e];
+    }
+    __syncthreads();
+    // channel cw = octet * 8 + e; octet = (warp % sets) * 32 + lane when octets > 32
+    for (int cw = tid; cw < CW; cw += 256) {
+      float s = 0.f;
+      if (octets <= 32) {
+        for (int wi = 0; wi < 8; ++wi) s += red[wi][cw];
+      } else {
+        const int set = (cw >> 3) / 32, idx = ((cw >> 3) % 32) * 8 + (cw & 7), sets = octets / 32;
+        for (int wi = set; wi < 8; wi += sets) s += red[wi][idx];
+      }
+      const int tap = kd * NT + j;
+      partial[(((long long)chunk * g.taps + tap) * CN + cn) * CW + cw] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// dw[co][ci][tap] = sum_chunk partial[chunk][tap][cn][cw];  wide_is_cout: cw = co, cn = ci (first conv), else cw = ci, cn = co
+__global__ void conv_small_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int taps, int CN, int CW, int wide_is_cout,
+                                               float* __restrict__ dw) {
+  const int total = taps * CN * CW;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cw = i % CW, cn = (i / CW) % CN, tap = i / (CW * CN);
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * total + i];
+  const int co = wide_is_cout ? cw : cn, ci = wide_is_cout ? cn : cw;
+  const int Cin = wide_is_cout ? CN : CW;
+  dw[((long long)co * Cin + ci) * taps + tap] = s;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int small_wgrad_chunks(const ConvGeom& g, int CW, int CN) {
+  const int P = 256 / (CW >> 3);
+  long long want = std::max<long long>(1, (long long)sm_count() * 2 / ((long long)g.kd * CN));
+  long long cap = std::max<long long>(1, g.M / ((long long)P * 8));
+  return (int)std::min<long long>(std::min(want, cap), 1024);
+}
+bool conv_small_wgrad_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (p->fwd.act_dtype != RHO_BF16 || !small_fast_geom(g) || g.C2 != 0) return false;
+  if (!((g.kh == 3 && g.kw == 3) || (g.kh == 1 && g.kw == 3) || (g.kh == 1 && g.kw == 1))) return false;
+  const bool first = g.Cin <= 4 && g.Cout % 8 == 0 && pow2(g.Cout >> 3) && g.Cout <= 2048;
+  const bool last = g.Cout <= 4 && g.Cin % 8 == 0 && pow2(g.Cin >> 3) && g.Cin <= 2048;
+  return first || last;
+}
+size_t conv_small_wgrad_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (!conv_small_wgrad_supported(g, p)) return 0;
+  const bool first = g.Cin <= 4 && g.Cout % 8 == 0;
+  const int CW = first ? g.Cout : g.Cin, CN = first ? g.Cin : g.Cout;
+  return (size_t)small_wgrad_chunks(g, CW, CN) * g.taps * CN * CW * sizeof(float);
+}
+int conv_small_wgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  const bool first = g.Cin <= 4 && g.Cout % 8 == 0;
+  const int CW = first ? g.Cout : g.Cin, CN = first ? g.Cin : g.Cout;
+  const int chunks = small_wgrad_chunks(g, CW, CN);
+  const size_t need = (size_t)chunks * g.taps * CN * CW * sizeof(float);
+  if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "conv_small_wgrad: workspace %zu < %zu", p->workspace_bytes, need);
+  float* partial = (float*)p->workspace;
+  const bf16* wide = (const bf16*)(first ? p->dy : p->fwd.x);
+  const bf16* narrow = (const bf16*)(first ? p->fwd.x : p->dy);
+  dim3 grid((unsigned)chunks, (unsigned)g.kd, (unsigned)CN);
+#define RHO_SWG(KH, KW)                                                                                                   \
+  do {                                                                                                                    \
+    if (first) conv_small_wgrad_kernel<1, KH, KW><<<grid, 256, 0, st>>>(g, wide, narrow, CW, CN, chunks, partial);       \
+    else conv_small_wgrad_kernel<-1, KH, KW><<<grid, 256, 0, st>>>(g, wide, narrow, CW, CN, chunks, partial);            \
+  } while (0)
+  if (g.kh == 3 && g.kw == 3) RHO_SWG(3, 3);
+  else if (g.kw == 3) RHO_SWG(1, 3);
+  else RHO_SWG(1, 1);
+#undef RHO_SWG
+  RHO_CHECK_LAUNCH("conv_small_wgrad");
+  const int total = g.taps * CN * CW;
+  conv_small_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, chunks, g.taps, CN, CW, first ? 1 : 0, p->dw);
+  RHO_CHECK_LAUNCH("conv_small_wgrad_reduce");
+  return RHO_OK;
+}
+
 int conv_small_fwd(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const int a = p->act_dtype, w = p->w_dtype, f = p->y_f32;
   if (a == RHO_BF16 && w == RHO_BF16 && small_fast_geom(g)) {

@@ -547,7 +547,9 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
 //   weights = [Cin][taps][Cout] with tap index reversed (a pure permutation of the packed bf16 forward weights, so it is
 //   rebuilt in the workspace on every call).
 // Fused-upsample convs: dgrad at the upsampled resolution into a temporary, then a 2x2 (H, W) sum-pool -- the adjoint of
-// the nearest-neighbour gather.  Strided (Downsample) convs stay on the CUDA-core engine (3 small layers).
+// the nearest-neighbour gather.  Strided (Downsample) convs: one launch per INPUT parity class (a_h, a_w); class a = 0 of a
+// stride-2 dim receives only tap k = 1 (from output i), class a = 1 taps k = 0 (from output i + 1) and k = 2 (from i);
+// the class grid is written back with output stride 2 / offset a.
 __global__ void pack_dgrad_kernel(const bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin, int taps) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -586,7 +588,8 @@ __global__ void sum_pool_split_kernel(const bf16* __restrict__ t, bf16* __restri
 static bool dgrad_tc_shape_ok(const ConvGeom& g, const rho_conv_bwd_params* p) {
   if (tc_disabled()) return false;
   if (p->fwd.act_dtype != RHO_BF16 || p->fwd.w_dtype != RHO_BF16) return false;
-  if (!(is_plain(g) || is_upsampled(g))) return false;
+  if (!(is_plain(g) || is_upsampled(g) || is_strided(g))) return false;
+  if (is_strided(g) && (g.C2 != 0 || (g.sh == 2 && g.kh != 3) || (g.sw == 2 && g.kw != 3))) return false;
   if (pick_block_k(g.Cout, 0) < 32 || pick_block_n(g.Cin) == 0) return false;
   if (g.C2 > 0 && (g.C1 % 32 != 0)) return false;
   if (g.taps > TC_MAX_TAPS) return false;
@@ -625,6 +628,43 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   tp.Cout = g.Cin; tp.C1 = g.Cout; tp.C2 = 0;
   tp.n_blocks = g.Cin / bn;
   tp.out_split = (!up && g.C2 > 0) ? g.C1 : 0;
+  if (is_strided(g)) {
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = encode_weight_map(&maps.w, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
+    if (rc) return rc;
+    ActView v;
+    v.base = p->dy;
+    v.dim[0] = g.Cout; v.dim[1] = g.Wo; v.dim[2] = g.Ho; v.dim[3] = g.Do; v.dim[4] = g.N;
+    v.stride[0] = (long long)g.Cout * 2; v.stride[1] = v.stride[0] * g.Wo; v.stride[2] = v.stride[1] * g.Ho; v.stride[3] = v.stride[2] * g.Do;
+    tp.Do = g.D; tp.Ho = g.H; tp.Wo = g.W;
+    for (int ah = 0; ah < g.sh; ++ah)
+      for (int aw = 0; aw < g.sw; ++aw) {
+        tp.Gd = g.D; tp.Gh = (g.H - ah + g.sh - 1) / g.sh; tp.Gw = (g.W - aw + g.sw - 1) / g.sw;
+        if (tp.Gh <= 0 || tp.Gw <= 0) continue;
+        tp.os_d = 1; tp.os_h = g.sh; tp.os_w = g.sw;
+        tp.oo_d = 0; tp.oo_h = ah; tp.oo_w = aw;
+        pick_tile(tp);
+        int nt = 0;
+        for (int t = 0; t < g.taps; ++t) {
+          const int kw = t % g.kw, kh = (t / g.kw) % g.kh, kd = t / (g.kw * g.kh);
+          int dh, dw;
+          if (g.sh == 2) { if (((kh + ah) & 1) == 0) continue; dh = (ah == 1 && kh == 0) ? 1 : 0; } else dh = g.ph - kh;
+          if (g.sw == 2) { if (((kw + aw) & 1) == 0) continue; dw = (aw == 1 && kw == 0) ? 1 : 0; } else dw = g.pw - kw;
+          tp.taps[nt].dn = 0; tp.taps[nt].dd = (int16_t)(g.pd - kd); tp.taps[nt].dh = (int16_t)dh; tp.taps[nt].dw = (int16_t)dw;
+          tp.taps[nt].map = 0;
+          tp.taps[nt].kofs = (g.taps - 1 - t) * g.Cout;     // pack_dgrad_kernel stores the taps reversed
+          ++nt;
+        }
+        tp.ntaps = nt;
+        const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
+        rc = encode_view(&maps.a[0][0], v, box, bk);
+        if (rc) return rc;
+        rc = dispatch_tc<bf16>(bn, bk, maps, tp, nullptr, nullptr, (bf16*)p->dx, (bf16*)nullptr, st);
+        if (rc) return rc;
+      }
+    return RHO_OK;
+  }
   pick_tile(tp);
   tp.ntaps = g.taps;
   for (int t = 0; t < g.taps; ++t) {
