@@ -10,6 +10,8 @@ size_t conv_wgrad_simt_workspace(const ConvGeom& g);
 // conv_small.cu
 bool conv_small_supported(const ConvGeom& g, const rho_conv_params* p);
 int conv_small_fwd(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
+bool conv_small_dgrad_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
+int conv_small_dgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 bool conv_small_wgrad_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
 size_t conv_small_wgrad_workspace(const ConvGeom& g, const rho_conv_bwd_params* p);
 int conv_small_wgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
@@ -100,6 +102,7 @@ int rho_conv_dgrad(const rho_conv_bwd_params* p, rho_stream_t stream) {
   const bool tc_ok = conv_dgrad_tc_supported(g, p);
   if (p->fwd.engine == RHO_CONV_TCGEN05 && !tc_ok) return fail(RHO_ERR_UNSUPPORTED, "conv_dgrad: tcgen05 engine does not take this shape");
   if (p->fwd.engine != RHO_CONV_SIMT && tc_ok) return conv_dgrad_tc(g, p, as_stream(stream));
+  if (p->fwd.engine == RHO_CONV_AUTO && conv_small_dgrad_supported(g, p)) return conv_small_dgrad(g, p, as_stream(stream));
   return conv_dgrad_simt(g, p, as_stream(stream));
 }
 

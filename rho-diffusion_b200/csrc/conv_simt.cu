@@ -258,6 +258,42 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const TA* __restric
     partial[(long long)blockIdx.x * C + c] = s;
   }
 }
+// bf16, C % 8 == 0, C <= 2048: 16-byte loads, 4 rows in flight per thread, rows of a CTA meet in shared memory
+__global__ void __launch_bounds__(256) colsum_partial8_kernel(const bf16* __restrict__ dy, long long M, int C, int chunks,
+                                                              float* __restrict__ partial) {
+  __shared__ float red[2048];
+  const int CV = C >> 3;
+  const int rows = 256 / CV;
+  const int row = threadIdx.x / CV, cv = threadIdx.x - row * CV;
+  const long long per = (M + chunks - 1) / chunks;
+  const long long m0 = (long long)blockIdx.x * per, m1 = min(M, m0 + per);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (row < rows) {
+    const bf16* src = dy + cv * 8;
+    auto accum = [&](const uint4& q) {
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[2 * j] += __uint_as_float(u[j] << 16); s[2 * j + 1] += __uint_as_float(u[j] & 0xffff0000u); }
+    };
+    long long m = m0 + row;
+    for (; m + 3ll * rows < m1; m += 4ll * rows) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(src + (m + (long long)u * rows) * C));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) accum(q[u]);
+    }
+    for (; m < m1; m += rows) accum(__ldg(reinterpret_cast<const uint4*>(src + m * C)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[row * C + cv * 8 + j] = s[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r) t += red[r * C + c];
+    partial[(long long)blockIdx.x * C + c] = t;
+  }
+}
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -275,6 +311,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TP* __restrict__
   int tap = (int)((i / Cin) % taps);
   int co = (int)(i / ((long long)Cin * taps));
   packed[i] = from_f32<TP>(w[((long long)co * Cin + ci) * taps + tap]);
+}
+
+// same re-layout through shared memory: one CTA = one output channel x 64 input channels x all taps; the fp32 source run
+// (64 * taps contiguous floats) is read coalesced, each tap row of 64 packed values is written contiguously
+template <typename TP>
+__global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ w, TP* __restrict__ packed, int Cin, int taps) {
+  extern __shared__ float wt[];                        // [64 * taps]
+  const int co = blockIdx.x, ci0 = blockIdx.y * 64;
+  const int nci = min(64, Cin - ci0);
+  const float* src = w + ((long long)co * Cin + ci0) * taps;
+  for (int i = threadIdx.x; i < nci * taps; i += 256) wt[i] = src[i];
+  __syncthreads();
+  TP* dst = packed + (long long)co * taps * Cin + ci0;
+  for (int i = threadIdx.x; i < nci * taps; i += 256) {
+    const int tap = i / nci, ci = i - tap * nci;
+    dst[(long long)tap * Cin + ci] = from_f32<TP>(wt[ci * taps + tap]);
+  }
 }
 
 // ---- host -----------------------------------------------------------------------------------------
@@ -367,6 +420,8 @@ int conv_wgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_
     int chunks = (int)std::min<long long>(256, std::max<long long>(1, g.M / 64));
     if (p->fwd.act_dtype == RHO_F32)
       colsum_partial_kernel<float><<<chunks, 256, 0, st>>>((const float*)p->dy, g.M, g.Cout, chunks, bias_ws);
+    else if (g.Cout % 8 == 0 && g.Cout <= 2048)
+      colsum_partial8_kernel<<<chunks, 256, 0, st>>>((const bf16*)p->dy, g.M, g.Cout, chunks, bias_ws);
     else
       colsum_partial_kernel<bf16><<<chunks, 256, 0, st>>>((const bf16*)p->dy, g.M, g.Cout, chunks, bias_ws);
     RHO_CHECK_LAUNCH("colsum_partial");
@@ -385,6 +440,15 @@ extern "C" int rho_conv_pack_weight(const float* w, void* packed, int packed_dty
   RHO_REQUIRE(w && packed && Cout > 0 && Cin > 0 && taps > 0, "conv_pack_weight: bad args");
   long long total = (long long)Cout * Cin * taps;
   unsigned blocks = (unsigned)ceil_div(total, 256);
+  if (taps > 1 && taps <= 64 && Cout <= 65535 * 32) {
+    dim3 grid((unsigned)Cout, (unsigned)ceil_div(Cin, 64));
+    const size_t smem = (size_t)64 * taps * sizeof(float);
+    if (packed_dtype == RHO_F32) pack_weight_tiled_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(w, (float*)packed, Cin, taps);
+    else if (packed_dtype == RHO_BF16) pack_weight_tiled_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(w, (bf16*)packed, Cin, taps);
+    else return fail(RHO_ERR_INVALID_ARG, "conv_pack_weight: bad dtype");
+    RHO_CHECK_LAUNCH("pack_weight");
+    return RHO_OK;
+  }
   if (packed_dtype == RHO_F32) pack_weight_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(w, (float*)packed, Cout, Cin, taps);
   else if (packed_dtype == RHO_BF16) pack_weight_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>(w, (bf16*)packed, Cout, Cin, taps);
   else return fail(RHO_ERR_INVALID_ARG, "conv_pack_weight: bad dtype");

@@ -176,14 +176,21 @@ __global__ void __launch_bounds__(256) conv_small_cout_vec_kernel(ConvGeom g, co
 // small-Cin: 8 lanes share a run of PW = 4 consecutive output positions along W, each lane produces 8 output channels
 // for all four (the (kw + j) input column is loaded once and feeds up to three taps; each weight vector is read from
 // shared memory once per four positions).  A warp store instruction writes four complete 128-byte lines at Cout = 64.
+// `flip`: the kernel computes the DATA gradient of a small-Cout conv (the roles swap: g.Cin = forward Cout, g.Cout = forward
+// Cin, x = dY) and `w` is the forward packed weight [g.Cin][taps][g.Cout], read with the taps reversed.
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_small_cin_row4_kernel(ConvGeom g, const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                                  const float* __restrict__ bias, bf16* __restrict__ y) {
+                                                                  const float* __restrict__ bias, bf16* __restrict__ y, int flip) {
   extern __shared__ __align__(16) float ws_dyn[];   // [tap*Cin + ci][Cout]
   const int K = g.taps * CIN;
   for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) {
-    const int co = i / K, k = i % K;
-    ws_dyn[k * g.Cout + co] = to_f32(w[i]);
+    if (!flip) {
+      const int co = i / K, k = i % K;
+      ws_dyn[k * g.Cout + co] = to_f32(w[i]);
+    } else {
+      const int co = i % g.Cout, tap = (i / g.Cout) % g.taps, ci = i / (g.Cout * g.taps);   // w[ci][tap][co]
+      ws_dyn[((g.taps - 1 - tap) * CIN + ci) * g.Cout + co] = to_f32(w[i]);
+    }
   }
   __syncthreads();
   const int groups = g.Cout >> 3;
@@ -293,7 +300,7 @@ static int launch_small_cout_vec(const ConvGeom& g, const rho_conv_params* p, cu
 static int launch_small_cin_row4(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const size_t smem = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
   const unsigned blocks = (unsigned)ceil_div((g.M >> 2) * (g.Cout >> 3), 256);
-#define RHO_SCR(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (bf16*)p->y)
+#define RHO_SCR(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (bf16*)p->y, 0)
   switch (g.Cin) {
     case 1: RHO_SCR(1); break;
     case 2: RHO_SCR(2); break;
@@ -446,6 +453,30 @@ int conv_small_wgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream
   const int total = g.taps * CN * CW;
   conv_small_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, chunks, g.taps, CN, CW, first ? 1 : 0, p->dw);
   RHO_CHECK_LAUNCH("conv_small_wgrad_reduce");
+  return RHO_OK;
+}
+
+// data gradient of the last conv (Cout <= 4): the first-conv kernel on dY with the flipped filter
+bool conv_small_dgrad_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
+  if (p->fwd.act_dtype != RHO_BF16 || p->fwd.w_dtype != RHO_BF16 || !small_fast_geom(g) || g.C2 != 0) return false;
+  if ((long long)g.taps * g.Cin * g.Cout > SC_MAX_W) return false;
+  return g.Cout <= 4 && g.Cin % 8 == 0 && g.W % 4 == 0 && g.kd % 2 == 1 && g.kh % 2 == 1 && g.kw % 2 == 1;
+}
+int conv_small_dgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  ConvGeom d = g;                       // swapped roles; unit stride + "same" padding: the grids coincide
+  d.Cin = g.Cout; d.C1 = g.Cout; d.Cout = g.Cin;
+  d.Ktot = d.taps * d.Cin;
+  const size_t smem = (size_t)d.taps * d.Cin * d.Cout * sizeof(float);
+  const unsigned blocks = (unsigned)ceil_div((d.M >> 2) * (d.Cout >> 3), 256);
+#define RHO_SCD(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(d, (const bf16*)p->dy, (const bf16*)p->fwd.w_packed, nullptr, (bf16*)p->dx, 1)
+  switch (d.Cin) {
+    case 1: RHO_SCD(1); break;
+    case 2: RHO_SCD(2); break;
+    case 3: RHO_SCD(3); break;
+    default: RHO_SCD(4); break;
+  }
+#undef RHO_SCD
+  RHO_CHECK_LAUNCH("conv_small_dgrad");
   return RHO_OK;
 }
 

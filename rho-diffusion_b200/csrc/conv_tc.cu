@@ -550,6 +550,21 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
 // the nearest-neighbour gather.  Strided (Downsample) convs: one launch per INPUT parity class (a_h, a_w); class a = 0 of a
 // stride-2 dim receives only tap k = 1 (from output i), class a = 1 taps k = 0 (from output i + 1) and k = 2 (from i);
 // the class grid is written back with output stride 2 / offset a.
+// tiled variant: one CTA transposes a [32 co][32 ci] block of one tap through shared memory (coalesced both ways)
+__global__ void __launch_bounds__(256) pack_dgrad_tiled_kernel(const bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin, int taps) {
+  __shared__ bf16 tile[32][34];
+  const int t = blockIdx.z, co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    if (co < Cout && ci < Cin) tile[r][tx] = wf[((long long)co * taps + (taps - 1 - t)) * Cin + ci];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (co < Cout && ci < Cin) wd[((long long)ci * taps + t) * Cout + co] = tile[tx][r];
+  }
+}
 __global__ void pack_dgrad_kernel(const bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin, int taps) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -612,9 +627,8 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   bf16* wd = (bf16*)p->workspace;
   bf16* tmp = (bf16*)((char*)p->workspace + align_up((size_t)g.Cout * g.Cin * g.taps * sizeof(bf16), 1024));
   {
-    long long total = (long long)g.Cout * g.Cin * g.taps;
-    int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
-    pack_dgrad_kernel<<<blocks, 256, 0, st>>>((const bf16*)p->fwd.w_packed, wd, g.Cout, g.Cin, g.taps);
+    dim3 pgrid((unsigned)ceil_div(g.Cout, 32), (unsigned)ceil_div(g.Cin, 32), (unsigned)g.taps);
+    pack_dgrad_tiled_kernel<<<pgrid, 256, 0, st>>>((const bf16*)p->fwd.w_packed, wd, g.Cout, g.Cin, g.taps);
     RHO_CHECK_LAUNCH("pack_dgrad");
   }
   const bool up = is_upsampled(g);

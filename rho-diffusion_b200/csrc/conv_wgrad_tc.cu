@@ -164,11 +164,51 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
 }
 
-// dw[co][ci][tap] = sum_split partial[split][tap][ci][co]
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps, float* __restrict__ dw) {
+// dw[co][ci][tap] = sum_split partial[split][tap][ci][co]: a full index reversal.  One CTA owns 32 output channels x CIT
+// input channels x all taps: the partials are read as 128-byte rows (co fastest), summed over the splits in a fixed order,
+// staged in shared memory, and written as runs of CIT * taps contiguous floats per output channel.
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps,
+                                                              int cit, float* __restrict__ dw) {
+  extern __shared__ float tile[];                      // [cit * taps][33]
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * cit;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long total = (long long)Cout * Cin * taps;
+  const int nci = min(cit, Cin - ci0);
+  const int rows = nci * taps;                          // row r <-> (ci = r / taps, tap = r % taps) in OUTPUT order
+  const bool co_ok = co0 + lane < Cout;
+  for (int r0 = wid; r0 < rows; r0 += 64) {             // 8 independent rows in flight per warp
+    const float* src[8];
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = min(r0 + 8 * u, rows - 1);
+      const int ci = ci0 + r / taps, tap = r % taps;
+      src[u] = partial + ((long long)tap * Cin + ci) * Cout + co0 + lane;
+      s[u] = 0.f;
+    }
+    if (co_ok) {
+      for (int k = 0; k < splits; ++k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += __ldg(src[u] + (long long)k * total);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 8 * u;
+      if (r < rows) tile[r * 33 + lane] = s[u];
+    }
+  }
+  __syncthreads();
+  for (int co = wid; co < 32 && co0 + co < Cout; co += 8) {
+    float* dst = dw + ((long long)(co0 + co) * Cin + ci0) * taps;
+    for (int r = lane; r < rows; r += 32) dst[r] = tile[r * 33 + co];
+  }
+}
+
+// small layers (few tiles, many splits): one thread per output element keeps the grid wide
+__global__ void wgrad_tc_reduce_flat_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps, float* __restrict__ dw) {
   const long long total = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // i indexes [tap][ci][co] (coalesced reads)
     const int co = (int)(i % Cout);
     const int ci = (int)((i / Cout) % Cin);
     const int tap = (int)(i / ((long long)Cout * Cin));
@@ -340,9 +380,15 @@ int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   else if (bn == 128) rc = wg_launch<128, 3>(maps, wp, partial, st);
   else rc = wg_launch<64, 4>(maps, wp, partial, st);
   if (rc) return rc;
-  long long total = (long long)g.Cout * g.Cin * g.taps;
-  int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
-  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(partial, wp.splits, g.Cout, g.Cin, g.taps, p->dw);
+  const int cit = std::max(1, std::min(g.Cin, 256 / g.taps));
+  dim3 rgrid((unsigned)ceil_div(g.Cout, 32), (unsigned)ceil_div(g.Cin, cit));
+  if ((long long)rgrid.x * rgrid.y >= 2ll * sm_count()) {
+    wgrad_tc_reduce_kernel<<<rgrid, 256, (size_t)cit * g.taps * 33 * sizeof(float), st>>>(partial, wp.splits, g.Cout, g.Cin, g.taps, cit, p->dw);
+  } else {
+    const long long total = (long long)g.Cout * g.Cin * g.taps;
+    wgrad_tc_reduce_flat_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8), 256, 0, st>>>(
+        partial, wp.splits, g.Cout, g.Cin, g.taps, p->dw);
+  }
   RHO_CHECK_LAUNCH("wgrad_tc_reduce");
   return RHO_OK;
 }

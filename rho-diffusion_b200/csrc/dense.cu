@@ -38,13 +38,28 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(rho_linear_params p) {
 }
 
 // dx[b][i] = act'(x[b][i]) * sum_o dy[b][o] * w[o][i]; thread per (b, i) (coalesced over i in w rows)
-__global__ void linear_bwd_dx_kernel(rho_linear_params p, const float* __restrict__ dy, int dy_stride, float* __restrict__ dx, int dx_stride) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.B * p.I) return;
-  int b = idx / p.I, i = idx % p.I;
+// CTA = 32 inputs x 8 output lanes (grid: I/32 x B): w rows are read as 128-byte segments, the 8 partial sums per input
+// meet in shared memory in a fixed order
+__global__ void __launch_bounds__(256) linear_bwd_dx_kernel(rho_linear_params p, const float* __restrict__ dy, int dy_stride,
+                                                            float* __restrict__ dx, int dx_stride) {
+  __shared__ float red[8][32];
+  const int b = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int o = 0; o < p.O; ++o) s = fmaf(dy[(long long)b * dy_stride + o], p.w[(long long)o * p.I + i], s);
-  dx[(long long)b * dx_stride + i] = s * act_grad(p.x[(long long)b * p.x_stride + i], p.act_in);
+  if (i < p.I) {
+    const float* dyb = dy + (long long)b * dy_stride;
+#pragma unroll 4
+    for (int o = ty; o < p.O; o += 8) s = fmaf(dyb[o], p.w[(long long)o * p.I + i], s);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < p.I) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    dx[(long long)b * dx_stride + i] = t * act_grad(p.x[(long long)b * p.x_stride + i], p.act_in);
+  }
 }
 
 // dw[o][i] = sum_b dy[b][o] * act(x[b][i]); thread per (o, i)
@@ -126,7 +141,7 @@ int rho_linear_bwd(const rho_linear_params* p, const float* dy, int32_t dy_strid
   RHO_REQUIRE(p && p->x && p->w && dy && p->B > 0 && p->I > 0 && p->O > 0, "linear_bwd: bad args");
   cudaStream_t st = as_stream(stream);
   if (dx) {
-    linear_bwd_dx_kernel<<<(unsigned)ceil_div((long long)p->B * p->I, 128), 128, 0, st>>>(*p, dy, dy_stride, dx, dx_stride);
+    linear_bwd_dx_kernel<<<dim3((unsigned)ceil_div(p->I, 32), (unsigned)p->B), 256, 0, st>>>(*p, dy, dy_stride, dx, dx_stride);
     RHO_CHECK_LAUNCH("linear_bwd_dx");
   }
   if (dw) {

@@ -351,6 +351,36 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_pass1_kernel(const TI* __re
   }
 }
 
+// chunk partials [n][chunk][C][3] -> [n][C][3]: CTA = 8 channels x 32 chunk lanes, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) gn_bwd_colsum_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ out) {
+  __shared__ float red[8][8][3];
+  const int n = blockIdx.y;
+  const int cl = threadIdx.x & 7, kl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
+  float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (c < C) {
+    for (int k = kl; k < chunks; k += 32) {
+      const float* o = partial + (((int64_t)n * chunks + k) * C + c) * 3;
+      t1 += o[0]; t2 += o[1]; t3 += o[2];
+    }
+  }
+#pragma unroll
+  for (int off = 8; off < 32; off <<= 1) {
+    t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+    t3 += __shfl_xor_sync(0xffffffffu, t3, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) { red[warp][lane][0] = t1; red[warp][lane][1] = t2; red[warp][lane][2] = t3; }
+  __syncthreads();
+  if (threadIdx.x < 24) {
+    const int ch = threadIdx.x / 3, j = threadIdx.x % 3;
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][ch][j];
+    if (blockIdx.x * 8 + ch < C) out[((int64_t)n * C + blockIdx.x * 8 + ch) * 3 + j] = s;
+  }
+}
+
 // one CTA per sample n: reduce chunk partials -> S[n][c][3], group means, per-sample param grads
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const float* __restrict__ partial, int chunks, int C, int G,
                                                                    int64_t S, const float* __restrict__ gamma,
@@ -664,6 +694,189 @@ static int gn_chunks8(int N, int64_t S, int C) {
   if (chunks > 8192) chunks = 8192;
   return (int)chunks;
 }
+
+// ------------------------------------------------------------------------------------------------
+// backward, bf16 fast path (same thread <-> 8-channel mapping as the forward fast path)
+// ------------------------------------------------------------------------------------------------
+// d act(t) / dt; SiLU through one MUFU (sigmoid(t) = 0.5 + 0.5 tanh(t/2))
+template <bool SILU>
+__device__ __forceinline__ float act_grad8(float t, int act) {
+  if (SILU) {
+    const float sg = fmaf(0.5f, tanh_approx(0.5f * t), 0.5f);
+    return sg * fmaf(t, 1.f - sg, 1.f);
+  }
+  return act_grad(t, act);
+}
+
+struct GnBwdCoef {
+  float r[8], m0[8];   // xhat = x * r + m0        (r = rstd, m0 = (pre_add - mean) * rstd)
+  float gf[8], bf[8];  // t = xhat * gf + bf        (gf = gamma * (1 + sc), bf = beta * (1 + sc) + sh)
+};
+__device__ __forceinline__ void gn_bwd_coef8(GnBwdCoef& k, int n, int c, int C, int G, const float* __restrict__ stats,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             const float* __restrict__ pre_add, int pre_stride, const float* __restrict__ scale,
+                                             const float* __restrict__ shift, int film_stride) {
+  const int cpg = C / G;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float mean = stats[((int64_t)n * G + g) * 2], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+    const float pa = pre_add ? pre_add[(int64_t)n * pre_stride + c + j] : 0.f;
+    const float f = scale ? 1.f + scale[(int64_t)n * film_stride + c + j] : 1.f;
+    const float sh = shift ? shift[(int64_t)n * film_stride + c + j] : 0.f;
+    k.r[j] = rstd;
+    k.m0[j] = (pa - mean) * rstd;
+    k.gf[j] = gamma[c + j] * f;
+    k.bf[j] = beta[c + j] * f + sh;
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(u[j] << 16); v[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u); }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_pass1_8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                                       const bf16* __restrict__ dy, const float* __restrict__ pre_add,
+                                                                       int pre_stride, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift, int film_stride,
+                                                                       const float* __restrict__ stats, int C1, int C2, int64_t S, int G,
+                                                                       int chunks, int act, float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int rows = GN_THREADS / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per, p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const int row = tid / CV, cv = tid - row * CV;
+  const int c = cv * 8;
+  __shared__ float sc1[2048], sc2[2048], sc3[2048];
+  float a1[8], a2[8], a3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; }
+  if (row < rows) {
+    GnBwdCoef k;
+    gn_bwd_coef8(k, n, c, C, G, stats, gamma, beta, pre_add, pre_stride, scale, shift, film_stride);
+    const bf16* src = c < C1 ? x + (int64_t)n * S * C1 + c : x2 + (int64_t)n * S * C2 + (c - C1);
+    const int64_t stride = c < C1 ? C1 : C2;
+    const bf16* dsrc = dy + (int64_t)n * S * C + c;
+    auto accum = [&](const uint4& qx, const uint4& qd) {
+      float v[8], d[8];
+      unpack8(qx, v);
+      unpack8(qd, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(v[j], k.r[j], k.m0[j]);
+        const float dv = d[j] * act_grad8<SILU>(fmaf(xh, k.gf[j], k.bf[j]), act);
+        a1[j] += dv;
+        a2[j] = fmaf(dv, xh, a2[j]);
+        a3[j] += xh;
+      }
+    };
+    int64_t p = p0 + row;
+    for (; p + rows < p1; p += 2 * (int64_t)rows) {
+      const uint4 qx0 = __ldg(reinterpret_cast<const uint4*>(src + p * stride));
+      const uint4 qx1 = __ldg(reinterpret_cast<const uint4*>(src + (p + rows) * stride));
+      const uint4 qd0 = __ldg(reinterpret_cast<const uint4*>(dsrc + p * C));
+      const uint4 qd1 = __ldg(reinterpret_cast<const uint4*>(dsrc + (p + rows) * C));
+      accum(qx0, qd0);
+      accum(qx1, qd1);
+    }
+    for (; p < p1; p += rows) accum(__ldg(reinterpret_cast<const uint4*>(src + p * stride)), __ldg(reinterpret_cast<const uint4*>(dsrc + p * C)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = row * C + c + j;
+      sc1[idx] = a1[j]; sc2[idx] = a2[j]; sc3[idx] = a3[j];
+    }
+  }
+  __syncthreads();
+  float* out = partial + ((int64_t)n * chunks + chunk) * C * 3;
+  for (int cc = tid; cc < C; cc += GN_THREADS) {
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int r = 0; r < rows; ++r) { t1 += sc1[r * C + cc]; t2 += sc2[r * C + cc]; t3 += sc3[r * C + cc]; }
+    out[cc * 3] = t1; out[cc * 3 + 1] = t2; out[cc * 3 + 2] = t3;
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_pass2_8_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x2,
+                                                                       const bf16* __restrict__ dy, const float* __restrict__ pre_add,
+                                                                       int pre_stride, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift, int film_stride,
+                                                                       const float* __restrict__ stats, const float* __restrict__ gmean,
+                                                                       int C1, int C2, int64_t S, int G, int chunks, int act,
+                                                                       bf16* __restrict__ dx, bf16* __restrict__ dx2) {
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int rows = GN_THREADS / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = (S + chunks - 1) / chunks;
+  const int64_t p0 = (int64_t)chunk * per, p1 = min(S, p0 + per);
+  const int tid = threadIdx.x;
+  const int row = tid / CV, cv = tid - row * CV;
+  if (row >= rows) return;
+  const int c = cv * 8;
+  const int cpg = C / G;
+  GnBwdCoef k;
+  gn_bwd_coef8(k, n, c, C, G, stats, gamma, beta, pre_add, pre_stride, scale, shift, film_stride);
+  // dx = rstd * (gf * dv - m1 - xhat * m2) = dv * A - B1 - xhat * B2
+  float A[8], B1[8], B2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    A[j] = k.r[j] * k.gf[j];
+    B1[j] = k.r[j] * gmean[((int64_t)n * G + g) * 2];
+    B2[j] = k.r[j] * gmean[((int64_t)n * G + g) * 2 + 1];
+  }
+  const bf16* src = c < C1 ? x + (int64_t)n * S * C1 + c : x2 + (int64_t)n * S * C2 + (c - C1);
+  bf16* dst = c < C1 ? dx + (int64_t)n * S * C1 + c : dx2 + (int64_t)n * S * C2 + (c - C1);
+  const int64_t stride = c < C1 ? C1 : C2;
+  const bf16* dsrc = dy + (int64_t)n * S * C + c;
+  auto transform = [&](const uint4& qx, const uint4& qd) -> uint4 {
+    float v[8], d[8];
+    unpack8(qx, v);
+    unpack8(qd, d);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float r2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float xh = fmaf(v[j + e], k.r[j + e], k.m0[j + e]);
+        const float dv = d[j + e] * act_grad8<SILU>(fmaf(xh, k.gf[j + e], k.bf[j + e]), act);
+        r2[e] = fmaf(dv, A[j + e], -fmaf(xh, B2[j + e], B1[j + e]));
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(r2[0], r2[1]);
+      ow[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return o;
+  };
+  int64_t p = p0 + row;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {
+    const uint4 qx0 = __ldg(reinterpret_cast<const uint4*>(src + p * stride));
+    const uint4 qx1 = __ldg(reinterpret_cast<const uint4*>(src + (p + rows) * stride));
+    const uint4 qd0 = __ldg(reinterpret_cast<const uint4*>(dsrc + p * C));
+    const uint4 qd1 = __ldg(reinterpret_cast<const uint4*>(dsrc + (p + rows) * C));
+    *reinterpret_cast<uint4*>(dst + p * stride) = transform(qx0, qd0);
+    *reinterpret_cast<uint4*>(dst + (p + rows) * stride) = transform(qx1, qd1);
+  }
+  for (; p < p1; p += rows)
+    *reinterpret_cast<uint4*>(dst + p * stride) = transform(__ldg(reinterpret_cast<const uint4*>(src + p * stride)), __ldg(reinterpret_cast<const uint4*>(dsrc + p * C)));
+}
+
+static int gn_chunks_bwd8(int N, int64_t S, int C) {
+  const int rows = GN_THREADS / (C >> 3);
+  int64_t chunks = ceil_div((int64_t)sm_count() * 2, N);     // one resident wave: 2 CTAs per SM
+  int64_t max_chunks = ceil_div(S, (int64_t)rows * 8);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  return (int)chunks;
+}
 static bool gn_fast8(const rho_gn_params* p) {
   const int C = p->C1 + p->C2;
   return p->in_dtype == RHO_BF16 && (p->C1 % 8 == 0) && (p->C2 % 8 == 0) && C <= 2048 && (C >> 3) <= GN_THREADS;
@@ -778,11 +991,11 @@ size_t rho_gn_bwd_workspace_bytes(const rho_gn_bwd_params* p) {
   if (!p) return 0;
   const rho_gn_params& f = p->fwd;
   const int C = f.C1 + f.C2;
-  int chunks = gn_chunks(f.N, f.S, C);
+  int chunks = std::max(gn_chunks(f.N, f.S, C), gn_fast8(&f) ? gn_chunks_bwd8(f.N, f.S, C) : 0);
   size_t partial = (size_t)f.N * chunks * C * 3;
   size_t sums = (size_t)f.N * C * 3;
   size_t gmean = (size_t)f.N * f.groups * 2;
-  return (partial + sums + gmean) * sizeof(float);
+  return (partial + 2 * sums + gmean) * sizeof(float);
 }
 
 int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
@@ -793,12 +1006,14 @@ int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
   RHO_REQUIRE(p->dy && p->dx && f.gamma && f.beta, "gn_bwd: null tensor");
   RHO_REQUIRE((f.C2 == 0) || p->dx2, "gn_bwd: dx2 required for concat input");
   const int C = f.C1 + f.C2;
-  int chunks = gn_chunks(f.N, f.S, C);
+  const bool fast = gn_fast8(&f) && f.out_dtype == RHO_BF16;
+  int chunks = fast ? gn_chunks_bwd8(f.N, f.S, C) : gn_chunks(f.N, f.S, C);
   size_t need = rho_gn_bwd_workspace_bytes(p);
   if (!p->workspace || p->workspace_bytes < need) return fail(RHO_ERR_WORKSPACE, "gn_bwd: workspace %zu < %zu", p->workspace_bytes, need);
   float* partial = (float*)p->workspace;
   float* sums = partial + (size_t)f.N * chunks * C * 3;
-  float* gmean = sums + (size_t)f.N * C * 3;
+  float* colsums = sums + (size_t)f.N * C * 3;
+  float* gmean = colsums + (size_t)f.N * C * 3;
   cudaStream_t st = as_stream(stream);
   dim3 grid(chunks, f.N);
 #define RHO_GNB1(TI, TO)                                                                                                          \
@@ -811,6 +1026,13 @@ int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
                                                            f.stats, gmean, f.C1, f.C2, f.S, f.groups, chunks, f.act, (TI*)p->dx,   \
                                                            (TI*)p->dx2)
   const int key = f.in_dtype * 2 + f.out_dtype;
+#define RHO_GNB8(KERN, SILU, ...)                                                                                              \
+  KERN<SILU><<<grid, GN_THREADS, 0, st>>>((const bf16*)f.x, (const bf16*)f.x2, (const bf16*)p->dy, f.pre_add, f.pre_add_stride, \
+                                          f.gamma, f.beta, f.scale, f.shift, f.film_stride, f.stats, __VA_ARGS__)
+  if (fast) {
+    if (f.act == RHO_ACT_SILU) RHO_GNB8(gn_bwd_pass1_8_kernel, true, f.C1, f.C2, f.S, f.groups, chunks, f.act, partial);
+    else RHO_GNB8(gn_bwd_pass1_8_kernel, false, f.C1, f.C2, f.S, f.groups, chunks, f.act, partial);
+  } else
   switch (key) {
     case 0: RHO_GNB1(float, float); break;
     case 1: RHO_GNB1(float, bf16); break;
@@ -819,13 +1041,19 @@ int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
     default: return fail(RHO_ERR_INVALID_ARG, "gn_bwd: bad dtype");
   }
   RHO_CHECK_LAUNCH("gn_bwd_pass1");
-  gn_bwd_reduce_kernel<<<f.N, GN_THREADS, 0, st>>>(partial, chunks, C, f.groups, f.S, f.gamma, f.beta, f.scale, f.film_stride, f.stats,
+  gn_bwd_colsum_kernel<<<dim3((C + 7) / 8, f.N), 256, 0, st>>>(partial, chunks, C, colsums);
+  RHO_CHECK_LAUNCH("gn_bwd_colsum");
+  gn_bwd_reduce_kernel<<<f.N, GN_THREADS, 0, st>>>(colsums, 1, C, f.groups, f.S, f.gamma, f.beta, f.scale, f.film_stride, f.stats,
                                                    sums, gmean, p->dscale, p->dshift, p->dfilm_stride, p->dpre_add);
   RHO_CHECK_LAUNCH("gn_bwd_reduce");
   if (p->dgamma || p->dbeta) {
     gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, f.N, C, f.scale, f.film_stride, p->dgamma, p->dbeta);
     RHO_CHECK_LAUNCH("gn_bwd_param");
   }
+  if (fast) {
+    if (f.act == RHO_ACT_SILU) RHO_GNB8(gn_bwd_pass2_8_kernel, true, gmean, f.C1, f.C2, f.S, f.groups, chunks, f.act, (bf16*)p->dx, (bf16*)p->dx2);
+    else RHO_GNB8(gn_bwd_pass2_8_kernel, false, gmean, f.C1, f.C2, f.S, f.groups, chunks, f.act, (bf16*)p->dx, (bf16*)p->dx2);
+  } else
   switch (key) {
     case 0: RHO_GNB2(float, float); break;
     case 1: RHO_GNB2(float, bf16); break;
@@ -835,6 +1063,7 @@ int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
   RHO_CHECK_LAUNCH("gn_bwd_pass2");
 #undef RHO_GNB1
 #undef RHO_GNB2
+#undef RHO_GNB8
   return RHO_OK;
 }
 

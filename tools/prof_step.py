@@ -50,5 +50,6 @@ for k, r in sorted(rows.items(), key=lambda kv: -kv[1][1])[:28]:
 
 print("-- individual launches of the CUDA-core conv engines (us) --")
 for e in prof.events():
-    if e.device_type == torch.autograd.DeviceType.CUDA and ("simt" in e.name or "small" in e.name):
+    pats = os.environ.get("RHO_PROF_LIST", "simt,small").split(",")
+    if e.device_type == torch.autograd.DeviceType.CUDA and any(q in e.name for q in pats):
         print(f"{e.device_time:10.1f}  {e.name[:90]}")
