@@ -1,24 +1,25 @@
 // QKVAttention / QKVAttentionLegacy (rho_diffusion/models/unet_v2.py:365-436) on the 5th-generation tensor cores:
 // flash-style forward with tcgen05 MMAs, TMEM accumulators and TMA-fed operands (sm_100a).
 //
-// One CTA = 128 query rows of one (sample, head); key tiles of 128.
-//   S = Q K^T      : tcgen05.mma 128x128x(ch)   -> TMEM columns [0,128)     (A = Q, B = K, both K-major from TMA)
-//   softmax        : thread r owns TMEM lane r = query row r, so the row max / row sum need NO shuffles:
-//                    pass 1 reads the row from TMEM for the max, pass 2 re-reads it, exponentiates (exp2, fp32),
-//                    and writes P as bf16 into shared memory in the 128-byte-swizzled K-major layout
-//   O += P V       : tcgen05.mma 128x(ch)x128   -> TMEM columns [128,128+ch) (A = P, B = V as an MN-major operand:
+// One CTA = 128 query rows of one (sample, head); key tiles of 64.
+//   S_j = Q K_j^T  : tcgen05.mma 128x64x(ch)  -> TMEM columns [64*(j&1), +64)  -- S is DOUBLE-BUFFERED: the issuer launches
+//                    S_{j+1} before it waits for P_j, so the tensor core computes the next logits while the row owners
+//                    exponentiate the current ones (no MMA latency on the softmax critical path)
+//   softmax        : thread r owns TMEM lane r = query row r, so row max / row sum need NO shuffles.  One sweep per tile:
+//                    p = exp2(s*c - m*c) against the running max known BEFORE the tile (lazy max: O is rescaled and the
+//                    tile redone only when a row outgrows it by 2^8; the stale max cancels in O / l and in the lse);
+//                    P goes to shared memory as bf16 in the 128-byte-swizzled K-major layout (double-buffered)
+//   O += P_j V_j   : tcgen05.mma 128x(ch)x64  -> TMEM columns [128,128+ch)  (A = P, B = V as an MN-major operand:
 //                    V is [keys x ch] row-major, exactly what channels-last qkv gives)
-//   when the running max moves, the owner threads rescale their O row in TMEM (tcgen05.ld / tcgen05.st).
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax / correction /
-// epilogue.  Two CTAs per SM (<= 97 KB smem, 256 TMEM columns each): one CTA's exponentials (MUFU-bound) overlap the
-// other's MMAs and loads.  The T x T weight matrix never exists in HBM (the reference materialises 4.3 GB per
-// sample per block at T = 16384).
+// epilogue.  ch = 64: two CTAs per SM (81 KB smem, 256 TMEM columns each).  The T x T weight matrix never exists in HBM
+// (the reference materialises 4.3 GB per sample per block at T = 16384).
 #include "tc_common.cuh"
 
 namespace rho {
 
 constexpr int AT_BM = 128;   // queries per CTA
-constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_BN = 64;    // keys per tile
 
 struct AttnTcParams {
   int T, heads, ch, order;
@@ -30,20 +31,21 @@ struct AttnTcParams {
 };
 
 template <int CH>
-__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnTcParams p,
-                                                                      bf16* __restrict__ out, float* __restrict__ lse) {
+__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
+    attn_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap kv_map, const AttnTcParams p,
+                   bf16* __restrict__ out, float* __restrict__ lse) {
   constexpr int KB = CH / 64;                   // 64-channel K blocks of Q / K, N atoms of V
-  constexpr int TILE_BYTES = 128 * 128;         // one [128 rows x 64 ch] bf16 block
-  constexpr int Q_BYTES = KB * TILE_BYTES, K_BYTES = KB * TILE_BYTES, V_BYTES = KB * TILE_BYTES;
-  constexpr int K_STAGES = CH == 64 ? 2 : 1;
-  constexpr int P_BYTES = 2 * TILE_BYTES;       // [2 key blocks][128 rows][64 keys]
+  constexpr int Q_TILE = AT_BM * 128;           // [128 rows x 64 ch] bf16
+  constexpr int KV_TILE = AT_BN * 128;          // [64 rows x 64 ch] bf16
+  constexpr int Q_BYTES = KB * Q_TILE, KV_BYTES = KB * KV_TILE;
+  constexpr int P_TILE = AT_BM * 128;           // [128 rows x 64 keys] bf16
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + K_STAGES * K_BYTES;
-  uint8_t* sP = sV + V_BYTES;
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_ready, p_ready, o_done;
+  uint8_t* sK = sQ + Q_BYTES;                   // [2 stages]
+  uint8_t* sV = sK + 2 * KV_BYTES;              // [2 stages]
+  uint8_t* sP = sV + 2 * KV_BYTES;              // [2 buffers]
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_ready[2], p_ready[2], o_done;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,10 +55,13 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
-    mbar_init(&s_ready, 1); mbar_init(&o_done, 1);
-    mbar_init(&p_ready, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_ready[s], 1);
+      mbar_init(&p_ready[s], 128);
+    }
+    mbar_init(&o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -66,22 +71,22 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = tmem_base_s;          // S: columns [0, 128)
+  const uint32_t tmem_s = tmem_base_s;          // S: columns [0, 64) and [64, 128)
   const uint32_t tmem_o = tmem_base_s + 128;    // O: columns [128, 128 + CH)
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&q_full, Q_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sQ + kb * TILE_BYTES, &qkv_map, &q_full, qc + kb * 64, q0, n);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sQ + kb * Q_TILE, &q_map, &q_full, qc + kb * 64, q0, n);
       for (int j = 0; j < nt; ++j) {
-        const int ks = j % K_STAGES;
-        const uint32_t kphase = (uint32_t)(j / K_STAGES) & 1;
-        mbar_wait(&k_empty[ks], kphase ^ 1);
-        mbar_expect_tx(&k_full[ks], K_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sK + ks * K_BYTES + kb * TILE_BYTES, &qkv_map, &k_full[ks], kc + kb * 64, j * AT_BN, n);
-        mbar_wait(&v_empty, (uint32_t)(j & 1) ^ 1);
-        mbar_expect_tx(&v_full, V_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sV + kb * TILE_BYTES, &qkv_map, &v_full, vc + kb * 64, j * AT_BN, n);
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], KV_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sK + s * KV_BYTES + kb * KV_TILE, &kv_map, &k_full[s], kc + kb * 64, j * AT_BN, n);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], KV_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(sV + s * KV_BYTES + kb * KV_TILE, &kv_map, &v_full[s], vc + kb * 64, j * AT_BN, n);
       }
     }
   } else if (warp == 1) {
@@ -91,37 +96,37 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(CH >> 3) << 17) |
                                 ((uint32_t)(AT_BM >> 4) << 24);
       auto issue_qk = [&](int j) {
-        const int ks = j % K_STAGES;
-        mbar_wait(&k_full[ks], (uint32_t)(j / K_STAGES) & 1);
+        const int s = j & 1;
+        mbar_wait(&k_full[s], (uint32_t)(j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * TILE_BYTES));
-          const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + ks * K_BYTES + kb * TILE_BYTES));
+          const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * Q_TILE));
+          const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + s * KV_BYTES + kb * KV_TILE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_qk, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s + (uint32_t)(s * AT_BN), a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_qk, (kb | k) != 0);
         }
-        umma_commit(&k_empty[ks]);
-        umma_commit(&s_ready);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_ready[s]);
       };
       mbar_wait(&q_full, 0);
       issue_qk(0);
       for (int j = 0; j < nt; ++j) {
-        mbar_wait(&p_ready, (uint32_t)j & 1);     // P_j is in smem and the softmax threads are done reading S_j
-        mbar_wait(&v_full, (uint32_t)j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {          // two 64-key blocks of P
-          const uint64_t a = at_desc_kmajor<128>(smem_u32(sP + kb * TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {           // 16 keys per MMA: two 8-row K atoms = 2048 bytes of V
-            const uint64_t b = at_desc_mnmajor(smem_u32(sV + (kb * 64 + k * 16) * 128), TILE_BYTES);
-            umma_f16(tmem_o, a + (uint64_t)(2 * k), b, idesc_pv, (j | kb | k) != 0);
-          }
-        }
-        umma_commit(&v_empty);
-        umma_commit(&o_done);
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1;
+        // S buffer (j+1)&1 was last read for tile j-1, whose p_ready was awaited in the previous iteration
         if (j + 1 < nt) issue_qk(j + 1);
+        mbar_wait(&p_ready[s], ph);               // P_j is in smem and the row owners are done reading S_j
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        const uint64_t a = at_desc_kmajor<128>(smem_u32(sP + s * P_TILE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {             // 16 keys per MMA: two 8-row K atoms = 2048 bytes of V
+          const uint64_t b = at_desc_mnmajor(smem_u32(sV + s * KV_BYTES + k * 16 * 128), KV_TILE);
+          umma_f16(tmem_o, a + (uint64_t)(2 * k), b, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(&o_done);
       }
     }
   } else {
@@ -130,93 +135,99 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     float m = -INFINITY, l = 0.f;
+    // One sweep over the 64 logits of this row: p = exp2(s*c - mb) (one FFMA + one MUFU per element) -> bf16 P in swizzled
+    // smem; returns the row sum and the row max of the raw logits.
+    auto exp_pass = [&](uint32_t ts, uint8_t* pbuf, int kvalid, float mb, float& lsum, float& mx_out) {
+      const bool full = kvalid >= AT_BN;
+      uint32_t va[32], vb[32];
+      tmem_ld32_async(ts + lane_addr, va);
+      tmem_ld32_async(ts + lane_addr + 32u, vb);
+      tmem_wait_ld();
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t(&v)[32] = half ? vb : va;
+        const int c = half * 32;
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+          float p0 = ex2_approx(fmaf(s0, p.scale_log2, -mb));
+          float p1 = ex2_approx(fmaf(s1, p.scale_log2, -mb));
+          if (full) {
+            mx0 = fmaxf(mx0, s0);
+            mx1 = fmaxf(mx1, s1);
+          } else {
+            const bool ok0 = c + e < kvalid, ok1 = c + e + 1 < kvalid;
+            p0 = ok0 ? p0 : 0.f;
+            p1 = ok1 ? p1 : 0.f;
+            mx0 = fmaxf(mx0, ok0 ? s0 : -INFINITY);
+            mx1 = fmaxf(mx1, ok1 ? s1 : -INFINITY);
+          }
+          if (e & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        // 32 keys = 4 chunks of 16 bytes; chunk index within the 128-byte row = c / 8 + i
+        uint8_t* rowp = pbuf + r * 128;
+        const int ch0 = c >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = (ch0 + i) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+      lsum = (ls0 + ls1) + (ls2 + ls3);
+      mx_out = fmaxf(mx0, mx1);
+    };
+    constexpr float AT_TAU = 8.0f;
     for (int j = 0; j < nt; ++j) {
-      mbar_wait(&s_ready, (uint32_t)j & 1);
+      const int s = j & 1;
+      mbar_wait(&s_ready[s], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      const uint32_t ts = tmem_s + (uint32_t)(s * AT_BN);
+      uint8_t* pbuf = sP + s * P_TILE;
       const int kvalid = p.T - j * AT_BN;         // keys >= kvalid are padding (only in the last tile)
-      const bool full = kvalid >= AT_BN;          // warp-uniform
-      // ---- pass 1: row max (TMEM loads software-pipelined: chunk c+1 is in flight while chunk c is reduced)
-      float mx = -INFINITY;
-      {
+      float lsum, mx;
+      if (j == 0) {
+        // first tile: the row max is not known yet -> one extra sweep for it
         uint32_t va[32], vb[32];
-        tmem_ld32_async(tmem_s + lane_addr, va);
+        tmem_ld32_async(ts + lane_addr, va);
+        tmem_ld32_async(ts + lane_addr + 32u, vb);
         tmem_wait_ld();
+        float mx0 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < AT_BN; c += 64) {
-          tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 32), vb);
-          if (full) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[e]), __uint_as_float(va[e + 1])));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c + e < kvalid) ? __uint_as_float(va[e]) : -INFINITY);
-          }
-          tmem_wait_ld();
-          if (c + 64 < AT_BN) tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 64), va);
-          if (full) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (c + 32 + e < kvalid) ? __uint_as_float(vb[e]) : -INFINITY);
-          }
-          if (c + 64 < AT_BN) tmem_wait_ld();
+        for (int e = 0; e < 32; ++e) {
+          mx0 = fmaxf(mx0, e < kvalid ? __uint_as_float(va[e]) : -INFINITY);
+          mx0 = fmaxf(mx0, 32 + e < kvalid ? __uint_as_float(vb[e]) : -INFINITY);
         }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2_approx((m - m_new) * p.scale_log2);   // m = -inf on the first tile -> 0
-      // ---- correction: rescale this row of O when the running max moved (PV_{j-1} has completed: s_ready(j) follows it)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        m = mx0;
+        exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
+      } else {
+        exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
+        if (__any_sync(0xffffffffu, (mx - m) * p.scale_log2 > AT_TAU)) {
+          const float m_new = fmaxf(m, mx);
+          const float alpha = ex2_approx((m - m_new) * p.scale_log2);
+          // rescale this row of O once every PV issued so far (tiles < j) has completed
+          mbar_wait(&o_done, (uint32_t)(j - 1) & 1);
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < CH; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
+          for (int c = 0; c < CH; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-          tmem_st32(tmem_o + lane_addr + (uint32_t)c, v);
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st32(tmem_o + lane_addr + (uint32_t)c, v);
+          }
+          l *= alpha;
+          m = m_new;
+          exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
         }
       }
-      l *= alpha;
-      m = m_new;
-      const float mb = m_new * p.scale_log2;
-      // ---- pass 2: p = exp2(s*c - m*c) (one FFMA + one MUFU per element), row sum, bf16 P into swizzled smem
-      {
-        uint32_t v[32];
-        float ls0 = 0.f, ls1 = 0.f;
-        tmem_ld32_async(tmem_s + lane_addr, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int c = 0; c < AT_BN; c += 32) {
-          uint32_t packed[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -mb));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -mb));
-            if (!full) {
-              p0 = (c + e < kvalid) ? p0 : 0.f;
-              p1 = (c + e + 1 < kvalid) ? p1 : 0.f;
-            }
-            ls0 += p0;
-            ls1 += p1;
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-          if (c + 32 < AT_BN) tmem_ld32_async(tmem_s + lane_addr + (uint32_t)(c + 32), v);   // v is dead: reuse for the next chunk
-          // 32 keys = 4 chunks of 16 bytes; key block kb = c / 64, chunk index within the 128-byte row = (c % 64) / 8 + i
-          uint8_t* rowp = sP + (c >> 6) * TILE_BYTES + r * 128;
-          const int ch0 = (c & 63) >> 3;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int chunk = (ch0 + i) ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          }
-          if (c + 32 < AT_BN) tmem_wait_ld();
-        }
-        l += ls0 + ls1;
-      }
+      l += lsum;
       tc_fence_before();          // order our tcgen05.ld/st before the MMAs the issuer launches after the barrier
       fence_proxy_async_smem();   // make the P stores visible to the tensor core (async proxy)
-      mbar_arrive(&p_ready);
+      mbar_arrive(&p_ready[s]);
     }
     // ---- epilogue: O / l -> bf16 -> global
     mbar_wait(&o_done, (uint32_t)(nt - 1) & 1);
@@ -230,10 +241,14 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1) attn_tc_kernel(const __
       tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
       if (q < p.T) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          float o[4] = {__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv, __uint_as_float(v[e + 2]) * inv,
-                        __uint_as_float(v[e + 3]) * inv};
-          store4(orow + c + e, o);
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          __nv_bfloat162 h2;
+          h2 = __floats2bfloat162_rn(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv); o.x = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv); o.y = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv); o.z = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv); o.w = *reinterpret_cast<uint32_t*>(&h2);
+          *reinterpret_cast<uint4*>(orow + c + e) = o;
         }
       }
     }
@@ -255,10 +270,9 @@ bool attention_fwd_tc_supported(const rho_attn_params* p) {
 }
 
 template <int CH>
-static int launch_attn_tc(const CUtensorMap& map, const AttnTcParams& ap, const rho_attn_params* p, cudaStream_t st) {
+static int launch_attn_tc(const CUtensorMap& qmap, const CUtensorMap& kvmap, const AttnTcParams& ap, const rho_attn_params* p, cudaStream_t st) {
   constexpr int KB = CH / 64;
-  constexpr int K_STAGES = CH == 64 ? 2 : 1;
-  constexpr size_t SMEM = (size_t)(KB + K_STAGES * KB + KB + 2) * 128 * 128 + 1024;
+  constexpr size_t SMEM = (size_t)KB * 16384 + 4 * (size_t)KB * 8192 + 2 * 16384 + 1024;
   auto kern = attn_tc_kernel<CH>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -267,7 +281,7 @@ static int launch_attn_tc(const CUtensorMap& map, const AttnTcParams& ap, const 
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div(p->T, AT_BM), p->heads, p->N);
-  kern<<<grid, 192, SMEM, st>>>(map, ap, (bf16*)p->out, p->lse);
+  kern<<<grid, 192, SMEM, st>>>(qmap, kvmap, ap, (bf16*)p->out, p->lse);
   RHO_CHECK_LAUNCH("attention_fwd_tcgen05");
   return RHO_OK;
 }
@@ -276,7 +290,7 @@ int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
   auto enc = get_encode();
   if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
   const int C = p->heads * p->ch;
-  CUtensorMap map;
+  CUtensorMap map, kvmap;
   cuuint64_t gdim[3] = {(cuuint64_t)(3 * C), (cuuint64_t)p->T, (cuuint64_t)p->N};
   cuuint64_t gstr[2] = {(cuuint64_t)(3 * C) * 2, (cuuint64_t)(3 * C) * 2 * (cuuint64_t)p->T};
   cuuint32_t bdim[3] = {64, 128, 1};
@@ -284,14 +298,18 @@ int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->qkv), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: %d", (int)r);
+  bdim[1] = AT_BN;
+  r = enc(&kvmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->qkv), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(kv) failed: %d", (int)r);
   AttnTcParams ap;
   ap.T = p->T; ap.heads = p->heads; ap.ch = p->ch; ap.order = p->order; ap.C = C;
   if (p->order == 0) { ap.q_col = 0; ap.k_col = p->ch; ap.v_col = 2 * p->ch; ap.head_stride = 3 * p->ch; }
   else { ap.q_col = 0; ap.k_col = C; ap.v_col = 2 * C; ap.head_stride = p->ch; }
   ap.scale = 1.0f / sqrtf((float)p->ch);
   ap.scale_log2 = ap.scale * 1.4426950408889634f;
-  if (p->ch == 64) return launch_attn_tc<64>(map, ap, p, st);
-  return launch_attn_tc<128>(map, ap, p, st);
+  if (p->ch == 64) return launch_attn_tc<64>(map, kvmap, ap, p, st);
+  return launch_attn_tc<128>(map, kvmap, ap, p, st);
 }
 
 }  // namespace rho
