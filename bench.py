@@ -307,7 +307,7 @@ def run_b200(args):
         g1.record()
         barrier()
         ms_train = g0.elapsed_time(g1)
-        train = {"ms": ms_train, "batch": Bt, "steps": args.train_steps, "loss": float(loss)}
+        train = {"ms": ms_train, "batch": Bt, "steps": args.train_steps, "loss": float(loss.detach())}
 
     # ---- reduce over ranks (max time)
     def max_over_ranks(v):

@@ -4,12 +4,13 @@
 // With S = scale * Q K^T, P = exp(S - lse) (lse from the forward), delta = rowsum(dO o O):
 //     dV = P^T dO        dP = dO V^T        dS = P o (dP - delta)        dQ = scale * dS K        dK = scale * dS^T Q
 // Two deterministic kernels (no atomics), both recomputing P from the saved log-sum-exp:
-//   attn_bwd_dq_kernel : one CTA = 128 queries, loops over 64-key tiles.
-//        S  = Q K_j^T  (128x64)  -> TMEM [0,64)          dP = dO V_j^T (128x64) -> TMEM [64,128)
+//   attn_bwd_dq_kernel : one CTA = 128 queries, loops over 32-key tiles.
+//        S  = Q K_j^T  (128x32)  and  dP = dO V_j^T (128x32) -> TMEM, DOUBLE-BUFFERED ([64b, 64b+32) / [64b+32, 64b+64)):
+//        the issuer launches tile j+1's pair before it waits for dS_j, so the tensor core works under the exponentials
 //        thread r <-> query row r: dS row -> bf16 -> swizzled smem;   dQ += dS K_j  -> TMEM [128,128+ch)
-//   attn_bwd_dkv_kernel: one CTA = 128 keys, loops over 64-query tiles (the transposed problem, so that the thread
+//   attn_bwd_dkv_kernel: one CTA = 128 keys, loops over 32-query tiles (the transposed problem, so that the thread
 //        <-> TMEM-lane mapping is again one thread per output row):
-//        S^T = K Q_i^T (128x64) -> TMEM [0,64)           dP^T = V dO_i^T        -> TMEM [64,128)
+//        S^T = K Q_i^T (128x32), dP^T = V dO_i^T -> TMEM, double-buffered the same way
 //        P^T, dS^T rows -> bf16 -> smem;   dV += P^T dO_i -> TMEM,   dK += dS^T Q_i -> TMEM
 //        (lse / delta are per COLUMN here: staged per tile in shared memory and read as broadcasts)
 // Every operand is a TMA box of the channels-last qkv / dout tensors in the 128-byte-swizzled layout: a [rows x 64 ch]
@@ -29,17 +30,64 @@ struct AttnBwdTcParams {
 };
 
 constexpr int AB_ROWS = 128;   // rows (queries resp. keys) owned by a CTA
-constexpr int AB_COLS = 64;    // columns (keys resp. queries) per inner tile
+constexpr int AB_COLS = 32;    // columns (keys resp. queries) per inner tile
+constexpr int AB_STAGES = 4;   // TMA ring depth of the 32-row operand tiles
+constexpr int AB_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2-9: two row-owner warps per TMEM lane quarter (16 columns each)
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
-// store 32 consecutive bf16 columns [c, c+32) of row r into a [128 rows][64 cols] 128B-swizzled K-major tile
+// Per-row softmax statistics in the layout the backward kernels stream: ld[(n, h)][tile of 32 rows][64] with
+// [0,32) = lse * log2(e) and [32,64) = delta = rowsum(dO o O); rows >= T are zero (256-byte aligned tiles for bulk copies)
+__global__ void attn_bwd_stats_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                      float* __restrict__ ld, int T, int heads, int ch, int tiles, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over (n, h, tile, 32 rows)
+  if (i >= total) return;
+  const int rr = (int)(i & 31);
+  const long long tile_idx = i >> 5;
+  const int tile = (int)(tile_idx % tiles);
+  const long long nh = tile_idx / tiles;
+  const int h = (int)(nh % heads);
+  const long long n = nh / heads;
+  const int q = tile * 32 + rr;
+  float l2 = 0.f, dl = 0.f;
+  if (q < T) {
+    const long long base = (n * T + q) * (long long)(heads * ch) + h * ch;
+    for (int c = 0; c < ch; c += 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(out + base + c);
+      const uint4 b = *reinterpret_cast<const uint4*>(dout + base + c);
+      const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dl += __uint_as_float(ua[j] << 16) * __uint_as_float(ub[j] << 16) + __uint_as_float(ua[j] & 0xffff0000u) * __uint_as_float(ub[j] & 0xffff0000u);
+    }
+    l2 = lse[nh * T + q] * AB_LOG2E;
+  }
+  float* o = ld + tile_idx * 64;
+  o[rr] = l2;
+  o[32 + rr] = dl;
+}
+
+// store 32 consecutive bf16 columns [c, c+32) (c = 0 or 32) of row r into a [128 rows][64 cols] 128B-swizzled K-major tile
 __device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int c, const uint32_t (&packed)[16]) {
   uint8_t* rowp = tile + r * 128;
   const int ch0 = c >> 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+    const int chunk = (ch0 + i) ^ (r & 7);
+    *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+  }
+}
+// 16 consecutive bf16 columns [c, c+16) (c multiple of 16)
+__device__ __forceinline__ void store_row_chunk16(uint8_t* tile, int r, int c, const uint32_t (&packed)[8]) {
+  uint8_t* rowp = tile + r * 128;
+  const int ch0 = c >> 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     const int chunk = (ch0 + i) ^ (r & 7);
     *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
   }
@@ -53,22 +101,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // dQ
 // ------------------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
-    attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv64,
-                       const __grid_constant__ CUtensorMap do128, const AttnBwdTcParams p, const float* __restrict__ lse,
-                       const float* __restrict__ delta, bf16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(AB_THREADS, CH == 64 ? 2 : 1)
+    attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv32,
+                       const __grid_constant__ CUtensorMap do128, const AttnBwdTcParams p, const float* __restrict__ ld,
+                       bf16* __restrict__ dqkv) {
   constexpr int KB = CH / 64;
   constexpr int ROW_TILE = AB_ROWS * 128;       // [128 rows x 64 ch] bf16
-  constexpr int COL_TILE = AB_COLS * 128;       // [64 rows x 64 ch] bf16
+  constexpr int COL_TILE = AB_COLS * 128;       // [32 rows x 64 ch] bf16
   constexpr int Q_BYTES = KB * ROW_TILE, KV_BYTES = KB * COL_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + Q_BYTES;
-  uint8_t* sK = sdO + Q_BYTES;                  // [2 stages][KB][64 x 64]
-  uint8_t* sV = sK + 2 * KV_BYTES;
-  uint8_t* sdS = sV + 2 * KV_BYTES;             // [128][64]
-  __shared__ uint64_t q_full, kv_full[2], kv_empty[2], sdp_ready, ds_ready, dq_done;
+  uint8_t* sK = sdO + Q_BYTES;                  // [AB_STAGES][KB][32 x 64]
+  uint8_t* sV = sK + AB_STAGES * KV_BYTES;
+  uint8_t* sdS = sV + AB_STAGES * KV_BYTES;     // [128][64]: tile j uses the 32-column half j & 1
+  __shared__ uint64_t q_full, kv_full[AB_STAGES], kv_empty[AB_STAGES], sdp_ready[2], ds_ready[2], dq_done;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,9 +126,9 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&sdp_ready, 1); mbar_init(&dq_done, 1);
-    mbar_init(&ds_ready, 128);
+    for (int s = 0; s < AB_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_ready[s], 1); mbar_init(&ds_ready[s], 256); }
+    mbar_init(&dq_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -90,104 +138,116 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = tmem_base_s;            // S : [0, 64)
-  const uint32_t tmem_dp = tmem_base_s + 64;      // dP: [64, 128)
-  const uint32_t tmem_dq = tmem_base_s + 128;     // dQ: [128, 128 + CH)
+  // buffer b: S at [64 b, 64 b + 32), dP at [64 b + 32, 64 b + 64);  dQ at [128, 128 + CH)
+  const uint32_t tmem_sdp = tmem_base_s;
+  const uint32_t tmem_dq = tmem_base_s + 128;
 
+  // Producer and issuer warps keep warp-uniform control flow; only the asynchronous instructions are issued by one lane.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&q_full, 2 * Q_BYTES);
       for (int kb = 0; kb < KB; ++kb) {
         tma_load_3d(sQ + kb * ROW_TILE, &qkv128, &q_full, qc + kb * 64, q0, n);
         tma_load_3d(sdO + kb * ROW_TILE, &do128, &q_full, h * CH + kb * 64, q0, n);
       }
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % AB_STAGES;
+      mbar_wait(&kv_empty[s], ((uint32_t)(j / AB_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[s], 2 * KV_BYTES);
         for (int kb = 0; kb < KB; ++kb) {
-          tma_load_3d(sK + s * KV_BYTES + kb * COL_TILE, &qkv64, &kv_full[s], kc + kb * 64, j * AB_COLS, n);
-          tma_load_3d(sV + s * KV_BYTES + kb * COL_TILE, &qkv64, &kv_full[s], vc + kb * 64, j * AB_COLS, n);
+          tma_load_3d(sK + s * KV_BYTES + kb * COL_TILE, &qkv32, &kv_full[s], kc + kb * 64, j * AB_COLS, n);
+          tma_load_3d(sV + s * KV_BYTES + kb * COL_TILE, &qkv32, &kv_full[s], vc + kb * 64, j * AB_COLS, n);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
-      const uint32_t idesc_dq = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
-                                ((uint32_t)(AB_ROWS >> 4) << 24);
-      auto issue_sdp = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1);
-        tc_fence_after();
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
+    const uint32_t idesc_dq = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                              ((uint32_t)(AB_ROWS >> 4) << 24);
+    auto issue_sdp = [&](int j) {
+      const int s = j % AB_STAGES, b = j & 1;
+      mbar_wait(&kv_full[s], (uint32_t)(j / AB_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ts = tmem_sdp + (uint32_t)(b * 64), tdp = ts + 32;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * ROW_TILE));
-          const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + s * KV_BYTES + kb * COL_TILE));
+          const uint64_t bd = at_desc_kmajor<128>(smem_u32(sK + s * KV_BYTES + kb * COL_TILE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(ts, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
         }
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t a = at_desc_kmajor<128>(smem_u32(sdO + kb * ROW_TILE));
-          const uint64_t b = at_desc_kmajor<128>(smem_u32(sV + s * KV_BYTES + kb * COL_TILE));
+          const uint64_t bd = at_desc_kmajor<128>(smem_u32(sV + s * KV_BYTES + kb * COL_TILE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_dp, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(tdp, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_s, (kb | k) != 0);
         }
-        umma_commit(&sdp_ready);
-      };
-      mbar_wait(&q_full, 0);
-      issue_sdp(0);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        mbar_wait(&ds_ready, (uint32_t)j & 1);    // dS_j is in smem; the row owners are done reading S_j / dP_j
-        tc_fence_after();
-        const uint64_t a = at_desc_kmajor<128>(smem_u32(sdS));
+        umma_commit(&sdp_ready[b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    issue_sdp(0);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % AB_STAGES, b = j & 1;
+      // TMEM buffer (j+1)&1 was last read for tile j-1, whose ds_ready was awaited in the previous iteration
+      if (j + 1 < nt) issue_sdp(j + 1);
+      mbar_wait(&ds_ready[b], (uint32_t)(j >> 1) & 1);   // dS_j is in smem; the row owners are done reading S_j / dP_j
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a = at_desc_kmajor<128>(smem_u32(sdS)) + (uint64_t)(4 * b);   // 32-column half b = +64 bytes
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {             // 16 keys per MMA = two 8-row atoms of the K tile
-          const uint64_t b = at_desc_mnmajor(smem_u32(sK + s * KV_BYTES + k * 16 * 128), COL_TILE);
-          umma_f16(tmem_dq, a + (uint64_t)(2 * k), b, idesc_dq, (j | k) != 0);
+        for (int k = 0; k < 2; ++k) {             // 16 keys per MMA = two 8-row atoms of the K tile
+          const uint64_t bd = at_desc_mnmajor(smem_u32(sK + s * KV_BYTES + k * 16 * 128), COL_TILE);
+          umma_f16(tmem_dq, a + (uint64_t)(2 * k), bd, idesc_dq, (j | k) != 0);
         }
         umma_commit(&kv_empty[s]);
-        if (j + 1 < nt) issue_sdp(j + 1);         // its commit also covers dQ_j: dS may be overwritten after sdp_ready
-        else umma_commit(&dq_done);
       }
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(&dq_done);
+    __syncwarp();
   } else {
     const int lane_base = 32 * (warp & 3);
+    const int half = (warp - 2) >> 2;             // which 16 of the tile's 32 columns this warp owns
     const int r = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const int q = q0 + r;
-    const long long row_idx = ((long long)n * p.heads + h) * p.T + q;
-    const float lse2 = q < p.T ? lse[row_idx] * AB_LOG2E : 0.f;
-    const float dl = q < p.T ? delta[row_idx] : 0.f;
+    const int ntile = (p.T + 31) / 32;
+    const float* ldrow = ld + ((((long long)n * p.heads + h) * ntile + (q >> 5)) << 6) + (q & 31);
+    const float lse2 = q < p.T ? ldrow[0] : 0.f;
+    const float dl = q < p.T ? ldrow[32] : 0.f;
     for (int j = 0; j < nt; ++j) {
-      mbar_wait(&sdp_ready, (uint32_t)j & 1);
+      const int b = j & 1;
+      mbar_wait(&sdp_ready[b], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      uint32_t vs[16], vd[16];
+      tmem_ld16_async(tmem_sdp + lane_addr + (uint32_t)(b * 64 + half * 16), vs);
+      tmem_ld16_async(tmem_sdp + lane_addr + (uint32_t)(b * 64 + 32 + half * 16), vd);
+      tmem_wait_ld();
+      uint32_t packed[8];
 #pragma unroll
-      for (int c = 0; c < AB_COLS; c += 32) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32_async(tmem_s + lane_addr + (uint32_t)c, vs);
-        tmem_ld32_async(tmem_dp + lane_addr + (uint32_t)c, vd);
-        tmem_wait_ld();
-        uint32_t packed[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -lse2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -lse2));
-          packed[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - dl), p1 * (__uint_as_float(vd[e + 1]) - dl));
-        }
-        store_row_chunk32(sdS, r, c, packed);
+      for (int e = 0; e < 16; e += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -lse2));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -lse2));
+        packed[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - dl), p1 * (__uint_as_float(vd[e + 1]) - dl));
       }
+      store_row_chunk16(sdS, r, b * 32 + half * 16, packed);
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&ds_ready);
+      mbar_arrive(&ds_ready[b]);
     }
     mbar_wait(&dq_done, 0);
     tc_fence_after();
     bf16* orow = dqkv + ((long long)n * p.T + q) * (3 * p.C) + qc;
 #pragma unroll 1
-    for (int c = 0; c < CH; c += 32) {
+    for (int c = half * (CH / 2); c < (half + 1) * (CH / 2); c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_dq + lane_addr + (uint32_t)c, v);
       if (q < p.T) {
@@ -212,10 +272,10 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
 // dK, dV
 // ------------------------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
-    attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv64,
-                        const __grid_constant__ CUtensorMap do64, const AttnBwdTcParams p, const float* __restrict__ lse,
-                        const float* __restrict__ delta, bf16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(AB_THREADS, CH == 64 ? 2 : 1)
+    attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap qkv128, const __grid_constant__ CUtensorMap qkv32,
+                        const __grid_constant__ CUtensorMap do32, const AttnBwdTcParams p, const float* __restrict__ ld,
+                        bf16* __restrict__ dqkv) {
   constexpr int KB = CH / 64;
   constexpr int ROW_TILE = AB_ROWS * 128;
   constexpr int COL_TILE = AB_COLS * 128;
@@ -225,13 +285,13 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;
   uint8_t* sV = sK + K_BYTES;
-  uint8_t* sQ = sV + K_BYTES;                   // [2 stages][KB][64 x 64]
-  uint8_t* sdO = sQ + 2 * QD_BYTES;
-  uint8_t* sP = sdO + 2 * QD_BYTES;             // P^T  [128 keys][64 queries]
-  uint8_t* sdS = sP + ROW_TILE;                 // dS^T [128 keys][64 queries]
-  __shared__ uint64_t kv_full, qd_full[2], qd_empty[2], st_ready, pds_ready, acc_done;
+  uint8_t* sQ = sV + K_BYTES;                   // [AB_STAGES][KB][32 x 64]
+  uint8_t* sdO = sQ + AB_STAGES * QD_BYTES;
+  uint8_t* sP = sdO + AB_STAGES * QD_BYTES;     // P^T  [128 keys][64]: tile i uses the 32-column half i & 1
+  uint8_t* sdS = sP + ROW_TILE;                 // dS^T [128 keys][64]
+  __shared__ uint64_t kv_full, qd_full[AB_STAGES], qd_empty[AB_STAGES], st_ready[2], pds_ready[2], acc_done;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float sLD[2][128];   // per query tile: [0,64) lse*log2e, [64,128) delta
+  __shared__ __align__(128) float sLD[AB_STAGES][64];   // per query tile: [0,32) lse*log2e, [32,64) delta (bulk-copied)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * AB_ROWS, h = blockIdx.y, n = blockIdx.z;
@@ -240,9 +300,9 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
 
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
-    mbar_init(&st_ready, 1); mbar_init(&acc_done, 1);
-    mbar_init(&pds_ready, 128);
+    for (int s = 0; s < AB_STAGES; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_ready[s], 1); mbar_init(&pds_ready[s], 256); }
+    mbar_init(&acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -252,122 +312,127 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_st = tmem_base_s;                 // S^T : [0, 64)
-  const uint32_t tmem_dpt = tmem_base_s + 64;           // dP^T: [64, 128)
-  const uint32_t tmem_dk = tmem_base_s + 128;           // dK  : [128, 128 + CH)
-  const uint32_t tmem_dv = tmem_base_s + 128 + CH;      // dV  : [128 + CH, 128 + 2 CH)
+  // buffer b: S^T at [64 b, 64 b + 32), dP^T at [64 b + 32, 64 b + 64);  dK at [128, 128 + CH), dV at [128 + CH, 128 + 2 CH)
+  const uint32_t tmem_st = tmem_base_s;
+  const uint32_t tmem_dk = tmem_base_s + 128;
+  const uint32_t tmem_dv = tmem_base_s + 128 + CH;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&kv_full, 2 * K_BYTES);
       for (int kb = 0; kb < KB; ++kb) {
         tma_load_3d(sK + kb * ROW_TILE, &qkv128, &kv_full, kc + kb * 64, k0, n);
         tma_load_3d(sV + kb * ROW_TILE, &qkv128, &kv_full, vc + kb * 64, k0, n);
       }
-      for (int i = 0; i < ni; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qd_empty[s], ((uint32_t)(i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qd_full[s], 2 * QD_BYTES);
+    }
+    __syncwarp();
+    for (int i = 0; i < ni; ++i) {
+      const int s = i % AB_STAGES;
+      mbar_wait(&qd_empty[s], ((uint32_t)(i / AB_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&qd_full[s], 2 * QD_BYTES + 256);
+        bulk_load(sLD[s], ld + ((((long long)n * p.heads + h) * ni + i) << 6), 256, &qd_full[s]);
         for (int kb = 0; kb < KB; ++kb) {
-          tma_load_3d(sQ + s * QD_BYTES + kb * COL_TILE, &qkv64, &qd_full[s], qc + kb * 64, i * AB_COLS, n);
-          tma_load_3d(sdO + s * QD_BYTES + kb * COL_TILE, &do64, &qd_full[s], h * CH + kb * 64, i * AB_COLS, n);
+          tma_load_3d(sQ + s * QD_BYTES + kb * COL_TILE, &qkv32, &qd_full[s], qc + kb * 64, i * AB_COLS, n);
+          tma_load_3d(sdO + s * QD_BYTES + kb * COL_TILE, &do32, &qd_full[s], h * CH + kb * 64, i * AB_COLS, n);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_st = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
-      const uint32_t idesc_acc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
-                                 ((uint32_t)(AB_ROWS >> 4) << 24);
-      auto issue_st = [&](int i) {
-        const int s = i & 1;
-        mbar_wait(&qd_full[s], (uint32_t)(i >> 1) & 1);
-        tc_fence_after();
+    const uint32_t idesc_st = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AB_COLS >> 3) << 17) | ((uint32_t)(AB_ROWS >> 4) << 24);
+    const uint32_t idesc_acc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                               ((uint32_t)(AB_ROWS >> 4) << 24);
+    auto issue_st = [&](int i) {
+      const int s = i % AB_STAGES, b = i & 1;
+      mbar_wait(&qd_full[s], (uint32_t)(i / AB_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ts = tmem_st + (uint32_t)(b * 64), tdp = ts + 32;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t a = at_desc_kmajor<128>(smem_u32(sK + kb * ROW_TILE));
-          const uint64_t b = at_desc_kmajor<128>(smem_u32(sQ + s * QD_BYTES + kb * COL_TILE));
+          const uint64_t bd = at_desc_kmajor<128>(smem_u32(sQ + s * QD_BYTES + kb * COL_TILE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_st, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(ts, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
         }
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t a = at_desc_kmajor<128>(smem_u32(sV + kb * ROW_TILE));
-          const uint64_t b = at_desc_kmajor<128>(smem_u32(sdO + s * QD_BYTES + kb * COL_TILE));
+          const uint64_t bd = at_desc_kmajor<128>(smem_u32(sdO + s * QD_BYTES + kb * COL_TILE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_dpt, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(tdp, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_st, (kb | k) != 0);
         }
-        umma_commit(&st_ready);
-      };
-      mbar_wait(&kv_full, 0);
-      issue_st(0);
-      for (int i = 0; i < ni; ++i) {
-        const int s = i & 1;
-        mbar_wait(&pds_ready, (uint32_t)i & 1);
-        tc_fence_after();
-        const uint64_t ap = at_desc_kmajor<128>(smem_u32(sP));
-        const uint64_t ads = at_desc_kmajor<128>(smem_u32(sdS));
+        umma_commit(&st_ready[b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&kv_full, 0);
+    issue_st(0);
+    for (int i = 0; i < ni; ++i) {
+      const int s = i % AB_STAGES, b = i & 1;
+      if (i + 1 < ni) issue_st(i + 1);
+      mbar_wait(&pds_ready[b], (uint32_t)(i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ap = at_desc_kmajor<128>(smem_u32(sP)) + (uint64_t)(4 * b);
+        const uint64_t ads = at_desc_kmajor<128>(smem_u32(sdS)) + (uint64_t)(4 * b);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {             // 16 queries per MMA
+        for (int k = 0; k < 2; ++k) {             // 16 queries per MMA
           const uint64_t bdo = at_desc_mnmajor(smem_u32(sdO + s * QD_BYTES + k * 16 * 128), COL_TILE);
           umma_f16(tmem_dv, ap + (uint64_t)(2 * k), bdo, idesc_acc, (i | k) != 0);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 2; ++k) {
           const uint64_t bq = at_desc_mnmajor(smem_u32(sQ + s * QD_BYTES + k * 16 * 128), COL_TILE);
           umma_f16(tmem_dk, ads + (uint64_t)(2 * k), bq, idesc_acc, (i | k) != 0);
         }
         umma_commit(&qd_empty[s]);
-        if (i + 1 < ni) issue_st(i + 1);
-        else umma_commit(&acc_done);
       }
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(&acc_done);
+    __syncwarp();
   } else {
     const int lane_base = 32 * (warp & 3);
     const int r = lane_base + lane;               // key row
-    const int t = threadIdx.x - 64;               // 0..127: slot in sLD
+    const int half = (warp - 2) >> 2;             // which 16 of the tile's 32 query columns this warp owns
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
-    const long long col_base = ((long long)n * p.heads + h) * p.T;
-    auto fetch = [&](int i) -> float {            // this thread's entry of tile i's lse/delta staging
-      const int qq = i * AB_COLS + (t & 63);
-      if (qq >= p.T) return 0.f;
-      return t < 64 ? lse[col_base + qq] * AB_LOG2E : delta[col_base + qq];
-    };
-    sLD[0][t] = fetch(0);
-    named_bar_sync(1, 128);
     for (int i = 0; i < ni; ++i) {
-      const float nxt = i + 1 < ni ? fetch(i + 1) : 0.f;
-      const float* ld = sLD[i & 1];
-      mbar_wait(&st_ready, (uint32_t)i & 1);
-      tc_fence_after();
+      const int b = i & 1, s = i % AB_STAGES;
+      // the statistics of this query tile landed with its Q / dO tiles (same barrier): pull them into registers
+      // before waiting for the MMAs
+      mbar_wait(&qd_full[s], (uint32_t)(i / AB_STAGES) & 1);
+      float4 l4[4], d4[4];
 #pragma unroll
-      for (int c = 0; c < AB_COLS; c += 32) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32_async(tmem_st + lane_addr + (uint32_t)c, vs);
-        tmem_ld32_async(tmem_dpt + lane_addr + (uint32_t)c, vd);
-        tmem_wait_ld();
-        uint32_t pp[16], pd[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(ld + c + e);
-          const float4 d4 = *reinterpret_cast<const float4*>(ld + 64 + c + e);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -l4.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -l4.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(vs[e + 2]), p.scale_log2, -l4.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(vs[e + 3]), p.scale_log2, -l4.w));
-          pp[e >> 1] = pack_bf16x2(p0, p1);
-          pp[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-          pd[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - d4.x), p1 * (__uint_as_float(vd[e + 1]) - d4.y));
-          pd[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(vd[e + 2]) - d4.z), p3 * (__uint_as_float(vd[e + 3]) - d4.w));
-        }
-        store_row_chunk32(sP, r, c, pp);
-        store_row_chunk32(sdS, r, c, pd);
+      for (int e = 0; e < 4; ++e) {
+        l4[e] = *reinterpret_cast<const float4*>(&sLD[s][half * 16 + 4 * e]);
+        d4[e] = *reinterpret_cast<const float4*>(&sLD[s][32 + half * 16 + 4 * e]);
       }
+      mbar_wait(&st_ready[b], (uint32_t)(i >> 1) & 1);
+      tc_fence_after();
+      uint32_t vs[16], vd[16];
+      tmem_ld16_async(tmem_st + lane_addr + (uint32_t)(b * 64 + half * 16), vs);
+      tmem_ld16_async(tmem_st + lane_addr + (uint32_t)(b * 64 + 32 + half * 16), vd);
+      tmem_wait_ld();
+      uint32_t pp[8], pd[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 lq = l4[e >> 2], dq = d4[e >> 2];
+        const float p0 = ex2_approx(fmaf(__uint_as_float(vs[e]), p.scale_log2, -lq.x));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(vs[e + 1]), p.scale_log2, -lq.y));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(vs[e + 2]), p.scale_log2, -lq.z));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(vs[e + 3]), p.scale_log2, -lq.w));
+        pp[e >> 1] = pack_bf16x2(p0, p1);
+        pp[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+        pd[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[e]) - dq.x), p1 * (__uint_as_float(vd[e + 1]) - dq.y));
+        pd[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(vd[e + 2]) - dq.z), p3 * (__uint_as_float(vd[e + 3]) - dq.w));
+      }
+      store_row_chunk16(sP, r, b * 32 + half * 16, pp);
+      store_row_chunk16(sdS, r, b * 32 + half * 16, pd);
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&pds_ready);
-      sLD[(i + 1) & 1][t] = nxt;
-      named_bar_sync(1, 128);
+      mbar_arrive(&pds_ready[b]);
     }
     mbar_wait(&acc_done, 0);
     tc_fence_after();
@@ -375,7 +440,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
     bf16* krow = dqkv + ((long long)n * p.T + key) * (3 * p.C) + kc;
     bf16* vrow = dqkv + ((long long)n * p.T + key) * (3 * p.C) + vc;
 #pragma unroll 1
-    for (int c = 0; c < CH; c += 32) {
+    for (int c = half * (CH / 2); c < (half + 1) * (CH / 2); c += 32) {
       uint32_t v[32], w[32];
       tmem_ld32_async(tmem_dk + lane_addr + (uint32_t)c, v);
       tmem_ld32_async(tmem_dv + lane_addr + (uint32_t)c, w);
@@ -428,10 +493,10 @@ static int make_map(CUtensorMap* map, const void* base, int channels, int T, int
 }
 
 template <int CH>
-static int launch_attn_bwd_tc(const rho_attn_bwd_params* p, const AttnBwdTcParams& ap, const float* delta, cudaStream_t st) {
+static int launch_attn_bwd_tc(const rho_attn_bwd_params* p, const AttnBwdTcParams& ap, const float* ld, cudaStream_t st) {
   constexpr int KB = CH / 64;
-  constexpr size_t SMEM_DQ = (size_t)(2 * KB * 16384 + 4 * KB * 8192 + 16384) + 1024;
-  constexpr size_t SMEM_DKV = (size_t)(2 * KB * 16384 + 4 * KB * 8192 + 2 * 16384) + 1024;
+  constexpr size_t SMEM_DQ = (size_t)(2 * KB * 16384 + 2 * AB_STAGES * KB * 4096 + 16384) + 1024;
+  constexpr size_t SMEM_DKV = (size_t)(2 * KB * 16384 + 2 * AB_STAGES * KB * 4096 + 2 * 16384) + 1024;
   const rho_attn_params& f = p->fwd;
   auto kq = attn_bwd_dq_kernel<CH>;
   auto kkv = attn_bwd_dkv_kernel<CH>;
@@ -442,31 +507,43 @@ static int launch_attn_bwd_tc(const rho_attn_bwd_params* p, const AttnBwdTcParam
     if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  CUtensorMap qkv128, qkv64, do128, do64;
-  int rc = make_map(&qkv128, f.qkv, 3 * ap.C, f.T, f.N, 128);
-  if (!rc) rc = make_map(&qkv64, f.qkv, 3 * ap.C, f.T, f.N, 64);
-  if (!rc) rc = make_map(&do128, p->dout, ap.C, f.T, f.N, 128);
-  if (!rc) rc = make_map(&do64, p->dout, ap.C, f.T, f.N, 64);
+  CUtensorMap qkv128, qkv32, do128, do32;
+  int rc = make_map(&qkv128, f.qkv, 3 * ap.C, f.T, f.N, AB_ROWS);
+  if (!rc) rc = make_map(&qkv32, f.qkv, 3 * ap.C, f.T, f.N, AB_COLS);
+  if (!rc) rc = make_map(&do128, p->dout, ap.C, f.T, f.N, AB_ROWS);
+  if (!rc) rc = make_map(&do32, p->dout, ap.C, f.T, f.N, AB_COLS);
   if (rc) return rc;
   dim3 grid((unsigned)ceil_div(f.T, AB_ROWS), f.heads, f.N);
-  kq<<<grid, 192, SMEM_DQ, st>>>(qkv128, qkv64, do128, ap, f.lse, delta, (bf16*)p->dqkv);
+  kq<<<grid, AB_THREADS, SMEM_DQ, st>>>(qkv128, qkv32, do128, ap, ld, (bf16*)p->dqkv);
   RHO_CHECK_LAUNCH("attention_bwd_dq_tcgen05");
-  kkv<<<grid, 192, SMEM_DKV, st>>>(qkv128, qkv64, do64, ap, f.lse, delta, (bf16*)p->dqkv);
+  kkv<<<grid, AB_THREADS, SMEM_DKV, st>>>(qkv128, qkv32, do32, ap, ld, (bf16*)p->dqkv);
   RHO_CHECK_LAUNCH("attention_bwd_dkv_tcgen05");
   return RHO_OK;
 }
 
-// delta must already hold rowsum(dO o O) as [N, heads, T] fp32
-int attention_bwd_tc(const rho_attn_bwd_params* p, const float* delta, cudaStream_t st) {
+size_t attention_bwd_tc_workspace(const rho_attn_bwd_params* p) {
   const rho_attn_params& f = p->fwd;
+  return (size_t)f.N * f.heads * ((f.T + 31) / 32) * 64 * sizeof(float);
+}
+
+int attention_bwd_tc(const rho_attn_bwd_params* p, cudaStream_t st) {
+  const rho_attn_params& f = p->fwd;
+  float* ld = (float*)p->workspace;
+  {
+    const int tiles = (f.T + 31) / 32;
+    const long long total = (long long)f.N * f.heads * tiles * 32;
+    attn_bwd_stats_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const bf16*)f.out, (const bf16*)p->dout, f.lse, ld, f.T, f.heads,
+                                                                         f.ch, tiles, total);
+    RHO_CHECK_LAUNCH("attention_bwd_stats");
+  }
   AttnBwdTcParams ap;
   ap.T = f.T; ap.heads = f.heads; ap.C = f.heads * f.ch;
   if (f.order == 0) { ap.q_col = 0; ap.k_col = f.ch; ap.v_col = 2 * f.ch; ap.head_stride = 3 * f.ch; }
   else { ap.q_col = 0; ap.k_col = ap.C; ap.v_col = 2 * ap.C; ap.head_stride = f.ch; }
   ap.scale = 1.0f / sqrtf((float)f.ch);
   ap.scale_log2 = ap.scale * AB_LOG2E;
-  if (f.ch == 64) return launch_attn_bwd_tc<64>(p, ap, delta, st);
-  return launch_attn_bwd_tc<128>(p, ap, delta, st);
+  if (f.ch == 64) return launch_attn_bwd_tc<64>(p, ap, ld, st);
+  return launch_attn_bwd_tc<128>(p, ap, ld, st);
 }
 
 }  // namespace rho

@@ -368,18 +368,19 @@ static int attn_fwd_t(const rho_attn_params* p, cudaStream_t st) {
 
 // attention_bwd_tc.cu
 bool attention_bwd_tc_supported(const rho_attn_bwd_params* p);
-int attention_bwd_tc(const rho_attn_bwd_params* p, const float* delta, cudaStream_t st);
+int attention_bwd_tc(const rho_attn_bwd_params* p, cudaStream_t st);
+size_t attention_bwd_tc_workspace(const rho_attn_bwd_params* p);
 
 template <typename T>
 static int attn_bwd_t(const rho_attn_bwd_params* p, cudaStream_t st) {
   const rho_attn_params& f = p->fwd;
   const float scale2 = 1.0f / sqrtf((float)f.ch);
   const int ch = f.ch;
+  if (attention_bwd_tc_supported(p)) return attention_bwd_tc(p, st);   // bf16, head dim 64 / 128: tcgen05
   float* delta = (float*)p->workspace;
   long long total = (long long)f.N * f.heads * f.T;
   attn_bwd_delta_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const T*)f.out, (const T*)p->dout, delta, f.T, f.heads, ch, total);
   RHO_CHECK_LAUNCH("attention_bwd_delta");
-  if (attention_bwd_tc_supported(p)) return attention_bwd_tc(p, delta, st);   // bf16, head dim 64 / 128: tcgen05
 #define RHO_AB(TS, CJ)                                                                                                   \
   do {                                                                                                                   \
     size_t smem = ((size_t)4 * TS * (ch + 4) + (size_t)2 * TS * (TS + 4) + 2 * TS) * sizeof(float);                      \
@@ -425,7 +426,9 @@ int rho_attention_fwd(const rho_attn_params* p, rho_stream_t stream) {
 
 size_t rho_attention_bwd_workspace_bytes(const rho_attn_bwd_params* p) {
   if (!p) return 0;
-  return (size_t)p->fwd.N * p->fwd.heads * p->fwd.T * sizeof(float);
+  const size_t simt = (size_t)p->fwd.N * p->fwd.heads * p->fwd.T * sizeof(float);
+  const size_t tc = attention_bwd_tc_workspace(p);
+  return simt > tc ? simt : tc;
 }
 
 int rho_attention_bwd(const rho_attn_bwd_params* p, rho_stream_t stream) {

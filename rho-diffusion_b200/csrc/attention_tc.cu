@@ -74,31 +74,40 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   const uint32_t tmem_s = tmem_base_s;          // S: columns [0, 64) and [64, 128)
   const uint32_t tmem_o = tmem_base_s + 128;    // O: columns [128, 128 + CH)
 
+  // Producer and issuer warps keep warp-uniform control flow (all lanes wait on the barriers); only the asynchronous
+  // instructions are issued by one elected lane.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&q_full, Q_BYTES);
       for (int kb = 0; kb < KB; ++kb) tma_load_3d(sQ + kb * Q_TILE, &q_map, &q_full, qc + kb * 64, q0, n);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1;
+      mbar_wait(&k_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&k_full[s], KV_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_3d(sK + s * KV_BYTES + kb * KV_TILE, &kv_map, &k_full[s], kc + kb * 64, j * AT_BN, n);
-        mbar_wait(&v_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&v_full[s], KV_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_3d(sV + s * KV_BYTES + kb * KV_TILE, &kv_map, &v_full[s], vc + kb * 64, j * AT_BN, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptors: D fp32, A/B bf16, M = 128
-      const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(CH >> 3) << 17) |
-                                ((uint32_t)(AT_BM >> 4) << 24);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (uint32_t)(j >> 1) & 1);
-        tc_fence_after();
+    // instruction descriptors: D fp32, A/B bf16, M = 128
+    const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+    const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(CH >> 3) << 17) |
+                              ((uint32_t)(AT_BM >> 4) << 24);
+    auto issue_qk = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(&k_full[s], (uint32_t)(j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + kb * Q_TILE));
@@ -108,17 +117,20 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
         }
         umma_commit(&k_empty[s]);
         umma_commit(&s_ready[s]);
-      };
-      mbar_wait(&q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1;
-        // S buffer (j+1)&1 was last read for tile j-1, whose p_ready was awaited in the previous iteration
-        if (j + 1 < nt) issue_qk(j + 1);
-        mbar_wait(&p_ready[s], ph);               // P_j is in smem and the row owners are done reading S_j
-        mbar_wait(&v_full[s], ph);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1;
+      // S buffer (j+1)&1 was last read for tile j-1, whose p_ready was awaited in the previous iteration
+      if (j + 1 < nt) issue_qk(j + 1);
+      mbar_wait(&p_ready[s], ph);               // P_j is in smem and the row owners are done reading S_j
+      mbar_wait(&v_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t a = at_desc_kmajor<128>(smem_u32(sP + s * P_TILE));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {             // 16 keys per MMA: two 8-row K atoms = 2048 bytes of V
@@ -128,6 +140,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
         umma_commit(&v_empty[s]);
         umma_commit(&o_done);
       }
+      __syncwarp();
     }
   } else {
     // ===== softmax / correction / epilogue: thread <-> query row =====

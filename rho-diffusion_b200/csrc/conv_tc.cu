@@ -115,47 +115,50 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ===== TMA producer (one elected lane) =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
-        const TcTap tap = p.taps[t];
-        for (int kb = 0; kb < kb_per_tap; ++kb) {
-          const int c = kb * BLOCK_K;
-          const int src = c >= p.C1 ? 1 : 0;
-          const int cc = src ? c - p.C1 : c;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const TcTap tap = p.taps[t];
+      for (int kb = 0; kb < kb_per_tap; ++kb) {
+        const int c = kb * BLOCK_K;
+        const int src = c >= p.C1 ? 1 : 0;
+        const int cc = src ? c - p.C1 : c;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_5d(sa, &maps.a[tap.map][src], &full_bar[stage], cc, w0 + tap.dw, h0 + tap.dh, d0 + tap.dd, n0 + tap.dn);
           tma_load_2d(sa + A_BYTES, &maps.w, &full_bar[stage], tap.kofs + c, nb * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc<BLOCK_N>();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = umma_desc<ROW_BYTES>(sa);
-        const uint64_t bdesc = umma_desc<ROW_BYTES>(sa + A_BYTES);
+    // ===== MMA issuer: uniform loop, one elected lane issues =====
+    const uint32_t idesc = umma_idesc<BLOCK_N>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+      const uint64_t adesc = umma_desc<ROW_BYTES>(sa);
+      const uint64_t bdesc = umma_desc<ROW_BYTES>(sa + A_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
           umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&accum_bar);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(&accum_bar);
+    __syncwarp();
   } else {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w % 4) .. +31 =====
     const int et = threadIdx.x - 64;   // 0..127

@@ -83,17 +83,18 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t0; t < t1; ++t) {
-        const int cls = t % p.ncls;
-        int r = t / p.ncls;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int td = r % p.tiles_d; r /= p.tiles_d;
-        const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = r * p.bn;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // whole warp walks the loop (uniform control flow keeps coordinates in uniform registers); one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int cls = t % p.ncls;
+      int r = t / p.ncls;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      const int td = r % p.tiles_d; r /= p.tiles_d;
+      const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = r * p.bn;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
         uint8_t* sa = smem + stage * STAGE_BYTES;
 #pragma unroll
@@ -107,19 +108,20 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
           tma_load_5d(sa + A_BYTES + b * BOX, &maps.dy[cls], &full_bar[stage], cob * BN + b * 64, w0, h0, d0, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D fp32, A/B bf16, both MN-major, M = 128, N = BN
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 0; s < nsteps; ++s) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+    // D fp32, A/B bf16, both MN-major, M = 128, N = BN
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < nsteps; ++s) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {   // 16 positions per MMA: two 8-row atoms = 2048 bytes
           const uint64_t a = wg_desc_mn(sa + k * 2048, BOX);
@@ -127,10 +129,12 @@ __global__ void __launch_bounds__(192) conv_wgrad_tc_kernel(const __grid_constan
           umma_f16(tmem_base, a, b, idesc, (s | k) != 0);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&accum_bar);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(&accum_bar);
+    __syncwarp();
   } else {
     const int lane_base = 32 * (warp & 3);
     const int r = lane_base + lane;            // accumulator row: atom = r / 64, ci within block = r % 64
