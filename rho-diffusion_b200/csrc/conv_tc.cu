@@ -44,6 +44,7 @@ struct TcParams {
   int C1, C2;              // K channels per source
   int n_blocks;            // Cout / BLOCK_N
   int out_split;           // > 0: output channels >= out_split go to y2 (pitch Cout - out_split), else y (pitch out_split)
+  int tma_store;           // epilogue stages 64-channel chunks in shared memory and writes them with TMA tensor stores
   int ntaps;
   TcTap taps[TC_MAX_TAPS];
 };
@@ -51,6 +52,7 @@ struct TcParams {
 struct TcMaps {
   CUtensorMap a[TC_MAX_MAPS][2];
   CUtensorMap w;
+  CUtensorMap y[2];        // output view(s) of this launch (TMA-store epilogue): y, and y2 for a split output
 };
 
 // UMMA shared-memory matrix descriptor, K-major operand, swizzle = row bytes (128 / 64 / 32)
@@ -173,6 +175,53 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
     const long long pos = (((long long)gn * p.Do + (gd * p.os_d + p.oo_d)) * p.Ho + (gh * p.os_h + p.oo_h)) * p.Wo + (gw * p.os_w + p.oo_w);
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if constexpr (BLOCK_N >= 64 && sizeof(TOut) == 2) {
+      if (p.tma_store) {
+        // Every MMA has completed, so the operand ring is free: stage [128 rows x 64 ch] bf16 chunks there (128-byte
+        // swizzle, conflict-free 16-byte stores) and hand each chunk to one TMA tensor store (coalesced, clips the tile
+        // overhang, asynchronous).
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          uint8_t* rowp = smem + cc * (TC_BM * 128) + r * 128;
+          const int ch = nb * BLOCK_N + cc * 64;                       // first output channel of the chunk
+          const bf16* res = (residual && valid) ? residual + pos * p.Cout + ch : nullptr;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(cc * 64 + hh * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[cc * 64 + hh * 32 + j + e];
+              if (res) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(res + hh * 32 + j));
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+              }
+              uint4 w4;
+              __nv_bfloat162 h2;
+              h2 = __floats2bfloat162_rn(o[0], o[1]); w4.x = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
+              const int chunk = (hh * 4 + (j >> 3)) ^ (r & 7);
+              *reinterpret_cast<uint4*>(rowp + chunk * 16) = w4;
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            const bool second = p.out_split > 0 && ch >= p.out_split;
+            tma_store_5d(&maps.y[second ? 1 : 0], smem + cc * (TC_BM * 128), second ? ch - p.out_split : ch, w0, h0, d0, n0);
+            bulk_commit_group();
+          }
+        }
+        if (et == 0) bulk_wait_group_read0();     // shared memory must stay intact until the stores have read it
+        goto epilogue_done;
+      }
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t v[32];
@@ -199,6 +248,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
         }
       }
     }
+  epilogue_done:;
   }
   tc_fence_before();
   __syncthreads();
@@ -299,9 +349,32 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, c
   return RHO_OK;
 }
 
+// view of the output positions this launch writes: grid coordinate j <-> output index j * os + oo in every dim
+static int encode_out_map(CUtensorMap* m, void* base, int C, const TcParams& p) {
+  ActView v;
+  v.dim[0] = C; v.dim[1] = p.Gw; v.dim[2] = p.Gh; v.dim[3] = p.Gd; v.dim[4] = p.N;
+  const long long e = (long long)C * 2;
+  v.stride[0] = e * p.os_w; v.stride[1] = e * p.Wo * p.os_h; v.stride[2] = e * p.Wo * p.Ho * p.os_d; v.stride[3] = e * p.Wo * p.Ho * p.Do;
+  v.base = (char*)base + (((long long)p.oo_d * p.Ho + p.oo_h) * p.Wo + p.oo_w) * e;
+  const int box[5] = {64, p.bw, p.bh, p.bd, p.bn};
+  return encode_view(m, v, box, 64);
+}
+
 template <typename TOut>
-static int dispatch_tc(int bn, int bk, const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2,
+static int dispatch_tc(int bn, int bk, const TcMaps& maps_in, const TcParams& p_in, const float* bias, const bf16* residual, TOut* y, TOut* y2,
                        cudaStream_t st) {
+  TcMaps maps = maps_in;
+  TcParams p = p_in;
+  p.tma_store = 0;
+  static int tma_epi = -1;
+  if (tma_epi < 0) { const char* e = getenv("RHO_CONV_TMA_STORE"); tma_epi = (e && e[0] == '0') ? 0 : 1; }
+  const int c_first = p.out_split > 0 ? p.out_split : p.Cout;
+  if (tma_epi && sizeof(TOut) == 2 && bn >= 64 && c_first % 64 == 0 && (p.Cout - c_first) % 64 == 0 && (p.out_split == 0 || y2 != nullptr)) {
+    int rc = encode_out_map(&maps.y[0], y, c_first, p);
+    if (!rc && p.out_split > 0) rc = encode_out_map(&maps.y[1], y2, p.Cout - p.out_split, p);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
 #define RHO_TC(BN, BK) \
   if (bn == BN && bk == BK) return launch_tc<BN, BK, TOut>(maps, p, bias, residual, y, y2, st)
   RHO_TC(256, 64); RHO_TC(128, 64); RHO_TC(64, 64); RHO_TC(32, 64);
