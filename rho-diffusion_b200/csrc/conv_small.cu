@@ -255,6 +255,173 @@ __global__ void __launch_bounds__(256) conv_small_cin_row4_kernel(ConvGeom g, co
   }
 }
 
+
+// ---- run kernels (kw = 3, pad 1, unit stride): every thread owns a RUN of consecutive output positions along W so that
+// an input column loaded once feeds the three kw taps, and the weights of one (kd, kh) filter row sit in registers.
+// small-Cout: lane v of an L-lane group owns channel octet v (Cin = 8 L) for a run of 4 positions: per filter row
+// 6 x 16-byte loads and 96 FMAs per output channel; the L partial sums meet in log2(L) shuffles.
+template <int L, typename TO>
+__global__ void __launch_bounds__(256) conv_small_cout_run4_kernel(ConvGeom g, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                   const float* __restrict__ bias, TO* __restrict__ y) {
+  extern __shared__ __align__(16) float ws_dyn[];   // [co][tap*Cin + ci]
+  const int K = g.taps * g.Cin;
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) ws_dyn[i] = to_f32(w[i]);
+  __syncthreads();
+  const int v = threadIdx.x % L;
+  const long long run = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const bool valid = run < (g.M >> 2);
+  unsigned t = valid ? (unsigned)run : 0u;
+  const unsigned wq = (unsigned)g.Wo >> 2;
+  const int ow0 = (int)(t % wq) * 4; t /= wq;
+  const int oh = (int)(t % (unsigned)g.Ho); t /= (unsigned)g.Ho;
+  const int od = (int)(t % (unsigned)g.Do);
+  const int n = (int)(t / (unsigned)g.Do);
+  float acc[4][4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[co][q] = 0.f;
+  for (int kd = 0; kd < g.kd; ++kd) {
+    const int pd = od + kd - g.pd;
+    if (pd < 0 || pd >= g.D) continue;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int ph = oh + kh - g.ph;
+      if (ph < 0 || ph >= g.H) continue;
+      const bf16* row = x + ((((long long)n * g.D + pd) * g.H + ph) * g.W) * g.Cin + v * 8;
+      uint4 raw[6];
+#pragma unroll
+      for (int col = 0; col < 6; ++col) {
+        const int pw = ow0 + col - 1;
+        raw[col] = (pw >= 0 && pw < g.W) ? __ldg(reinterpret_cast<const uint4*>(row + (long long)pw * g.Cin)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float xv[6][8];
+#pragma unroll
+      for (int col = 0; col < 6; ++col) {
+        const uint32_t u[4] = {raw[col].x, raw[col].y, raw[col].z, raw[col].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xv[col][2 * j] = __uint_as_float(u[j] << 16); xv[col][2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u); }
+      }
+      const int k0 = ((kd * g.kh + kh) * 3) * g.Cin + v * 8;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (co < g.Cout) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws_dyn[co * K + k0 + kw * g.Cin]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&ws_dyn[co * K + k0 + kw * g.Cin + 4]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float* xx = xv[q + kw];
+              float a = acc[co][q];
+              a = fmaf(xx[0], w0.x, a); a = fmaf(xx[1], w0.y, a); a = fmaf(xx[2], w0.z, a); a = fmaf(xx[3], w0.w, a);
+              a = fmaf(xx[4], w1.x, a); a = fmaf(xx[5], w1.y, a); a = fmaf(xx[6], w1.z, a); a = fmaf(xx[7], w1.w, a);
+              acc[co][q] = a;
+            }
+          }
+        }
+      }
+    }
+  }
+  const long long m0 = run * 4;
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    if (co < g.Cout) {
+      const float b = bias ? bias[co] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float s = acc[co][q];
+#pragma unroll
+        for (int off = L >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (v == 0 && valid) y[(m0 + q) * g.Cout + co] = from_f32<TO>(s + b);
+      }
+    }
+  }
+}
+
+// small-Cin: a thread owns 8 output channels for a run of 8 positions; per filter row the 10 input columns and, per input
+// channel, the 3 x 8 weights are in registers: 6 shared-memory loads per 192 FMAs.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_small_cin_row8_kernel(ConvGeom g, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const float* __restrict__ bias, bf16* __restrict__ y, int flip) {
+  extern __shared__ __align__(16) float ws_dyn[];   // [tap*Cin + ci][Cout]
+  const int K = g.taps * CIN;
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) {
+    if (!flip) {
+      const int co = i / K, k = i % K;
+      ws_dyn[k * g.Cout + co] = to_f32(w[i]);
+    } else {
+      const int co = i % g.Cout, tap = (i / g.Cout) % g.taps, ci = i / (g.Cout * g.taps);   // w[ci][tap][co]
+      ws_dyn[((g.taps - 1 - tap) * CIN + ci) * g.Cout + co] = to_f32(w[i]);
+    }
+  }
+  __syncthreads();
+  const int groups = g.Cout >> 3;
+  const int wq = g.Wo >> 3;
+  const long long total = (g.M >> 3) * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % groups) * 8;
+  unsigned t = (unsigned)(idx / groups);
+  const int ow0 = (int)(t % (unsigned)wq) * 8; t /= (unsigned)wq;
+  const int oh = (int)(t % (unsigned)g.Ho); t /= (unsigned)g.Ho;
+  const int od = (int)(t % (unsigned)g.Do);
+  const int n = (int)(t / (unsigned)g.Do);
+  float acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float b = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q][j] = b;
+  }
+  for (int kd = 0; kd < g.kd; ++kd) {
+    const int pd = od + kd - g.pd;
+    if (pd < 0 || pd >= g.D) continue;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int ph = oh + kh - g.ph;
+      if (ph < 0 || ph >= g.H) continue;
+      const bf16* row = x + ((((long long)n * g.D + pd) * g.H + ph) * g.W) * CIN;
+      float xv[10][CIN];
+#pragma unroll
+      for (int col = 0; col < 10; ++col) {
+        const int pw = ow0 + col - 1;
+        const bool ok = pw >= 0 && pw < g.W;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xv[col][ci] = ok ? to_f32(row[(long long)pw * CIN + ci]) : 0.f;
+      }
+      const int tap0 = (kd * g.kh + kh) * 3;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        float wr[3][8];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wp = &ws_dyn[((tap0 + kw) * CIN + ci) * g.Cout + c0];
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+          wr[kw][0] = w0.x; wr[kw][1] = w0.y; wr[kw][2] = w0.z; wr[kw][3] = w0.w;
+          wr[kw][4] = w1.x; wr[kw][5] = w1.y; wr[kw][6] = w1.z; wr[kw][7] = w1.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float xx = xv[q + kw][ci];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(xx, wr[kw][j], acc[q][j]);
+          }
+      }
+    }
+  }
+  const long long m0 = (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(acc[q][2 * j], acc[q][2 * j + 1]);
+    *reinterpret_cast<uint4*>(y + (m0 + q) * g.Cout + c0) = o;
+  }
+}
+
 bool conv_small_supported(const ConvGeom& g, const rho_conv_params* p) {
   if (p->residual || g.C2 != 0) return false;
   if ((long long)g.taps * g.Cin * g.Cout > SC_MAX_W) return false;
@@ -282,9 +449,22 @@ static int launch_small(const ConvGeom& g, const rho_conv_params* p, cudaStream_
 static bool small_fast_geom(const ConvGeom& g) {
   return g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1 && g.M < (1ll << 31);
 }
+static bool run_geom(const ConvGeom& g) { return g.kw == 3 && g.pw == 1 && (g.kh == 1 || g.ph == g.kh / 2) && (g.kd == 1 || g.pd == g.kd / 2); }
 template <typename TO>
 static int launch_small_cout_vec(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const int octets = g.Cin >> 3;
+  if (run_geom(g) && g.Wo % 4 == 0 && (octets == 4 || octets == 8 || octets == 16 || octets == 32)) {
+    const size_t smem_r = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
+    const unsigned blocks_r = (unsigned)ceil_div((g.M >> 2) * octets, 256);
+#define RHO_SCRUN(LL) conv_small_cout_run4_kernel<LL, TO><<<blocks_r, 256, smem_r, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (TO*)p->y)
+    if (octets == 4) RHO_SCRUN(4);
+    else if (octets == 8) RHO_SCRUN(8);
+    else if (octets == 16) RHO_SCRUN(16);
+    else RHO_SCRUN(32);
+#undef RHO_SCRUN
+    RHO_CHECK_LAUNCH("conv_small_cout_run4");
+    return RHO_OK;
+  }
   const int L = octets % 8 == 0 ? 8 : octets % 4 == 0 ? 4 : octets % 2 == 0 ? 2 : 1;
   const size_t smem = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
   const unsigned blocks = (unsigned)ceil_div(g.M * L, 256);
@@ -299,6 +479,19 @@ static int launch_small_cout_vec(const ConvGeom& g, const rho_conv_params* p, cu
 }
 static int launch_small_cin_row4(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const size_t smem = (size_t)g.taps * g.Cin * g.Cout * sizeof(float);
+  if (run_geom(g) && g.Wo % 8 == 0) {
+    const unsigned blocks8 = (unsigned)ceil_div((g.M >> 3) * (g.Cout >> 3), 256);
+#define RHO_SCR8(CI) conv_small_cin_row8_kernel<CI><<<blocks8, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (bf16*)p->y, 0)
+    switch (g.Cin) {
+      case 1: RHO_SCR8(1); break;
+      case 2: RHO_SCR8(2); break;
+      case 3: RHO_SCR8(3); break;
+      default: RHO_SCR8(4); break;
+    }
+#undef RHO_SCR8
+    RHO_CHECK_LAUNCH("conv_small_cin_row8");
+    return RHO_OK;
+  }
   const unsigned blocks = (unsigned)ceil_div((g.M >> 2) * (g.Cout >> 3), 256);
 #define RHO_SCR(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(g, (const bf16*)p->x, (const bf16*)p->w_packed, p->bias, (bf16*)p->y, 0)
   switch (g.Cin) {
@@ -467,6 +660,19 @@ int conv_small_dgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream
   d.Cin = g.Cout; d.C1 = g.Cout; d.Cout = g.Cin;
   d.Ktot = d.taps * d.Cin;
   const size_t smem = (size_t)d.taps * d.Cin * d.Cout * sizeof(float);
+  if (run_geom(d) && d.Wo % 8 == 0) {
+    const unsigned blocks8 = (unsigned)ceil_div((d.M >> 3) * (d.Cout >> 3), 256);
+#define RHO_SCD8(CI) conv_small_cin_row8_kernel<CI><<<blocks8, 256, smem, st>>>(d, (const bf16*)p->dy, (const bf16*)p->fwd.w_packed, nullptr, (bf16*)p->dx, 1)
+    switch (d.Cin) {
+      case 1: RHO_SCD8(1); break;
+      case 2: RHO_SCD8(2); break;
+      case 3: RHO_SCD8(3); break;
+      default: RHO_SCD8(4); break;
+    }
+#undef RHO_SCD8
+    RHO_CHECK_LAUNCH("conv_small_dgrad8");
+    return RHO_OK;
+  }
   const unsigned blocks = (unsigned)ceil_div((d.M >> 2) * (d.Cout >> 3), 256);
 #define RHO_SCD(CI) conv_small_cin_row4_kernel<CI><<<blocks, 256, smem, st>>>(d, (const bf16*)p->dy, (const bf16*)p->fwd.w_packed, nullptr, (bf16*)p->dx, 1)
   switch (d.Cin) {

@@ -141,6 +141,12 @@ CONV_CASES = [
     (2, 1, 128, 0, 64, (5, 6), 3, 1, 2, False),                # Upsample 2-D (4 output-parity classes)
     (1, 2, 64, 0, 64, (19,), 3, 1, 2, False),                  # Upsample 1-D (2 classes)
     (3, 1, 256, 0, 256, (2, 4, 8), 3, 1, (1, 2, 2), False),    # Upsample 3-D, two ci blocks per tap
+    # run kernels of the degenerate first / last convs (runs of 8 resp. 4 positions along W)
+    (3, 2, 64, 0, 1, (4, 6, 12), 3, 1, 1, False),              # last conv of the 3-D configs (Cout = 1, 8 channel octets)
+    (3, 2, 2, 0, 64, (3, 5, 16), 3, 1, 1, False),              # first conv, two input channels
+    (1, 2, 1, 0, 64, (40,), 3, 1, 1, False),                   # first conv 1-D
+    (1, 3, 128, 0, 2, (20,), 3, 1, 1, False),                  # last conv 1-D, 16 octets, two output channels
+    (2, 2, 256, 0, 1, (6, 8), 3, 1, 1, False),                 # last conv 2-D, 32 octets
 ]
 
 
