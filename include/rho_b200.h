@@ -285,6 +285,46 @@ int rho_adamw_ema_step(const rho_adamw_params* p, rho_stream_t stream);
 /* stand-alone ExponentialMovingAverage.update for one tensor (ema.py:52-57): shadow -= one_minus_decay * (shadow - p) */
 int rho_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, rho_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GaussianDiffusionPipeline (rho_diffusion/diffusion/gaussian_diffusion.py): the x0-prediction pipeline that
+ * scripts/inference.py:122-176 drives (cosine schedule, FIXED_LARGE variance, dynamic thresholding, DDIM eta = 0).
+ *   rho_lincomb2      out = ca[t_n] * a + cb[t_n] * b per sample: q_sample (gaussian_diffusion.py:294-312) with the
+ *                     reference's float64-built sqrt_alphas_cumprod / sqrt_one_minus_alphas_cumprod tables cast to fp32
+ *                     (_extract_into_tensor, :91-104)
+ *   rho_abs_quantile  out[n] = max(floor_value, torch.quantile(|x[n, :]|, q)) with torch's linear interpolation
+ *                     between the order statistics k_lo = floor(q (P-1)) and k_hi = ceil(q (P-1)), weight = frac
+ *                     (process_xstart, :400-408).  Exact radix selection on the bit patterns, no sort.
+ *   rho_x0_step       one sampling update for a model that predicts x0 (:338-443):
+ *                       pred = thresh ? clamp(model_out, -s_n, s_n) / s_n : model_out
+ *                       mode 0, ddim_sample (:654-702): eps = (sqrt_recip_abar x - pred) / sqrt_recipm1_abar,
+ *                               sigma = eta sqrt((1-abar_prev)/(1-abar)) sqrt(1 - abar/abar_prev),
+ *                               x <- pred sqrt(abar_prev) + sqrt(1 - abar_prev - sigma^2) eps + [t != 0] sigma noise
+ *                       mode 1, p_sample (:512-556):  x <- coef1 pred + coef2 x + [t != 0] exp(0.5 logvar) noise
+ *                     t comes per sample from `t` or, for graph replay, from the device scalar `t_scalar`. */
+int rho_lincomb2(const float* a, const float* b, const int64_t* t, const float* ca, const float* cb, int32_t T,
+                 int32_t N, int64_t per_sample, float* out, rho_stream_t stream);
+size_t rho_abs_quantile_workspace_bytes(int32_t N);
+int rho_abs_quantile(const float* x, int32_t N, int64_t per_sample, int64_t k_lo, int64_t k_hi, float weight,
+                     float floor_value, float* out, void* workspace, size_t workspace_bytes, rho_stream_t stream);
+typedef struct rho_x0_step_params {
+  const void* model_out;     /* [N, per_sample] model prediction of x0, NC[D]HW order */
+  int32_t model_dtype;       /* RHO_F32 | RHO_BF16 */
+  int32_t mode;              /* 0 = DDIM, 1 = ancestral posterior */
+  float* x;                  /* in/out x_t -> x_{t-1}, fp32 */
+  const float* noise;        /* optional: NULL drops the noise term (mode 0 with eta == 0; mode 1 => the posterior mean) */
+  float* pred_xstart;        /* optional output */
+  const float* thresh;       /* [N] dynamic threshold s_n >= 1, or NULL for no clipping */
+  const int64_t* t;          /* [N] per-sample step, or NULL */
+  const int64_t* t_scalar;   /* device scalar step (takes precedence), or NULL */
+  int32_t T, N;
+  int64_t per_sample;
+  float eta;
+  const float* alphas_cumprod; const float* alphas_cumprod_prev;
+  const float* sqrt_recip_alphas_cumprod; const float* sqrt_recipm1_alphas_cumprod;       /* mode 0 */
+  const float* posterior_mean_coef1; const float* posterior_mean_coef2; const float* model_log_variance; /* mode 1 */
+} rho_x0_step_params;
+int rho_x0_step(const rho_x0_step_params* p, rho_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

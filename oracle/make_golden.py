@@ -206,14 +206,94 @@ def gen_ddpm(ref):
           "denoised mean", float(d["reverse"]["denoised"].mean()))
 
 
+def gen_gaussian(ref):
+    """GaussianDiffusionPipeline (x0-prediction, cosine tables, dynamic thresholding, DDIM eta = 0) on the film3d UNet:
+    tables, q_sample, p_mean_variance / p_sample / ddim_sample on fixed inputs, the 20-step generate loop and the
+    double-noising training loss, with every RNG draw recorded."""
+    case = "film3d"
+    spec = UNET_CASES[case]
+    kwargs = dict(spec["kwargs"])
+    T = 20
+    sched = ref.schedule.LinearSchedule(T, 1e-3, 0.02)   # ignored by the pipeline (it builds its own cosine tables)
+    pipe = ref.GaussianDiffusionPipeline(ref.UNet, kwargs, sched, "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4})
+    manifest = {k: tuple(v.shape) for k, v in pipe.backbone.state_dict().items()}
+    pipe.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+    pipe.eval()
+    x0 = synth_input("gauss.x0", spec["x_shape"], kind="rand") * 2 - 1
+    y = synth_input(case + ".y", (spec["x_shape"][0], 4 * kwargs["model_channels"]), kind="rand")
+    d = {"T": T, "manifest": manifest}
+    d["tables"] = {k: torch.from_numpy(getattr(pipe, k).copy()) for k in
+                   ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                    "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+                    "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")}
+    rec = {"randn": [], "randint": []}
+    real_randn_like, real_randint = torch.randn_like, torch.randint
+
+    def randn_like(x, *a, **k):
+        r = real_randn_like(x, *a, **k)
+        rec["randn"].append(r.clone())
+        return r
+
+    def randint(*a, **k):
+        r = real_randint(*a, **k)
+        rec["randint"].append(r.clone())
+        return r
+
+    torch.randn_like, torch.randint = randn_like, randint
+    try:
+        torch.manual_seed(21516)
+        t = torch.tensor([3, 17])
+        x_t, noise = pipe.forward_process(x0, t)
+        d["q_sample"] = {"t": t, "noise": noise.clone(), "x_t": x_t.clone()}
+        # fixed "model": a scaled copy of the input so that the dynamic threshold is active (|x| quantile > 1)
+        fake = synth_input("gauss.model_out", spec["x_shape"]) * 1.7
+        with torch.no_grad():
+            pmv = pipe.p_mean_variance(lambda x, t, **kw: fake, x_t, t, clip_denoised=True)
+            d["p_mean_variance"] = {k: v.clone() for k, v in pmv.items()}
+            rec["randn"].clear()
+            ps = pipe.p_sample(lambda x, t, **kw: fake, x_t, t)
+            d["p_sample"] = {"noise": rec["randn"][0].clone(), "sample": ps["sample"].clone()}
+            t0 = torch.tensor([0, 5])
+            rec["randn"].clear()
+            ps0 = pipe.p_sample(lambda x, t, **kw: fake, x_t, t0)
+            d["p_sample_t0"] = {"t": t0, "noise": rec["randn"][0].clone(), "sample": ps0["sample"].clone()}
+            dd = pipe.ddim_sample(lambda x, t, **kw: fake, x_t, t)
+            d["ddim_sample"] = {"sample": dd["sample"].clone(), "pred_xstart": dd["pred_xstart"].clone()}
+            d["fake_scale"] = 1.7
+        # training step (double noising quirk), conditional
+        rec["randn"].clear(); rec["randint"].clear()
+        pipe.train()
+        loss = pipe.training_step([x0, y])
+        d["train"] = {"t_idx": rec["randint"][0].clone(), "noise": rec["randn"][0].clone(), "loss": loss.detach().clone()}
+        pipe.zero_grad()
+        loss.backward()
+        d["train"]["grad_stats"] = {n: torch.stack([p.grad.double().norm(), p.grad.double().sum()]).float()
+                                    for n, p in pipe.backbone.named_parameters() if p.grad is not None}
+        pipe.eval()
+        # generate loop (DDIM eta = 0): only the initial draw matters
+        rec["randn"].clear()
+        torch.manual_seed(4242)
+        res = pipe.reverse_process(torch.zeros(spec["x_shape"]), conditions=y, t_checkpoints=None)
+        d["reverse"] = {"x_init": rec["randn"][0].clone(), "denoised": res["denoised"].clone()}
+    finally:
+        torch.randn_like, torch.randint = real_randn_like, real_randint
+    torch.save(d, os.path.join(OUT, "gaussian_film3d.pt"))
+    print("gaussian loss", float(d["train"]["loss"]), "denoised mean/std", float(d["reverse"]["denoised"].mean()),
+          float(d["reverse"]["denoised"].std()))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "gaussian":     # regenerate one fixture only
+        gen_gaussian(ref)
+        return
     gen_schedule(ref)
     gen_embeddings(ref)
     gen_unet(ref)
     gen_ddpm(ref)
+    gen_gaussian(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -104,6 +104,8 @@ def load():
     ns.utils = importlib.import_module("rho_diffusion.utils")
     ns.ddpm = importlib.import_module("rho_diffusion.diffusion.ddpm")
     ns.ema = importlib.import_module("rho_diffusion.ema")
+    ns.gaussian = importlib.import_module("rho_diffusion.diffusion.gaussian_diffusion")
+    ns.GaussianDiffusionPipeline = ns.gaussian.GaussianDiffusionPipeline
     ns.UNet = ns.unet_v2.UNet
     ns.DDPM = ns.ddpm.DDPM
     ns.MultiEmbeddings = ns.conditioning.MultiEmbeddings

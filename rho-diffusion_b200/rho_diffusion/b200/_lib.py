@@ -90,6 +90,16 @@ class AdamWParams(C.Structure):
     ]
 
 
+class X0StepParams(C.Structure):
+    _fields_ = [
+        ("model_out", c_vp), ("model_dtype", c_i32), ("mode", c_i32), ("x", c_vp), ("noise", c_vp), ("pred_xstart", c_vp),
+        ("thresh", c_vp), ("t", c_vp), ("t_scalar", c_vp), ("T", c_i32), ("N", c_i32), ("per_sample", c_i64), ("eta", c_f32),
+        ("alphas_cumprod", c_vp), ("alphas_cumprod_prev", c_vp), ("sqrt_recip_alphas_cumprod", c_vp),
+        ("sqrt_recipm1_alphas_cumprod", c_vp), ("posterior_mean_coef1", c_vp), ("posterior_mean_coef2", c_vp),
+        ("model_log_variance", c_vp),
+    ]
+
+
 P = C.POINTER
 # name -> (restype, argtypes); every symbol declared in include/rho_b200.h
 SIGNATURES = {
@@ -132,6 +142,10 @@ SIGNATURES = {
     "rho_mse_loss": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp]),
     "rho_adamw_ema_step": (C.c_int, [P(AdamWParams), c_vp]),
     "rho_ema_update": (C.c_int, [c_vp, c_vp, c_i64, c_f32, c_vp]),
+    "rho_lincomb2": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    "rho_abs_quantile_workspace_bytes": (c_sz, [c_i32]),
+    "rho_abs_quantile": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),
+    "rho_x0_step": (C.c_int, [P(X0StepParams), c_vp]),
 }
 
 _lib = None

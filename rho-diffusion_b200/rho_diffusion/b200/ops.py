@@ -660,3 +660,59 @@ def ema_update(shadow: torch.Tensor, p: torch.Tensor, one_minus_decay: float) ->
     _need_cuda(shadow, p)
     assert shadow.is_contiguous() and p.is_contiguous() and shadow.dtype == torch.float32 and p.dtype == torch.float32
     L.check(L.lib().rho_ema_update(shadow.data_ptr(), p.data_ptr(), shadow.numel(), one_minus_decay, stream()), "ema_update")
+
+
+# ------------------------------------------------------------------------------------------------
+# GaussianDiffusionPipeline step kernels (gaussian_diffusion.py)
+# ------------------------------------------------------------------------------------------------
+def lincomb2(a, b, t, ca, cb):
+    """out[n] = ca[t_n] * a[n] + cb[t_n] * b[n]  (q_sample / posterior mean with fp32 coefficient tables)."""
+    _need_cuda(a, b, t, ca, cb)
+    a = a.float().contiguous()
+    b = b.float().contiguous()
+    t = t.to(torch.int64).contiguous()
+    out = torch.empty_like(a)
+    N = a.shape[0]
+    L.check(L.lib().rho_lincomb2(a.data_ptr(), b.data_ptr(), t.data_ptr(), ca.data_ptr(), cb.data_ptr(), ca.numel(), N, a.numel() // N,
+                                 out.data_ptr(), stream()), "lincomb2")
+    return out
+
+
+def quantile_ranks(per_sample: int, q: float):
+    """torch.quantile's interpolation position, evaluated in float32 like ATen does (rank = q * (n - 1))."""
+    pos = torch.tensor(q, dtype=torch.float32) * (per_sample - 1)
+    lo = torch.floor(pos)
+    k_lo = int(lo)
+    k_hi = int(torch.ceil(pos))
+    return k_lo, min(k_hi, per_sample - 1), float(pos - lo)
+
+
+def abs_quantile(x, q: float, floor_value: float = float("-inf"), out=None):
+    """out[n] = max(floor_value, quantile_q(|x[n]|)) with torch.quantile's linear interpolation (process_xstart)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N = x.shape[0]
+    per = x.numel() // N
+    k_lo, k_hi, w = quantile_ranks(per, q)
+    if out is None:
+        out = torch.empty((N,), dtype=torch.float32, device=x.device)
+    ws = workspace(L.lib().rho_abs_quantile_workspace_bytes(N), x.device)
+    L.check(L.lib().rho_abs_quantile(x.data_ptr(), N, per, k_lo, k_hi, w, floor_value, out.data_ptr(), ws.data_ptr(), ws.numel(), stream()),
+            "abs_quantile")
+    return out
+
+
+def x0_step(model_out, x, tables: dict, mode: int, t=None, t_scalar=None, thresh=None, noise=None, eta: float = 0.0, pred_xstart=None):
+    """In-place x_t -> x_{t-1} for an x0-predicting model: mode 0 = ddim_sample, mode 1 = p_sample (see rho_b200.h)."""
+    _need_cuda(model_out, x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and model_out.is_contiguous()
+    p = L.X0StepParams()
+    p.model_out, p.model_dtype, p.mode = model_out.data_ptr(), dt(model_out), mode
+    p.x, p.noise, p.pred_xstart, p.thresh = x.data_ptr(), ptr(noise), ptr(pred_xstart), ptr(thresh)
+    p.t, p.t_scalar = ptr(t), ptr(t_scalar)
+    p.T, p.N, p.per_sample, p.eta = tables["alphas_cumprod"].numel(), x.shape[0], x.numel() // x.shape[0], eta
+    for k in ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+              "posterior_mean_coef1", "posterior_mean_coef2", "model_log_variance"):
+        setattr(p, k, tables[k].data_ptr())
+    L.check(L.lib().rho_x0_step(C.byref(p), stream()), "x0_step")
+    return x

@@ -90,3 +90,71 @@ class AncestralSampler:
                 buffer[:, idx].copy_(self.x)
                 idx += 1
         return {"buffer": buffer, "denoised": self.x.clone()}
+
+
+class X0Sampler:
+    """DDIM (eta = 0) loop of GaussianDiffusionPipeline.reverse_process (gaussian_diffusion.py:1029-1099) for an
+    x0-predicting backbone: one graph = UNet eval + per-sample |x0| quantile (dynamic threshold) + fused DDIM update +
+    timestep decrement.  With eta = 0 the trajectory is a deterministic function of x_T."""
+
+    def __init__(self, backbone, shape, device, tables, percentile=0.9, cond_example=None, use_cuda_graph=True, eta=0.0):
+        assert eta == 0.0, "the reference's reverse_process calls ddim_sample with its default eta = 0"
+        self.backbone = backbone
+        self.shape = tuple(shape)
+        self.device = device
+        self.tables = tables
+        self.T = int(tables["alphas_cumprod"].numel())
+        self.percentile = percentile
+        self.use_graph = bool(use_cuda_graph)
+        self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
+        self.tt = torch.zeros((self.shape[0],), dtype=torch.int64, device=device)
+        self.t_scalar = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.thresh = torch.ones((self.shape[0],), dtype=torch.float32, device=device)
+        self.cond = cond_example.clone() if cond_example is not None else None
+        self.graph = None
+
+    def _step(self):
+        out = self.backbone(self.x, self.tt, self.cond) if self.cond is not None else self.backbone(self.x, self.tt)
+        out = out.float().contiguous()
+        ops.abs_quantile(out, self.percentile, floor_value=1.0, out=self.thresh)
+        ops.x0_step(out, self.x, self.tables, mode=0, t_scalar=self.t_scalar, thresh=self.thresh)
+        ops.advance_timestep(self.t_scalar, self.tt)
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.t_scalar.fill_(1)
+            self.tt.fill_(1)
+            self._step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        self.t_scalar.fill_(1)
+        self.tt.fill_(1)
+        with torch.cuda.graph(g):
+            self._step()
+        self.graph = g
+
+    def run(self, x_init, cond=None, t_checkpoints=None, num_steps=None):
+        T = self.T if num_steps is None else int(num_steps)
+        if self.use_graph and self.graph is None:
+            self._capture()
+        self.x.copy_(x_init.reshape(self.shape).to(torch.float32))
+        if self.cond is not None:
+            self.cond.copy_(cond)
+        self.tt.fill_(T - 1)
+        self.t_scalar.fill_(T - 1)
+        buffer, n_ckpt, idx = None, 0, 0
+        if t_checkpoints is not None:
+            n_ckpt = len(t_checkpoints)
+            buffer = torch.zeros((self.shape[0], n_ckpt, *self.shape[1:]), dtype=torch.float32, device=self.device)
+        per_ckpt = T // n_ckpt if n_ckpt else T          # gaussian_diffusion.py:1048
+        for t in range(T - 1, -1, -1):
+            if self.use_graph:
+                self.graph.replay()
+            else:
+                self._step()
+            if buffer is not None and t % per_ckpt == 0 and idx < n_ckpt:
+                buffer[:, idx].copy_(self.x)
+                idx += 1
+        return {"buffer": buffer, "denoised": self.x.clone()}
