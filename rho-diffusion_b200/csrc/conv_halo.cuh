@@ -1,0 +1,331 @@
+// Halo-reuse variant of the tcgen05 implicit-GEMM conv (included by conv_tc.cu) for the layers whose per-tap operand
+// reloads make the generic kernel L2 -> shared-memory bound: stride-1 3x3(x3) convs with Cout <= 128 on wide planes
+// (the 64^3 and 32x32x64 levels of the 3-D UNet: 128 output positions x 64 channels need 27 x 24 KB of TMA traffic per
+// 28 MFLOP tile there, which caps the generic kernel at ~635 TFLOP/s).
+//
+// Idea: index one (n, d) plane by the PADDED-FLAT position q = h * Wp + (w + 1), Wp = W + 1 (one zero column shared by the
+// right edge of row h and the left edge of row h + 1).  In that index space every in-plane filter tap (dh, dw) is a pure
+// row shift by dh * Wp + dw.  So ONE TMA box load of rows [h_lo, h_lo + R) x columns [-1, W) x 64 channels per depth
+// slice (out-of-bounds rows / the w = -1 column are zero-filled by the TMA unit = "same" padding) serves all 9 in-plane
+// taps: the UMMA A descriptor simply starts (q0 + dh * Wp + dw - h_lo * Wp) rows into the slab.  A 128-byte-swizzled
+// K-major operand may start at any 128-byte row because the swizzle is a function of the absolute shared-memory address
+// (verified on sm_100a with tools/ubench/umma_shift.cu; base_offset stays 0).
+// One CTA owns MT consecutive 128-position tiles (MT accumulators in TMEM), so a weight tile is loaded once per MT MMAs
+// groups and the slab halo (2 Wp + 2 rows) is amortised over MT * 128 rows: 4-5x less TMA traffic than per-tap loads.
+// The kernel is persistent (one CTA per SM, static round-robin over work items) with double-buffered TMEM accumulators,
+// so the epilogue of item i overlaps the MMAs of item i + 1.  Rows with q % Wp == 0 are the padding column: computed and
+// dropped (1 / Wp waste).
+#pragma once
+
+namespace rho {
+
+constexpr int HALO_MAX_STAGES = 8;
+
+struct HaloParams {
+  int N, D, H, W, Wp;
+  int C1, C2, Cin, Cout;
+  int kd, pd;                 // depth taps (1 or 3) and padding
+  int n_blocks;               // Cout / BLOCK_N
+  int tiles_per_plane, groups_per_plane;
+  long long total_items;
+  int R;                      // slab rows (h extent of the A box)
+  int a_stage_bytes;          // R * Wp * 128 rounded up to 1024
+  int SA, SB;                 // ring depths
+  int out_split;              // > 0: channels >= out_split go to y2 (dgrad of a concat input)
+};
+
+struct HaloMaps {
+  CUtensorMap a[2];
+  CUtensorMap w;
+};
+
+template <int BLOCK_N, int MT>
+__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
+                                                           const float* __restrict__ bias, const bf16* __restrict__ residual,
+                                                           bf16* __restrict__ y, bf16* __restrict__ y2) {
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr uint32_t TMEM_COLS = 2 * MT * BLOCK_N;
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.SA * p.a_stage_bytes;
+  __shared__ uint64_t a_full[HALO_MAX_STAGES], a_empty[HALO_MAX_STAGES], b_full[HALO_MAX_STAGES], b_empty[HALO_MAX_STAGES];
+  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.Cin >> 6;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // work item -> (output-channel block, tile group, plane)
+  auto decode = [&](long long item, int& nb, int& q0, int& mt_here, int& d, int& n, int& h_lo) {
+    nb = (int)(item % p.n_blocks);
+    long long g = item / p.n_blocks;
+    const int group = (int)(g % p.groups_per_plane);
+    const long long plane = g / p.groups_per_plane;
+    d = (int)(plane % p.D);
+    n = (int)(plane / p.D);
+    q0 = group * MT * 128;
+    mt_here = min(MT, p.tiles_per_plane - group * MT);
+    h_lo = (q0 + p.Wp - 1) / p.Wp - 2;         // floor((q0 - Wp - 1) / Wp) for q0 >= 0
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int nb, q0, mt_here, d, n, h_lo;
+      decode(item, nb, q0, mt_here, d, n, h_lo);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int c = kb * 64;
+        const int src = c >= p.C1 ? 1 : 0;
+        const int cc = src ? c - p.C1 : c;
+        for (int dd = 0; dd < p.kd; ++dd) {
+          mbar_wait(&a_empty[sa], pha ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[sa], (uint32_t)(p.R * p.Wp * 128));
+            tma_load_5d(sA + (size_t)sa * p.a_stage_bytes, &maps.a[src], &a_full[sa], cc, -1, h_lo, d + dd - p.pd, n);
+          }
+          __syncwarp();
+          if (++sa == p.SA) { sa = 0; pha ^= 1; }
+          for (int t9 = 0; t9 < 9; ++t9) {
+            mbar_wait(&b_empty[sb], phb ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[sb], B_BYTES);
+              tma_load_2d(sB + sb * B_BYTES, &maps.w, &b_full[sb], (dd * 9 + t9) * p.Cin + c, nb * BLOCK_N);
+            }
+            __syncwarp();
+            if (++sb == p.SB) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int sa = 0, sb = 0, ab = 0;
+    uint32_t pha = 0, phb = 0, phacc = 0;
+    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int nb, q0, mt_here, d, n, h_lo;
+      decode(item, nb, q0, mt_here, d, n, h_lo);
+      mbar_wait(&acc_empty[ab], phacc ^ 1);       // the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(ab * MT * BLOCK_N);
+      const int row_base = q0 - h_lo * p.Wp;
+      bool first = true;
+      for (int kb = 0; kb < KB; ++kb) {
+        for (int dd = 0; dd < p.kd; ++dd) {
+          mbar_wait(&a_full[sa], pha);
+          const uint32_t a_addr = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int shift = (t9 / 3 - 1) * p.Wp + (t9 % 3 - 1);
+            mbar_wait(&b_full[sb], phb);
+            tc_fence_after();
+            const uint64_t bdesc = at_desc_kmajor<128>(smem_u32(sB + sb * B_BYTES));
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) {
+                if (i < mt_here) {
+                  const uint64_t adesc = at_desc_kmajor<128>(a_addr + (uint32_t)(row_base + i * 128 + shift) * 128u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(tacc + (uint32_t)(i * BLOCK_N), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, !(first && k == 0));
+                }
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            first = false;
+            if (++sb == p.SB) { sb = 0; phb ^= 1; }
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == p.SA) { sa = 0; pha ^= 1; }
+        }
+      }
+      if (elect_one()) umma_commit(&acc_full[ab]);
+      __syncwarp();
+      if (++ab == 2) { ab = 0; phacc ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 =====
+    const int et = threadIdx.x - 64;
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    int ab = 0;
+    uint32_t phacc = 0;
+    int nb_loaded = -1;
+    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int nb, q0, mt_here, d, n, h_lo;
+      decode(item, nb, q0, mt_here, d, n, h_lo);
+      if (nb != nb_loaded) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < BLOCK_N; i += 128) sbias[i] = bias ? bias[nb * BLOCK_N + i] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        nb_loaded = nb;
+      }
+      mbar_wait(&acc_full[ab], phacc);
+      tc_fence_after();
+      const long long plane_pos = ((long long)n * p.D + d) * p.H * p.W;
+      for (int i = 0; i < mt_here; ++i) {
+        const int q = q0 + i * 128 + r;
+        const int h = q / p.Wp, wq = q - h * p.Wp;
+        const bool valid = wq != 0 && h < p.H;
+        const long long pos = plane_pos + (long long)h * p.W + (wq - 1);
+        const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((ab * MT + i) * BLOCK_N);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tsrc + (uint32_t)c0, v);
+          if (valid) {
+            const int ch = nb * BLOCK_N + c0;
+            bf16* dst;
+            if (p.out_split > 0 && ch >= p.out_split) dst = y2 + pos * (p.Cout - p.out_split) + (ch - p.out_split);
+            else dst = y + pos * (p.out_split > 0 ? p.out_split : p.Cout) + ch;
+            const bf16* res = residual ? residual + pos * p.Cout + ch : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[c0 + j + e];
+              if (res) {
+                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(res + j));
+                const uint32_t u[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+              }
+              uint4 w4;
+              __nv_bfloat162 h2;
+              h2 = __floats2bfloat162_rn(o[0], o[1]); w4.x = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
+              *reinterpret_cast<uint4*>(dst + j) = w4;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (++ab == 2) { ab = 0; phacc ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+struct HaloPlan {
+  bool ok;
+  int bn, mt;
+  HaloParams p;
+  size_t smem;
+};
+
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RHO_CONV_HALO"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+// Cin = K channels (C1 + C2, each a multiple of 64), Cout = output channels of this launch
+static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, int kd, int kh, int kw) {
+  HaloPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (halo_mode() == 0 || tc_disabled()) return pl;
+  if (kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return pl;
+  if (C1 % 64 != 0 || C2 % 64 != 0 || (Cout != 64 && Cout != 128)) return pl;
+  if (W < 16 || W > 255 || (long long)H * (W + 1) < 256) return pl;
+  pl.bn = Cout;
+  pl.mt = Cout == 64 ? 4 : 2;
+  HaloParams& p = pl.p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Wp = W + 1;
+  p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
+  p.kd = kd; p.pd = kd / 2;
+  p.n_blocks = 1;
+  p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
+  p.groups_per_plane = (int)ceil_div(p.tiles_per_plane, pl.mt);
+  p.total_items = (long long)N * D * p.groups_per_plane * p.n_blocks;
+  int R = 0;
+  for (int g = 0; g < p.groups_per_plane; ++g) {
+    const int q0 = g * pl.mt * 128;
+    const int h_lo = (q0 + p.Wp - 1) / p.Wp - 2;
+    const int last = q0 + pl.mt * 128 - 1 + p.Wp + 1;          // highest flat row any tap of the group touches
+    R = std::max(R, last / p.Wp - h_lo + 1);
+  }
+  if (R > 256) return pl;
+  p.R = R;
+  p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * 128, 1024);
+  const size_t budget = 227 * 1024 - 1024 /* static */ - 1024 /* alignment slack */ - 1024;
+  const size_t b_bytes = (size_t)pl.bn * 128;
+  p.SB = pl.bn == 64 ? 5 : 4;
+  long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
+  if (sa < 2) return pl;
+  p.SA = (int)std::min<long long>(sa, 3);
+  // spend what is left on a deeper weight ring
+  long long extra = ((long long)budget - (long long)p.SA * p.a_stage_bytes) / (long long)b_bytes;
+  p.SB = (int)std::min<long long>(HALO_MAX_STAGES, std::max<long long>(p.SB, extra));
+  pl.smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * b_bytes + 1024;
+  pl.ok = true;
+  return pl;
+}
+
+template <int BLOCK_N, int MT>
+static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bias, const bf16* residual, bf16* y, bf16* y2, cudaStream_t st) {
+  auto kern = conv_halo_kernel<BLOCK_N, MT>;
+  static size_t attr_bytes = 0;
+  if (pl.smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_halo: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
+    attr_bytes = pl.smem;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(pl.p.total_items, (long long)sm_count());
+  kern<<<grid, 192, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
+  RHO_CHECK_LAUNCH("conv_halo_tcgen05");
+  return RHO_OK;
+}
+
+// x / x2: channels-last [N, D, H, W, C1 / C2]; w: packed [Cout][taps][Cin] bf16 (taps in (kd, kh, kw) order)
+static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, const void* w, const float* bias, const bf16* residual, bf16* y,
+                         bf16* y2, int out_split, cudaStream_t st) {
+  HaloPlan pl = pl_in;
+  HaloParams& p = pl.p;
+  p.out_split = out_split;
+  HaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int box[5] = {64, p.Wp, p.R, 1, 1};
+  for (int s = 0; s < 2; ++s) {
+    const int C = s ? p.C2 : p.C1;
+    if (C == 0) continue;
+    ActView v;
+    v.base = s ? x2 : x;
+    v.dim[0] = C; v.dim[1] = p.W; v.dim[2] = p.H; v.dim[3] = p.D; v.dim[4] = p.N;
+    v.stride[0] = (long long)C * 2; v.stride[1] = v.stride[0] * p.W; v.stride[2] = v.stride[1] * p.H; v.stride[3] = v.stride[2] * p.D;
+    int rc = encode_view(&maps.a[s], v, box, 64);
+    if (rc) return rc;
+  }
+  int rc = encode_weight_map(&maps.w, w, (long long)p.kd * 9 * p.Cin, p.Cout, 64, pl.bn);
+  if (rc) return rc;
+  if (pl.bn == 64) return launch_halo<64, 4>(maps, pl, bias, residual, y, y2, st);
+  return launch_halo<128, 2>(maps, pl, bias, residual, y, y2, st);
+}
+
+}  // namespace rho

@@ -392,6 +392,10 @@ static bool tc_disabled() {
   return v == 1;
 }
 
+}  // namespace rho
+#include "conv_halo.cuh"
+namespace rho {
+
 // ---- decomposition plans --------------------------------------------------------------------------------
 // A fused nearest-x2 upsample turns the 3-tap filter of an upsampled dim into, per OUTPUT parity p, a 2-tap filter on
 // the un-upsampled input:  p = 0: {x[i-1]*w0, x[i]*(w1+w2)},  p = 1: {x[i]*(w0+w1), x[i+1]*w2}.  One launch per parity
@@ -570,6 +574,10 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
     return RHO_OK;
   }
 
+  if (is_plain(g)) {
+    const HaloPlan hp = halo_plan(g.N, g.D, g.H, g.W, g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw);
+    if (hp.ok) return conv_halo_run(hp, p->x, p->x2, p->w_packed, p->bias, (const bf16*)p->residual, (bf16*)p->y, nullptr, 0, st);
+  }
   tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
   pick_tile(tp);
   const int box[5] = {bk, tp.bw, tp.bh, tp.bd, tp.bn};
@@ -754,6 +762,11 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
         if (rc) return rc;
       }
     return RHO_OK;
+  }
+  if (!up) {
+    // plain stride-1 conv of dY with the flipped filter: the halo-reuse kernel takes it when the shape qualifies
+    const HaloPlan hp = halo_plan(g.N, g.Do, g.Ho, g.Wo, g.Cout, 0, g.Cin, g.kd, g.kh, g.kw);
+    if (hp.ok) return conv_halo_run(hp, p->dy, nullptr, wd, nullptr, nullptr, (bf16*)p->dx, (bf16*)p->dx2, tp.out_split, st);
   }
   pick_tile(tp);
   tp.ntaps = g.taps;

@@ -242,7 +242,7 @@ bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
   if (strided && ((g.sh == 2 && g.H < 2) || (g.sw == 2 && g.W < 2))) return false;   // an empty parity view cannot be encoded
   if (g.Cin % 64 != 0 || g.C1 % 64 != 0 || wg_block_n(g.Cout) == 0) return false;
   if (g.taps > 28) return false;
-  const int units = g.Cin >= 128 ? g.taps * (g.Cin / 128) : (g.taps + 1) / 2;
+  const int units = (g.taps * (g.Cin / 64) + 1) / 2;
   if (units > 256) return false;
   if (g.N > 32767 || g.D > 32767 || g.H > 32767 || g.W > 32767) return false;
   return get_encode() != nullptr;
@@ -287,17 +287,15 @@ static void wg_plan(const ConvGeom& g, WgParams& wp) {
       wp.off_d[t][cls] = (int8_t)ed; wp.off_h[t][cls] = (int8_t)dh; wp.off_w[t][cls] = (int8_t)dw;
     }
   }
+  // units = consecutive pairs of the (tap, 64-channel block) list: two ci blocks of one tap when the block count is even,
+  // the same block of two taps when Cin = 64, and pairs that straddle taps when the block count is odd (Cin = 192, 320, ...)
   int u = 0;
-  if (g.Cin >= 128) {
-    for (int t = 0; t < g.taps; ++t)
-      for (int cb = 0; cb < g.Cin / 128; ++cb, ++u) {
-        wp.unit_tap[0][u] = wp.unit_tap[1][u] = (int16_t)t;
-        wp.unit_cib[0][u] = (int16_t)(2 * cb); wp.unit_cib[1][u] = (int16_t)(2 * cb + 1);
-      }
-  } else {
-    for (int t = 0; t < g.taps; t += 2, ++u) {
-      wp.unit_tap[0][u] = (int16_t)t; wp.unit_tap[1][u] = (int16_t)std::min(t + 1, g.taps - 1);
-      wp.unit_cib[0][u] = wp.unit_cib[1][u] = 0;
+  {
+    const int nblk = g.Cin / 64, total = g.taps * nblk;
+    for (int i = 0; i < total; i += 2, ++u) {
+      const int j = std::min(i + 1, total - 1);        // odd total: the last unit duplicates its atom (skipped by the epilogue)
+      wp.unit_tap[0][u] = (int16_t)(i / nblk); wp.unit_cib[0][u] = (int16_t)(i % nblk);
+      wp.unit_tap[1][u] = (int16_t)(j / nblk); wp.unit_cib[1][u] = (int16_t)(j % nblk);
     }
   }
   wp.m_units = u;

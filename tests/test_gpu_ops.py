@@ -147,6 +147,24 @@ CONV_CASES = [
     (1, 2, 1, 0, 64, (40,), 3, 1, 1, False),                   # first conv 1-D
     (1, 3, 128, 0, 2, (20,), 3, 1, 1, False),                  # last conv 1-D, 16 octets, two output channels
     (2, 2, 256, 0, 1, (6, 8), 3, 1, 1, False),                 # last conv 2-D, 32 octets
+    # halo-reuse tcgen05 kernel (stride-1 3x3(x3), Cout 64 / 128, planes of >= 256 padded-flat positions): 30..35
+    (3, 2, 64, 0, 64, (3, 20, 24), 3, 1, 1, True),             # 4 tiles per plane (one group), identity residual
+    (3, 1, 128, 64, 64, (4, 33, 37), 3, 1, 1, False),          # concat input (3 K blocks), ragged plane, several groups
+    (3, 2, 64, 0, 128, (2, 17, 16), 3, 1, 1, False),           # Cout 128 (two tiles per group), narrowest plane
+    (2, 3, 64, 64, 128, (40, 48), 3, 1, 1, True),              # 2-D (kd = 1), concat, dgrad splits 128 channels 64 | 64
+    (3, 1, 192, 0, 64, (5, 64, 64), 3, 1, 1, False),           # the 64^2-plane geometry of the 3-D UNet's top level
+    (2, 1, 128, 0, 128, (31, 255), 3, 1, 1, False),            # widest supported row (Wp = 256)
+    # every (h channels + skip channels -> Cout) combination of the 3-D 64^3 UNet's up path (config D), small spatial dims:
+    # odd counts of 64-channel K blocks (192, 320) pair weight-gradient units across taps
+    (3, 1, 128, 64, 64, (2, 8, 8), 3, 1, 1, False),
+    (3, 1, 128, 64, 128, (2, 8, 8), 3, 1, 1, False),
+    (3, 1, 256, 128, 128, (2, 8, 8), 3, 1, 1, False),
+    (3, 1, 256, 128, 256, (2, 4, 8), 3, 1, 1, False),
+    (3, 1, 512, 256, 256, (2, 4, 8), 3, 1, 1, False),
+    (3, 1, 512, 256, 512, (2, 4, 4), 3, 1, 1, False),
+    (3, 1, 512, 512, 512, (2, 4, 4), 3, 1, 1, False),
+    (3, 1, 256, 64, 64, (2, 8, 8), 3, 1, 1, False),            # 320 = 5 K blocks
+    (3, 1, 192, 0, 64, (2, 8, 8), 1, 1, 1, False),             # 1x1x1 skip conv on 3 K blocks
 ]
 
 
@@ -193,7 +211,7 @@ def test_conv_fwd_bwd(ops, dtype, case):
         assert rel_err(nc(resd.grad), dy) < 1e-6
 
 
-@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20)])
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20, 30, 31, 32, 33, 34, 35)])
 def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     """The bf16 shapes above must run on the tcgen05 engine (forced: an unsupported shape would raise), and agree with
     the CUDA-core engine on the same inputs to fp32-accumulation rounding."""
