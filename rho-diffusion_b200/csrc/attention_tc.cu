@@ -14,6 +14,8 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax / correction /
 // epilogue.  ch = 64: two CTAs per SM (81 KB smem, 256 TMEM columns each).  The T x T weight matrix never exists in HBM
 // (the reference materialises 4.3 GB per sample per block at T = 16384).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace rho {
@@ -30,7 +32,7 @@ struct AttnTcParams {
   float scale;               // ch^-1/2
 };
 
-template <int CH>
+template <int CH, int POLY_MASK>
 __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap kv_map, const AttnTcParams p,
                    bf16* __restrict__ out, float* __restrict__ lse) {
@@ -150,13 +152,21 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
     float m = -INFINITY, l = 0.f;
     // One sweep over the 64 logits of this row: p = exp2(s*c - mb) (one FFMA + one MUFU per element) -> bf16 P in swizzled
     // smem; returns the row sum and the row max of the raw logits.
-    auto exp_pass = [&](uint32_t ts, uint8_t* pbuf, int kvalid, float mb, float& lsum, float& mx_out) {
-      const bool full = kvalid >= AT_BN;
+    // Exponentials: the MUFU unit delivers 16 ex2 / clk / SM, half of what the tensor core can consume at ch = 64, so a
+    // compile-time subset of the element PAIRS (POLY_MASK, period 8 pairs) is evaluated on the FMA pipes instead, two
+    // elements per instruction (f32x2): x clamped to >= -126, n = round(x) by the magic-number add, f = x - n in
+    // [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (7.5e-5 relative, far below bf16 resolution), 2^n by an integer
+    // add into the exponent field.
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    auto exp_pass = [&](auto full_c, uint32_t ts, uint8_t* pbuf, int kvalid, float mb, float& lsum, float& mx_out) {
+      constexpr bool full = decltype(full_c)::value;
       uint32_t va[32], vb[32];
       tmem_ld32_async(ts + lane_addr, va);
       tmem_ld32_async(ts + lane_addr + 32u, vb);
       tmem_wait_ld();
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+      const uint64_t negmb2 = pack2(-mb, -mb);
+      uint64_t ls01 = 0ull, ls23 = 0ull;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t(&v)[32] = half ? vb : va;
@@ -165,19 +175,41 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
-          float p0 = ex2_approx(fmaf(s0, p.scale_log2, -mb));
-          float p1 = ex2_approx(fmaf(s1, p.scale_log2, -mb));
+          const uint64_t x2 = fma2(pack2(s0, s1), scale2, negmb2);
+          uint64_t p2;
+          if ((POLY_MASK >> ((e >> 1) & 7)) & 1) {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+            const uint64_t t2 = add2(xc, pack2(12582912.f, 12582912.f));
+            const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+            const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), xc);
+            uint64_t q2 = fma2(f2, pack2(0.0551716648042202f, 0.0551716648042202f), pack2(0.2426111251115799f, 0.2426111251115799f));
+            q2 = fma2(q2, f2, pack2(0.6932609677314758f, 0.6932609677314758f));
+            q2 = fma2(q2, f2, pack2(0.9999280571937561f, 0.9999280571937561f));
+            uint32_t tl, th, ql, qh;
+            unpack2u(t2, tl, th);
+            unpack2u(q2, ql, qh);
+            p2 = pack2u(ql + (tl << 23), qh + (th << 23));     // 2^n: add n into the exponent field
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p2 = pack2(ex2_approx(x0), ex2_approx(x1));
+          }
           if (full) {
             mx0 = fmaxf(mx0, s0);
             mx1 = fmaxf(mx1, s1);
           } else {
             const bool ok0 = c + e < kvalid, ok1 = c + e + 1 < kvalid;
-            p0 = ok0 ? p0 : 0.f;
-            p1 = ok1 ? p1 : 0.f;
+            float p0, p1;
+            unpack2(p2, p0, p1);
+            p2 = pack2(ok0 ? p0 : 0.f, ok1 ? p1 : 0.f);
             mx0 = fmaxf(mx0, ok0 ? s0 : -INFINITY);
             mx1 = fmaxf(mx1, ok1 ? s1 : -INFINITY);
           }
-          if (e & 2) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
+          if (e & 2) ls23 = add2(ls23, p2); else ls01 = add2(ls01, p2);
+          float p0, p1;
+          unpack2(p2, p0, p1);
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
         }
@@ -190,7 +222,10 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
           *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
         }
       }
-      lsum = (ls0 + ls1) + (ls2 + ls3);
+      float a0, a1, a2, a3;
+      unpack2(ls01, a0, a1);
+      unpack2(ls23, a2, a3);
+      lsum = (a0 + a1) + (a2 + a3);
       mx_out = fmaxf(mx0, mx1);
     };
     constexpr float AT_TAU = 8.0f;
@@ -215,27 +250,29 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
           mx0 = fmaxf(mx0, 32 + e < kvalid ? __uint_as_float(vb[e]) : -INFINITY);
         }
         m = mx0;
-        exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
-      } else {
-        exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
-        if (__any_sync(0xffffffffu, (mx - m) * p.scale_log2 > AT_TAU)) {
-          const float m_new = fmaxf(m, mx);
-          const float alpha = ex2_approx((m - m_new) * p.scale_log2);
-          // rescale this row of O once every PV issued so far (tiles < j) has completed
-          mbar_wait(&o_done, (uint32_t)(j - 1) & 1);
-          tc_fence_after();
+      }
+      // one sweep against the running max known before the tile; redone (once) after a rescale of O when a row of this
+      // warp outgrew the stale max by more than 2^AT_TAU.  Single call site per variant: the sweep is ~1000 instructions.
 #pragma unroll 1
-          for (int c = 0; c < CH; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        if (kvalid >= AT_BN) exp_pass(std::true_type{}, ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
+        else exp_pass(std::false_type{}, ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
+        if (attempt == 1 || j == 0 || !__any_sync(0xffffffffu, (mx - m) * p.scale_log2 > AT_TAU)) break;
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx((m - m_new) * p.scale_log2);
+        // rescale this row of O once every PV issued so far (tiles < j) has completed
+        mbar_wait(&o_done, (uint32_t)(j - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < CH; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_o + lane_addr + (uint32_t)c, v);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            tmem_st32(tmem_o + lane_addr + (uint32_t)c, v);
-          }
-          l *= alpha;
-          m = m_new;
-          exp_pass(ts, pbuf, kvalid, m * p.scale_log2, lsum, mx);
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st32(tmem_o + lane_addr + (uint32_t)c, v);
         }
+        l *= alpha;
+        m = m_new;
       }
       l += lsum;
       tc_fence_before();          // order our tcgen05.ld/st before the MMAs the issuer launches after the barrier
@@ -282,11 +319,11 @@ bool attention_fwd_tc_supported(const rho_attn_params* p) {
   return get_encode() != nullptr;
 }
 
-template <int CH>
+template <int CH, int POLY_MASK>
 static int launch_attn_tc(const CUtensorMap& qmap, const CUtensorMap& kvmap, const AttnTcParams& ap, const rho_attn_params* p, cudaStream_t st) {
   constexpr int KB = CH / 64;
   constexpr size_t SMEM = (size_t)KB * 16384 + 4 * (size_t)KB * 8192 + 2 * 16384 + 1024;
-  auto kern = attn_tc_kernel<CH>;
+  auto kern = attn_tc_kernel<CH, POLY_MASK>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -321,8 +358,20 @@ int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
   else { ap.q_col = 0; ap.k_col = C; ap.v_col = 2 * C; ap.head_stride = p->ch; }
   ap.scale = 1.0f / sqrtf((float)p->ch);
   ap.scale_log2 = ap.scale * 1.4426950408889634f;
-  if (p->ch == 64) return launch_attn_tc<64>(map, kvmap, ap, p, st);
-  return launch_attn_tc<128>(map, kvmap, ap, p, st);
+  // pairs (of every 8) whose exponentials run on the FMA pipes: RHO_ATTN_POLY = 0 | 2 | 3 | 4.  Measured on B200 (T = 16384,
+  // ch = 64, N = 8): 742 / 735 / 739 / 696 TFLOP/s -- the sweep is issue-bound as soon as the MUFU is relieved, so the default
+  // stays 0 (all exponentials on the MUFU); the hook is kept for re-tuning.
+  static int poly = -1;
+  if (poly < 0) { const char* e = getenv("RHO_ATTN_POLY"); poly = e ? atoi(e) : 0; }
+  if (p->ch == 64) {
+    if (poly == 0) return launch_attn_tc<64, 0x00>(map, kvmap, ap, p, st);
+    if (poly == 2) return launch_attn_tc<64, 0x22>(map, kvmap, ap, p, st);
+    if (poly == 4) return launch_attn_tc<64, 0xAA>(map, kvmap, ap, p, st);
+    if (poly == 3) return launch_attn_tc<64, 0x4A>(map, kvmap, ap, p, st);
+    return launch_attn_tc<64, 0x00>(map, kvmap, ap, p, st);
+  }
+  if (poly != 0) return launch_attn_tc<128, 0x22>(map, kvmap, ap, p, st);
+  return launch_attn_tc<128, 0x00>(map, kvmap, ap, p, st);
 }
 
 }  // namespace rho
