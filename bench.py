@@ -92,6 +92,17 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(batch):
+    """DRAM bytes of the tcgen05 conv kernels of ONE eval (sum over their launches) from the committed `ncu --set full`
+    capture of tools/one_eval.py at the same batch (profiles/r01_ncu_traffic_b<batch>.json), or None."""
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_traffic_b{batch}.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    return d.get("conv_tcgen05")
+
+
 def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -323,7 +334,8 @@ def run_b200(args):
         train["ms"] = max_over_ranks(train["ms"])
 
     if rank == 0:
-        conv = prof.get("conv", {"ms": 0.0, "flops": 0.0, "launches": 0})
+        conv = prof.get("conv", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        traffic = ncu_traffic(B)
         attn = prof.get("attention", {"ms": 0.0, "flops": 0.0, "launches": 0})
         gn = prof.get("gn_apply", {"ms": 0.0, "bytes": 0.0, "launches": 0})
         total_prof_ms = sum(v["ms"] for v in prof.values())
@@ -332,7 +344,11 @@ def run_b200(args):
         flops_per_eval = (conv["flops"] + attn["flops"]) / B
         roofline = {
             "kernel": "conv_nd implicit GEMM (forward)", "bound": "tensor", "achieved": conv_tflops, "peak": peak,
-            "unit": "TFLOP/s", "frac": (conv_tflops / peak) if peak else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": (conv_tflops / peak) if peak else None,
+            "traffic": (traffic["dram_bytes"] / traffic["launches"]) if traffic else None,
+            "traffic_note": ("DRAM read+write bytes per launch, averaged over the %d tcgen05 conv launches of one eval (ncu --set full, "
+                             "profiles/r01_ncu_traffic_b%d.json); algorithmic bytes per launch (inputs + weights + outputs once): %.3e"
+                             % (traffic["launches"], B, conv["bytes"] / max(conv["launches"], 1))) if traffic else None,
             "peak_source": pk["source"] + " (bf16 sustained)" if peak else "n/a for the fp32 CUDA-core engine",
             "launches_per_eval": conv["launches"], "share_of_eval_time": conv["ms"] / total_prof_ms if total_prof_ms else None,
             "algorithmic_gflop_per_eval_per_sample": flops_per_eval / 1e9,
@@ -375,10 +391,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("RHO_BENCH_BATCH", "2")), help="sampling batch per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("RHO_BENCH_BATCH", "8")), help="sampling batch per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--train-steps", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_STEPS", "3")))
-    ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "1")))
+    ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "4")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-table", default=None, help="write a per-kernel-shape table (CUDA-event times of one eager eval) to this CSV")
     args = ap.parse_args()

@@ -48,3 +48,18 @@ def cond_values(case: str):
     if case == "galaxy2d":
         return [[0.25, 1.0, 410.0, 0.0], [1.0, 1.0, 400.0, 0.0]]
     return None
+
+
+def loss_curve_inputs(step: int, shape, T: int, n_data: int = 8):
+    """Deterministic (data batch index, t, noise) of training step ``step`` of the 1k-step loss-curve fixture -- shared by
+    the golden generator (oracle/make_golden.py::gen_loss_curve) and tests/test_gpu_fullsize.py.  Uses the CPU generator
+    through functions captured at import (the golden generator patches ``torch.randint`` / ``torch.randn_like``)."""
+    g = _torch.Generator().manual_seed(100003 * (step + 1))
+    t = _RANDINT(0, T, (shape[0],), generator=g)
+    noise = _RANDN(shape, generator=g)
+    return step % n_data, t, noise
+
+
+import torch as _torch  # noqa: E402
+
+_RANDINT, _RANDN = _torch.randint, _torch.randn

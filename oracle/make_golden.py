@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
-from oracle.cases import TIMESTEPS, UNET_CASES, cond_values  # noqa: E402
+from oracle.cases import TIMESTEPS, UNET_CASES, cond_values, loss_curve_inputs  # noqa: E402
 from oracle.synth import synth_input, synth_state_dict  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -282,6 +282,76 @@ def gen_gaussian(ref):
           float(d["reverse"]["denoised"].std()))
 
 
+LOSS_CURVE_STEPS = 1000
+
+
+def gen_loss_curve(ref):
+    """1000 AdamW steps of the UNMODIFIED reference ``DDPM.training_step`` (lr 1e-4 as in examples/*.json, T = 1000 linear
+    schedule, conditional film3d UNet) on 8 cycling synthetic batches with recorded (t, eps): the loss curve the CUDA
+    trainer has to reproduce (north-star acceptance: "training loss curve matches the reference over 1k steps")."""
+    case = "film3d"
+    spec = UNET_CASES[case]
+    kwargs = dict(spec["kwargs"])
+    T = 1000
+    sched = ref.schedule.LinearSchedule(T, 1e-3, 0.02)
+    ddpm = ref.DDPM(ref.UNet, kwargs, sched, "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4})
+    manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+    ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+    ddpm.train()
+    opt = ddpm.configure_optimizers(1)["optimizer"]
+    shape = spec["x_shape"]
+    data = [synth_input(f"curve.x0.{i}", shape, kind="rand") for i in range(8)]
+    labels = [synth_input(f"curve.y.{i}", (shape[0], 4 * kwargs["model_channels"]), kind="rand") for i in range(8)]
+    cur = {}
+    real_randn_like, real_randint = torch.randn_like, torch.randint
+    torch.randn_like = lambda x, *a, **k: cur["noise"].clone()
+    torch.randint = lambda *a, **k: cur["t"].clone()
+    losses = []
+    try:
+        torch.set_num_threads(max(1, (os.cpu_count() or 2)))
+        for step in range(LOSS_CURVE_STEPS):
+            i, cur["t"], cur["noise"] = loss_curve_inputs(step, shape, T)
+            opt.zero_grad()
+            loss = ddpm.training_step([data[i], labels[i]])
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+            if step % 100 == 0:
+                print("step", step, losses[-1], flush=True)
+    finally:
+        torch.randn_like, torch.randint = real_randn_like, real_randint
+    final = {k: v.detach().flatten()[:256].clone() for k, v in ddpm.backbone.state_dict().items()
+             if k in ("out.2.weight", "input_blocks.0.0.weight", "time_embed.0.weight", "middle_block.1.qkv.weight")}
+    torch.save({"T": T, "manifest": manifest, "losses": torch.tensor(losses, dtype=torch.float64), "final_params": final},
+               os.path.join(OUT, "loss_curve_film3d.pt"))
+    print("loss curve: first", losses[:3], "last", losses[-3:])
+
+
+def gen_sph_harm(ref):
+    """compute_spherical_harmonic of the UNMODIFIED reference (rho_diffusion/data/synthetic.py:83-124) for a few (l, m) on
+    the default 32^3 grid.  scipy.special.sph_harm (removed in SciPy 1.17) and h5py (absent) are shimmed for the import."""
+    import importlib
+    import types
+
+    import numpy as np
+    import scipy.special as sp
+    if not hasattr(sp, "sph_harm"):
+        sp.sph_harm = lambda m, n, theta, phi: sp.sph_harm_y(n, m, phi, theta)
+    if "h5py" not in sys.modules:
+        sys.modules["h5py"] = types.SimpleNamespace(File=object)
+    syn = importlib.import_module("rho_diffusion.data.synthetic")
+    grid = np.linspace(-2.0, 2.0, 32)
+    out = {}
+    for l, m in [(0, 0), (1, -1), (2, 1), (3, 3), (4, -2), (5, 4)]:
+        _, density, real = syn.compute_spherical_harmonic(grid, grid, grid, m=m, l=l)
+        out[(l, m)] = {"density": torch.from_numpy(density.astype(np.float32))[::3, ::3, ::3].clone(),
+                       "stats": torch.tensor([density.min(), density.max(), density.mean(), density.std()], dtype=torch.float64)}
+    ds = syn.SphericalHarmonicDataset(max_l=5, random_seed=1616)
+    first = [ds.random_set for _ in range(8)]
+    torch.save({"fields": out, "random_sets": first}, os.path.join(OUT, "sph_harm.pt"))
+    print("sph_harm fixture:", first)
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -289,11 +359,19 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "gaussian":     # regenerate one fixture only
         gen_gaussian(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "sph_harm":
+        gen_sph_harm(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "loss_curve":
+        gen_loss_curve(ref)
+        return
     gen_schedule(ref)
     gen_embeddings(ref)
     gen_unet(ref)
     gen_ddpm(ref)
     gen_gaussian(ref)
+    gen_sph_harm(ref)
+    gen_loss_curve(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,3 +1,5 @@
 from rho_diffusion.data.parameter_space import AbstractParameterSpace, DiscreteParameterSpace, sample_from_discrete_parameter_space
+from rho_diffusion.data.synthetic import SphericalHarmonicDataset, compute_spherical_harmonic, make_spherical_grid
 
-__all__ = ["AbstractParameterSpace", "DiscreteParameterSpace", "sample_from_discrete_parameter_space"]
+__all__ = ["AbstractParameterSpace", "DiscreteParameterSpace", "sample_from_discrete_parameter_space", "SphericalHarmonicDataset",
+           "compute_spherical_harmonic", "make_spherical_grid"]

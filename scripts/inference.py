@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Sampling from a trained checkpoint -- the B200 counterpart of the reference's ``scripts/inference.py``: builds the
+``GaussianDiffusionPipeline`` exactly as the reference does (lines 122-143), loads ``model.pth`` strictly, and calls
+``generate(parameter_space=config.inference.parameter_space)`` (DDIM eta = 0 with dynamic thresholding, one CUDA graph
+per step).  The result is written with ``torch.save`` (``--out``) and, when h5py is importable, to
+``config.inference.cache_file`` under the key ``data`` like the reference.
+
+    python scripts/inference.py examples/config_spherical_harmonics.json -p model.pth -d cuda -n 10
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from pathlib import Path
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "rho-diffusion_b200"))
+
+import torch  # noqa: E402
+
+from rho_diffusion import diffusion  # noqa: E402
+from rho_diffusion.config import ExperimentConfig  # noqa: E402
+from rho_diffusion.registry import registry  # noqa: E402
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("json_config", type=Path)
+    parser.add_argument("-p", dest="model_checkpoint_path", type=Path, required=False)
+    parser.add_argument("-d", "--device", dest="device", type=str, default="cuda")
+    parser.add_argument("-n", dest="n_samples", type=int, default=10)
+    parser.add_argument("-f", dest="forced_overwrite", action="store_true", default=False)
+    parser.add_argument("--out", default="inference_output.pt")
+    parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--steps", type=int, default=0, help="override the number of diffusion steps (0 = config)")
+    args = parser.parse_args()
+
+    from rho_diffusion import b200 as accel
+
+    config = ExperimentConfig.from_json(args.json_config)
+    torch.manual_seed(config.inference.seed)
+    device = torch.device(args.device)
+    schedule = registry.get("schedules", config.noise_schedule.name)(device=device, **config.noise_schedule.kwargs)
+    parameter_space = registry.get("datasets", config.dataset.name).parameter_space
+    cond_fn = config.model.kwargs.get("cond_fn")
+    # the shipped spherical-harmonics labels are same-shape sha512 embeddings (added to the time embedding directly,
+    # unet_v2.py:705-712); MultiEmbeddings is only built when the dataset class exposes a discrete parameter space
+    cond_kwargs = {"parameter_space": parameter_space, "embedding_dim": 128} if (cond_fn and parameter_space is not None) else None
+    model = diffusion.GaussianDiffusionPipeline(
+        backbone=config.model.name, backbone_kwargs=config.model.kwargs, schedule=schedule, loss_func=config.training.loss_fn,
+        timesteps=args.steps or config.noise_schedule.kwargs["num_steps"], cond_fn=cond_fn if cond_kwargs else None,
+        cond_fn_kwargs=cond_kwargs, optimizer=config.optimizer.name, opt_kwargs=config.optimizer.kwargs,
+        sample_every_n_epochs=config.training.sample_every_n_epochs, sampling_batch_size=args.n_samples,
+        sample_parameter_space=config.inference.parameter_space)
+    ckpt = args.model_checkpoint_path or config.inference.checkpoint
+    model.backbone.load_state_dict(torch.load(ckpt), strict=True)
+    model.eval()
+    model.to(device)
+    model = accel.optimize(model, dtype=torch.bfloat16 if args.dtype == "bf16" else torch.float32)
+    if cond_kwargs is not None:
+        pred = model.generate(parameter_space=config.inference.parameter_space, random=False)
+    else:
+        # same-shape label embeddings (the convention of SphericalHarmonicDataset.__getitem__, synthetic.py:299-300): one
+        # sha512 embedding per point of the inference parameter space, batch-sharded across ranks like generate()
+        import itertools
+        from rho_diffusion.utils import calculate_sha512_embedding
+        keys = list(config.inference.parameter_space.keys())
+        combos = list(itertools.product(*config.inference.parameter_space.values()))[: args.n_samples]
+        emb_dim = 4 * int(config.model.kwargs["model_channels"])
+        cond = torch.stack([calculate_sha512_embedding({k: int(v) for k, v in zip(keys, c)}, l=emb_dim) for c in combos]).to(device)
+        shape = [len(combos), int(config.model.kwargs["out_channels"])] + [int(s) for s in config.model.kwargs["data_shape"]]
+        pred = model.reverse_process(torch.zeros(shape, device=device), conditions=cond)["denoised"]
+    torch.save(pred.cpu(), args.out)
+    print("generated", tuple(pred.shape), "mean %.4f std %.4f ->" % (float(pred.mean()), float(pred.std())), args.out)
+    cache = config.inference.cache_file
+    if cache:
+        try:
+            import h5py
+            if args.forced_overwrite or not os.path.isfile(cache):
+                with h5py.File(cache, "w") as h5f:
+                    h5f["data"] = pred.cpu().numpy()
+        except ImportError:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+"""Full-size checks (BASELINE.json configurations) and the 1k-step training loss curve.
+
+* config D (3-D 64^3, 163 M parameters, attention at T = 16384): one UNet eval at batch 1 against the CPU oracle at full
+  size (bf16 tensor-core path within 2e-2, fp32 exact path within 1e-5 -- the north-star tolerances), plus size-independent
+  properties: per-sample independence (a batch of two equals two batches of one), determinism, and the ancestral update
+  leaving x inside [-1, 1];
+* config A (examples/config_spherical_harmonics.json: 3-D 32^3, mc 64, attention at 16 / 8): same parity check;
+* the loss curve of 1000 AdamW steps against the curve the UNMODIFIED reference produced on the same (data, t, eps)
+  sequence (tests/golden/loss_curve_film3d.pt, oracle/make_golden.py::gen_loss_curve).
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import ROOT, load_golden  # noqa: E402
+from oracle import torch_oracle as O  # noqa: E402
+from oracle.cases import UNET_CASES  # noqa: E402
+from oracle.synth import synth_input, synth_state_dict  # noqa: E402
+
+DEV = "cuda"
+
+CONFIG_D = dict(dims=3, in_channels=1, out_channels=1, model_channels=64, num_res_blocks=2, data_shape=[64, 64, 64],
+                attention_resolutions=[4], use_scale_shift_norm=True, num_heads=4, num_classes=20, activation="SiLU",
+                use_new_attention_order=True)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def build_unet(kwargs, dtype):
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.models.unet_v2 import UNet
+    model = UNet(**kwargs)
+    manifest = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = synth_state_dict(manifest, seed=777)
+    model.load_state_dict(sd, strict=True)
+    return set_compute_dtype(model.to(DEV).eval(), dtype), sd
+
+
+@pytest.fixture(scope="module")
+def config_d_oracle():
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, sd = build_unet(CONFIG_D, torch.bfloat16)
+    x = synth_input("full.x", (2, 1, 64, 64, 64))
+    y = synth_input("full.y", (2, 256), kind="rand")
+    t = torch.tensor([437, 12])
+    with torch.inference_mode():
+        ref = O.unet_forward(sd, O.UNetSpec(**CONFIG_D), x[:1], t[:1], y[:1])      # ~5-15 s of CPU
+    return model, sd, x, y, t, ref
+
+
+def test_config_d_full_size_bf16_eval_matches_oracle(config_d_oracle):
+    model, sd, x, y, t, ref = config_d_oracle
+    with torch.inference_mode():
+        got = model(x[:1].to(DEV), t[:1].to(DEV), y[:1].to(DEV))
+    err = rel_l2(got, ref)
+    print("config D (64^3) bf16 vs fp32 oracle: rel L2", err)
+    assert got.shape == ref.shape and err < 2e-2
+
+
+def test_config_d_full_size_fp32_eval_matches_oracle(config_d_oracle):
+    from rho_diffusion.b200 import set_compute_dtype
+    model, sd, x, y, t, ref = config_d_oracle
+    set_compute_dtype(model, torch.float32)
+    try:
+        with torch.inference_mode():
+            got = model(x[:1].to(DEV), t[:1].to(DEV), y[:1].to(DEV))
+    finally:
+        set_compute_dtype(model, torch.bfloat16)
+    err = rel_l2(got, ref)
+    print("config D (64^3) fp32 vs fp32 oracle: rel L2", err)
+    assert err < 1e-5
+
+
+def test_config_d_samples_are_independent_and_deterministic(config_d_oracle):
+    model, sd, x, y, t, ref = config_d_oracle
+    with torch.inference_mode():
+        both = model(x.to(DEV), t.to(DEV), y.to(DEV))
+        again = model(x.to(DEV), t.to(DEV), y.to(DEV))
+        one = model(x[1:].to(DEV), t[1:].to(DEV), y[1:].to(DEV))
+    assert torch.equal(both, again)                       # no atomics / no run-to-run variation
+    assert rel_l2(both[1:], one) < 1e-6                   # no cross-sample coupling (GroupNorm statistics are per sample)
+
+
+def test_config_d_sampling_steps_stay_bounded_and_deterministic(config_d_oracle):
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    from rho_diffusion.b200 import set_compute_dtype
+    model, sd, x, y, t, ref = config_d_oracle
+    ddpm = DDPM("UNetv2", dict(CONFIG_D), LinearSchedule(1000, 1e-3, 0.02), "MSELoss", timesteps=1000, optimizer="AdamW",
+                opt_kwargs={"lr": 1e-4})
+    ddpm.backbone.load_state_dict(sd)
+    ddpm = set_compute_dtype(ddpm.to(DEV).eval(), torch.bfloat16)
+    outs = []
+    for _ in range(2):
+        ddpm._noise_calls = 0
+        res = ddpm.reverse_process(torch.zeros((1, 1, 64, 64, 64), device=DEV), conditions=y[:1].to(DEV), num_steps=6)
+        outs.append(res["denoised"])
+    assert torch.equal(outs[0], outs[1])
+    assert torch.isfinite(outs[0]).all() and outs[0].min() >= -1 and outs[0].max() <= 1
+
+
+def test_config_a_shipped_config_eval_matches_oracle():
+    """examples/config_spherical_harmonics.json (model kwargs restated; the reference JSON is not read at test time)."""
+    kwargs = dict(dims=3, in_channels=1, out_channels=1, model_channels=64, num_res_blocks=2, data_shape=[32, 32, 32],
+                  attention_resolutions=[16, 8], use_scale_shift_norm=True, num_heads=4, num_classes=20, activation="SiLU",
+                  use_new_attention_order=False)
+    model, sd = build_unet(kwargs, torch.bfloat16)
+    x = synth_input("cfgA.x", (2, 1, 32, 32, 32))
+    y = synth_input("cfgA.y", (2, 256), kind="rand")
+    t = torch.tensor([999, 3])
+    with torch.inference_mode():
+        ref = O.unet_forward(sd, O.UNetSpec(**kwargs), x, t, y)
+        got = model(x.to(DEV), t.to(DEV), y.to(DEV))
+    err = rel_l2(got, ref)
+    print("config A (32^3) bf16 vs fp32 oracle: rel L2", err)
+    assert err < 2e-2
+
+
+@pytest.mark.parametrize("dtype,tol_first,tol_smooth", [(torch.float32, 2e-3, 2e-2), (torch.bfloat16, 5e-2, 5e-2)])
+def test_loss_curve_matches_reference_over_1k_steps(dtype, tol_first, tol_smooth):
+    from oracle.cases import loss_curve_inputs
+    from rho_diffusion.b200 import optimize, set_compute_dtype
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    g = load_golden("loss_curve_film3d.pt")
+    spec = UNET_CASES["film3d"]
+    T = g["T"]
+    ddpm = DDPM("UNetv2", dict(spec["kwargs"]), LinearSchedule(T, 1e-3, 0.02), "MSELoss", timesteps=T, optimizer="AdamW",
+                opt_kwargs={"lr": 1e-4})
+    ddpm.backbone.load_state_dict(synth_state_dict(g["manifest"], seed=777))
+    ddpm = set_compute_dtype(ddpm.to(DEV), dtype)
+    opt = ddpm.configure_optimizers(1)["optimizer"]
+    ddpm, fused = optimize(ddpm, optimizer=opt, dtype=dtype)
+    ddpm.train()
+    shape = spec["x_shape"]
+    data = [synth_input(f"curve.x0.{i}", shape, kind="rand").to(DEV) for i in range(8)]
+    labels = [synth_input(f"curve.y.{i}", (shape[0], 128), kind="rand").to(DEV) for i in range(8)]
+    ref = g["losses"]
+    steps = len(ref)
+    losses = torch.zeros(steps, dtype=torch.float32, device=DEV)
+    for step in range(steps):
+        i, t, noise = loss_curve_inputs(step, shape, T)
+        fused.zero_grad()
+        loss = ddpm.training_step([data[i], labels[i]], t=t, noise=noise.to(DEV))
+        loss.backward()
+        fused.step()
+        losses[step] = loss.detach()
+    got = losses.double().cpu()
+    first = float(((got[:20] - ref[:20]).abs() / ref[:20]).max())
+    k = 50
+    sm_got = got.unfold(0, k, k).mean(dim=1)
+    sm_ref = ref.unfold(0, k, k).mean(dim=1)
+    smooth = float(((sm_got - sm_ref).abs() / sm_ref).max())
+    print(f"loss curve {dtype}: first-20 max rel dev {first:.2e}, 50-step-mean max rel dev {smooth:.2e}, "
+          f"ref {float(ref[0]):.4f} -> {float(sm_ref[-1]):.4f}, got {float(got[0]):.4f} -> {float(sm_got[-1]):.4f}")
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"loss_curve_{str(dtype).split('.')[-1]}.json"), "w") as fh:
+            json.dump({"ref": ref.tolist(), "got": got.tolist()}, fh)
+    assert first < tol_first
+    assert smooth < tol_smooth
+    assert float(sm_got[-1]) < 0.7 * float(sm_got[0])           # it actually trains

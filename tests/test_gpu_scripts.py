@@ -1,0 +1,41 @@
+"""The reference's entry points on the B200 backend: ``scripts/training_ddp.py`` trains the shipped spherical-harmonics
+config (examples/config_spherical_harmonics.json, identical to the reference's file up to the device strings) for a few
+steps and writes a reference-layout checkpoint; ``scripts/inference.py`` loads it strictly into the
+GaussianDiffusionPipeline and generates."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import ROOT  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def run(cmd, **kw):
+    res = subprocess.run([sys.executable] + cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, **kw)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    return res.stdout
+
+
+def test_training_script_then_inference_script(tmp_path):
+    cfg = os.path.join(ROOT, "examples", "config_spherical_harmonics.json")
+    ckpt = str(tmp_path / "model.pth")
+    out = run(["scripts/training_ddp.py", cfg, "-d", "cuda", "-e", "1", "--max-steps", "4", "--num-workers", "2", "--save", ckpt])
+    losses = [float(line.split("loss: ")[1].split(",")[0]) for line in out.splitlines() if "loss: " in line]
+    assert losses and all(0.0 < v < 5.0 for v in losses), out[-1500:]
+    sd = torch.load(ckpt)
+    assert "input_blocks.0.0.weight" in sd and sd["input_blocks.0.0.weight"].shape == (64, 1, 3, 3, 3)
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    gen = str(tmp_path / "gen.pt")
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "3", "--steps", "6", "--out", gen])
+    x = torch.load(gen)
+    assert x.shape == (3, 1, 32, 32, 32) and torch.isfinite(x).all(), out[-1500:]

@@ -165,3 +165,27 @@ def test_no_cpu_fallback():
     m = UNet(data_shape=8, in_channels=1, model_channels=32, out_channels=1, num_res_blocks=1)
     with pytest.raises(_lib.RhoB200Error):
         m(torch.zeros(1, 1, 8, 8), torch.zeros(1, dtype=torch.long))
+
+
+def test_spherical_harmonic_dataset_matches_reference():
+    """SphericalHarmonicDataset (reference data/synthetic.py) -- fields, (l, m) draw sequence and label embeddings."""
+    import numpy as np
+    from conftest import load_golden
+    from rho_diffusion.data.synthetic import SphericalHarmonicDataset, compute_spherical_harmonic
+    from rho_diffusion.registry import registry
+    from rho_diffusion.utils import calculate_sha512_embedding
+    g = load_golden("sph_harm.pt")
+    grid = np.linspace(-2.0, 2.0, 32)
+    for (l, m), want in g["fields"].items():
+        _, density, _ = compute_spherical_harmonic(grid, grid, grid, m=m, l=l)
+        got = torch.from_numpy(density.astype(np.float32))
+        assert torch.allclose(got[::3, ::3, ::3], want["density"], rtol=0, atol=1e-6), (l, m)
+        stats = torch.tensor([density.min(), density.max(), density.mean(), density.std()], dtype=torch.float64)
+        assert torch.allclose(stats, want["stats"], rtol=1e-9, atol=1e-12), (l, m)
+    ds = registry.get("datasets", "SphericalHarmonicDataset")(max_l=5, random_seed=1616)
+    assert [ds.random_set for _ in range(8)] == [tuple(t) for t in g["random_sets"]]
+    ds = SphericalHarmonicDataset(max_l=5, random_seed=1616)
+    x, emb = ds[0]
+    l, m = g["random_sets"][0]
+    assert x.shape == (1, 32, 32, 32) and x.dtype == torch.float32 and len(ds) == 1000
+    assert torch.equal(emb, calculate_sha512_embedding({"l": l, "m": m}, l=256))
