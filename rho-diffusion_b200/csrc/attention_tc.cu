@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   uint8_t* sK = sQ + Q_BYTES;                   // [2 stages]
   uint8_t* sV = sK + 2 * KV_BYTES;              // [2 stages]
   uint8_t* sP = sV + 2 * KV_BYTES;              // [2 buffers]
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_ready[2], p_ready[2], o_done;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_ready[2], p_ready[2], o_done, o_final;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
       mbar_init(&p_ready[s], 128);
     }
     mbar_init(&o_done, 1);
+    mbar_init(&o_final, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
         }
         umma_commit(&v_empty[s]);
         umma_commit(&o_done);
+        if (j == nt - 1) umma_commit(&o_final);
       }
       __syncwarp();
     }
@@ -279,8 +281,9 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
       fence_proxy_async_smem();   // make the P stores visible to the tensor core (async proxy)
       mbar_arrive(&p_ready[s]);
     }
-    // ---- epilogue: O / l -> bf16 -> global
-    mbar_wait(&o_done, (uint32_t)(nt - 1) & 1);
+    // ---- epilogue: O / l -> bf16 -> global.  A dedicated single-phase barrier: a parity wait on o_done would pass spuriously
+    // if PV(nt-2) had not completed yet (the barrier two phases behind has the same parity as the awaited one).
+    mbar_wait(&o_final, 0);
     tc_fence_after();
     const int q = q0 + r;
     const float inv = 1.0f / l;

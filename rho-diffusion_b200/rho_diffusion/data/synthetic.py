@@ -54,6 +54,8 @@ def compute_spherical_harmonic(x, y, z, m: int, l: int, normalize: bool = True):
 
 @registry.register_dataset("SphericalHarmonicDataset")
 class SphericalHarmonicDataset(torch.utils.data.Dataset):
+    parameter_space = None          # class-level default of the reference's MultiVariateDataset (data/base.py:27)
+
     def __init__(self, max_l: int | None, h5_path=None, length: int = 1000, random_seed: int | None = None,
                  use_emb_as_labels: bool = True, **grid_kwargs):
         if h5_path is not None:

@@ -2,6 +2,8 @@
 usage: ncu_traffic.py raw.csv out.json"""
 import csv, json, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
+while rows and (len(rows[0]) < 5 or rows[0][0] != "ID"):      # skip ncu's ==PROF== log lines (--log-file mode)
+    rows.pop(0)
 hdr, units, data = rows[0], rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
 def val(r, k, scale_units=True):
