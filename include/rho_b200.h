@@ -97,7 +97,15 @@ typedef struct rho_conv_params {
   void* y;                   /* [N,Do,Ho,Wo,Cout] */
   void* workspace;
   size_t workspace_bytes;
+  /* optional fused GroupNorm statistics of the OUTPUT (the next layer of every conv in the UNet is a GroupNorm32,
+   * layers.py:71-74): when non-NULL and rho_conv_stats_rows(p) = R > 0, the epilogue also writes, for every sample n, row
+   * r < R and output channel c, the sum and the sum of squares of the bf16-rounded outputs of one tile:
+   * stats_partial[((n * R + r) * Cout + c) * 2 + {0, 1}] (fp32, every slot written, fixed order: deterministic).
+   * rho_gn_stats_from_partials turns them into the (mean, rstd) that rho_gn_apply / rho_gn_bwd consume. */
+  float* stats_partial;
 } rho_conv_params;
+/* rows per sample of stats_partial for this geometry / engine, or 0 when the launch cannot produce statistics */
+int32_t rho_conv_stats_rows(const rho_conv_params* p);
 
 /* packed forward weights: [Cout][taps][Cin] (K-major rows, K = tap*Cin + ci, tap = (kd*KH + kh)*KW + kw).
  * `w` is the reference state_dict tensor, fp32 [Cout, Cin, kd, kh, kw]. */
@@ -161,6 +169,11 @@ typedef struct rho_gn_params {
 } rho_gn_params;
 size_t rho_gn_workspace_bytes(const rho_gn_params* p);
 int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream);
+/* same result as rho_gn_stats (p->stats), but from the per-tile channel sums a conv epilogue left behind
+ * (rho_conv_params.stats_partial): part1 / rows1 for x (C1 channels), part2 / rows2 for x2 (C2 channels, or NULL / 0).
+ * Sums are merged in double precision in a fixed order; no pass over the activations.  Not usable with pre_add. */
+int rho_gn_stats_from_partials(const rho_gn_params* p, const float* part1, int32_t rows1, const float* part2, int32_t rows2,
+                               rho_stream_t stream);
 int rho_gn_apply(const rho_gn_params* p, rho_stream_t stream);
 
 typedef struct rho_gn_bwd_params {

@@ -17,6 +17,7 @@ size_t conv_small_wgrad_workspace(const ConvGeom& g, const rho_conv_bwd_params* 
 int conv_small_wgrad(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
 // conv_tc.cu
 bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p);
+int conv_fwd_tc_stats_rows(const ConvGeom& g, const rho_conv_params* p);
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st);
 bool conv_dgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p);
 int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st);
@@ -61,6 +62,13 @@ int rho_conv_pack_weight_aux(const rho_conv_params* p, const float* w, void* aux
   if (rc) return rc;
   RHO_REQUIRE(w && aux, "conv_pack_weight_aux: null pointer");
   return conv_pack_weight_aux(g, p, w, aux, as_stream(stream));
+}
+
+int32_t rho_conv_stats_rows(const rho_conv_params* p) {
+  ConvGeom g;
+  if (!p || make_geom(p, g)) return 0;
+  if (p->engine == RHO_CONV_SIMT) return 0;
+  return conv_fwd_tc_stats_rows(g, p);
 }
 
 size_t rho_conv_workspace_bytes(const rho_conv_params* p) {

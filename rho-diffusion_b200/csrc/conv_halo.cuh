@@ -32,6 +32,7 @@ struct HaloParams {
   int a_stage_bytes;          // R * Wp * 128 rounded up to 1024
   int SA, SB;                 // ring depths
   int out_split;              // > 0: channels >= out_split go to y2 (dgrad of a concat input)
+  float* stat_part;           // optional fused GroupNorm statistics: one row of channel sums per work item (see rho_b200.h)
 };
 
 struct HaloMaps {
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[128];
+  __shared__ float sstat[4][BLOCK_N][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.Cin >> 6;
@@ -183,43 +185,69 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
       mbar_wait(&acc_full[ab], phacc);
       tc_fence_after();
       const long long plane_pos = ((long long)n * p.D + d) * p.H * p.W;
+      float st1[BLOCK_N / 32], st2[BLOCK_N / 32];       // lane l: sums of channel c0 + l over this warp's rows of the item
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) { st1[c] = 0.f; st2[c] = 0.f; }
       for (int i = 0; i < mt_here; ++i) {
         const int q = q0 + i * 128 + r;
         const int h = q / p.Wp, wq = q - h * p.Wp;
         const bool valid = wq != 0 && h < p.H;
         const long long pos = plane_pos + (long long)h * p.W + (wq - 1);
         const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((ab * MT + i) * BLOCK_N);
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tsrc + (uint32_t)c0, v);
-          if (valid) {
-            const int ch = nb * BLOCK_N + c0;
-            bf16* dst;
-            if (p.out_split > 0 && ch >= p.out_split) dst = y2 + pos * (p.Cout - p.out_split) + (ch - p.out_split);
-            else dst = y + pos * (p.out_split > 0 ? p.out_split : p.Cout) + ch;
-            const bf16* res = residual ? residual + pos * p.Cout + ch : nullptr;
+          float xs[32];
+          const int ch = nb * BLOCK_N + c0;
+          bf16* dst;
+          if (p.out_split > 0 && ch >= p.out_split) dst = y2 + pos * (p.Cout - p.out_split) + (ch - p.out_split);
+          else dst = y + pos * (p.out_split > 0 ? p.out_split : p.Cout) + ch;
+          const bf16* res = (residual && valid) ? residual + pos * p.Cout + ch : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
+          for (int j = 0; j < 32; j += 8) {
+            float o[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[c0 + j + e];
-              if (res) {
-                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(res + j));
-                const uint32_t u[4] = {qv.x, qv.y, qv.z, qv.w};
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[c0 + j + e];
+            if (res) {
+              const uint4 qv = __ldg(reinterpret_cast<const uint4*>(res + j));
+              const uint32_t u[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
-              }
-              uint4 w4;
-              __nv_bfloat162 h2;
-              h2 = __floats2bfloat162_rn(o[0], o[1]); w4.x = *reinterpret_cast<uint32_t*>(&h2);
-              h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
-              h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
-              h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
-              *reinterpret_cast<uint4*>(dst + j) = w4;
+              for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+            }
+            uint4 w4;
+            __nv_bfloat162 h2;
+            h2 = __floats2bfloat162_rn(o[0], o[1]); w4.x = *reinterpret_cast<uint32_t*>(&h2);
+            h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
+            h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
+            h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
+            if (valid) *reinterpret_cast<uint4*>(dst + j) = w4;
+            if (p.stat_part) {
+              const uint32_t u[4] = {valid ? w4.x : 0u, valid ? w4.y : 0u, valid ? w4.z : 0u, valid ? w4.w : 0u};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { xs[j + 2 * e] = __uint_as_float(u[e] << 16); xs[j + 2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u); }
             }
           }
+          if (p.stat_part) {
+            float s1, s2;
+            warp_colsum32(xs, lane, s1, s2);
+            st1[c0 >> 5] += s1;
+            st2[c0 >> 5] += s2;
+          }
         }
+      }
+      if (p.stat_part) {
+        // the four warps' sums in a fixed order -> one row of stat_part per item
+#pragma unroll
+        for (int c = 0; c < BLOCK_N / 32; ++c) { sstat[warp & 3][c * 32 + lane][0] = st1[c]; sstat[warp & 3][c * 32 + lane][1] = st2[c]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et < BLOCK_N) {
+          const float a1 = (sstat[0][et][0] + sstat[1][et][0]) + (sstat[2][et][0] + sstat[3][et][0]);
+          const float a2 = (sstat[0][et][1] + sstat[1][et][1]) + (sstat[2][et][1] + sstat[3][et][1]);
+          const long long row = item / p.n_blocks;       // (sample, plane, group) in launch order = n * rows_per_sample + ...
+          *reinterpret_cast<float2*>(p.stat_part + (row * p.Cout + nb * BLOCK_N + et) * 2) = make_float2(a1, a2);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
@@ -274,7 +302,7 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   if (R > 256) return pl;
   p.R = R;
   p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * 128, 1024);
-  const size_t budget = 227 * 1024 - 1024 /* static */ - 1024 /* alignment slack */ - 1024;
+  const size_t budget = 227 * 1024 - 3072 /* static: barriers, bias, statistics scratch */ - 1024 /* alignment slack */ - 1024;
   const size_t b_bytes = (size_t)pl.bn * 128;
   p.SB = pl.bn == 64 ? 5 : 4;
   long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
@@ -305,10 +333,11 @@ static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bi
 
 // x / x2: channels-last [N, D, H, W, C1 / C2]; w: packed [Cout][taps][Cin] bf16 (taps in (kd, kh, kw) order)
 static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, const void* w, const float* bias, const bf16* residual, bf16* y,
-                         bf16* y2, int out_split, cudaStream_t st) {
+                         bf16* y2, int out_split, float* stat_part, cudaStream_t st) {
   HaloPlan pl = pl_in;
   HaloParams& p = pl.p;
   p.out_split = out_split;
+  p.stat_part = stat_part;
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int box[5] = {64, p.Wp, p.R, 1, 1};

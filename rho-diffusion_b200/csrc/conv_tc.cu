@@ -45,6 +45,8 @@ struct TcParams {
   int n_blocks;            // Cout / BLOCK_N
   int out_split;           // > 0: output channels >= out_split go to y2 (pitch Cout - out_split), else y (pitch out_split)
   int tma_store;           // epilogue stages 64-channel chunks in shared memory and writes them with TMA tensor stores
+  float* stat_part;        // optional per-tile channel sums of the output (fused GroupNorm statistics), see rho_b200.h
+  int stat_rows, stat_row_off;   // rows per sample of stat_part; first row of this launch (parity class of a fused upsample)
   int ntaps;
   TcTap taps[TC_MAX_TAPS];
 };
@@ -77,7 +79,7 @@ __device__ __forceinline__ uint32_t umma_idesc() {
 
 // ------------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int BLOCK_K, int STAGES, typename TOut>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
+__global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
                                                       const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                       TOut* __restrict__ y, TOut* __restrict__ y2) {
   constexpr int ROW_BYTES = BLOCK_K * 2;
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[BLOCK_N];
+  __shared__ float sstat[2][4][64][2];   // fused GroupNorm statistics: [chunk parity][epilogue warp][channel][sum, sum of squares]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = blockIdx.x % p.n_blocks;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(cc * 64 + hh * 32), v);
+            float xs[32];                       // the bf16-rounded outputs of this row (0 outside the tensor): statistics input
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float o[8];
@@ -206,8 +210,20 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
               h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
               h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
               h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
+              if (p.stat_part) {
+                if (!valid) w4 = make_uint4(0u, 0u, 0u, 0u);          // rows clipped by the TMA store must not count
+                const uint32_t u[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { xs[j + 2 * e] = __uint_as_float(u[e] << 16); xs[j + 2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u); }
+              }
               const int chunk = (hh * 4 + (j >> 3)) ^ (r & 7);
               *reinterpret_cast<uint4*>(rowp + chunk * 16) = w4;
+            }
+            if (p.stat_part) {
+              float s1, s2;
+              warp_colsum32(xs, lane, s1, s2);
+              sstat[cc & 1][warp & 3][hh * 32 + lane][0] = s1;
+              sstat[cc & 1][warp & 3][hh * 32 + lane][1] = s2;
             }
           }
           fence_proxy_async_smem();
@@ -216,6 +232,13 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Tc
             const bool second = p.out_split > 0 && ch >= p.out_split;
             tma_store_5d(&maps.y[second ? 1 : 0], smem + cc * (TC_BM * 128), second ? ch - p.out_split : ch, w0, h0, d0, n0);
             bulk_commit_group();
+          }
+          if (p.stat_part && et < 64) {
+            // the four warps' partial sums in a fixed order; one row of stat_part per (sample, tile)
+            const float a1 = (sstat[cc & 1][0][et][0] + sstat[cc & 1][1][et][0]) + (sstat[cc & 1][2][et][0] + sstat[cc & 1][3][et][0]);
+            const float a2 = (sstat[cc & 1][0][et][1] + sstat[cc & 1][1][et][1]) + (sstat[cc & 1][2][et][1] + sstat[cc & 1][3][et][1]);
+            const long long row = (long long)tn * p.stat_rows + p.stat_row_off + ((long long)td * p.tiles_h + th) * p.tiles_w + tw;
+            *reinterpret_cast<float2*>(p.stat_part + (row * p.Cout + ch + et) * 2) = make_float2(a1, a2);
           }
         }
         if (et == 0) bulk_wait_group_read0();     // shared memory must stay intact until the stores have read it
@@ -360,14 +383,19 @@ static int encode_out_map(CUtensorMap* m, void* base, int C, const TcParams& p) 
   return encode_view(m, v, box, 64);
 }
 
+static int tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RHO_CONV_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+
 template <typename TOut>
 static int dispatch_tc(int bn, int bk, const TcMaps& maps_in, const TcParams& p_in, const float* bias, const bf16* residual, TOut* y, TOut* y2,
                        cudaStream_t st) {
   TcMaps maps = maps_in;
   TcParams p = p_in;
   p.tma_store = 0;
-  static int tma_epi = -1;
-  if (tma_epi < 0) { const char* e = getenv("RHO_CONV_TMA_STORE"); tma_epi = (e && e[0] == '0') ? 0 : 1; }
+  const int tma_epi = tma_store_enabled();
   const int c_first = p.out_split > 0 ? p.out_split : p.Cout;
   if (tma_epi && sizeof(TOut) == 2 && bn >= 64 && c_first % 64 == 0 && (p.Cout - c_first) % 64 == 0 && (p.out_split == 0 || y2 != nullptr)) {
     int rc = encode_out_map(&maps.y[0], y, c_first, p);
@@ -375,6 +403,7 @@ static int dispatch_tc(int bn, int bk, const TcMaps& maps_in, const TcParams& p_
     if (rc) return rc;
     p.tma_store = 1;
   }
+  if (!p.tma_store) p.stat_part = nullptr;       // (conv_fwd_tc_stats_rows only offers statistics when this path is taken)
 #define RHO_TC(BN, BK) \
   if (bn == BN && bk == BK) return launch_tc<BN, BK, TOut>(maps, p, bias, residual, y, y2, st)
   RHO_TC(256, 64); RHO_TC(128, 64); RHO_TC(64, 64); RHO_TC(32, 64);
@@ -489,6 +518,8 @@ static bool is_plain(const ConvGeom& g) { return g.sd == 1 && g.sh == 1 && g.sw 
 static bool is_strided(const ConvGeom& g) { return g.sd == 1 && (g.sh == 2 || g.sw == 2) && g.ud == 1 && g.uh == 1 && g.uw == 1; }
 static bool is_upsampled(const ConvGeom& g) { return g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && (g.uh == 2 || g.uw == 2); }
 
+int conv_fwd_tc_stats_rows(const ConvGeom& g, const rho_conv_params* p);
+
 bool conv_fwd_tc_supported(const ConvGeom& g, const rho_conv_params* p) {
   if (!tc_common_ok(g, p)) return false;
   if (is_plain(g) || is_strided(g)) return true;
@@ -534,6 +565,34 @@ static ActView parity_view(const void* base, const ConvGeom& g, int C, int ph, i
   return v;
 }
 
+// rows per sample of rho_conv_params.stats_partial (0: this launch cannot produce the fused GroupNorm statistics)
+int conv_fwd_tc_stats_rows(const ConvGeom& g, const rho_conv_params* p) {
+  if (!conv_fwd_tc_supported(g, p) || p->y_f32) return 0;
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("RHO_FUSE_GN_STATS"); fuse = (e && e[0] == '0') ? 0 : 1; }
+  if (!fuse) return 0;
+  if (is_plain(g)) {
+    const HaloPlan hp = halo_plan(g.N, g.D, g.H, g.W, g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw);
+    if (hp.ok) return g.D * hp.p.groups_per_plane;
+  }
+  if (!tma_store_enabled() || pick_block_n(g.Cout) < 64 || g.Cout % 64 != 0) return 0;
+  TcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.N = g.N;
+  int classes = 1;
+  if (is_upsampled(g)) {
+    AuxTable t;
+    if (!build_up_table(g, t)) return 0;
+    classes = t.nclass;
+    tp.Gd = g.D; tp.Gh = g.H; tp.Gw = g.W;
+  } else {
+    tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
+  }
+  pick_tile(tp);
+  if (tp.bn != 1) return 0;                       // a tile must not straddle samples
+  return classes * tp.tiles_w * tp.tiles_h * tp.tiles_d;
+}
+
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   const int bk = pick_block_k(g.C1, g.C2), bn = pick_block_n(g.Cout);
   TcParams tp;
@@ -546,6 +605,9 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
+  float* stat_part = (p->stats_partial && conv_fwd_tc_stats_rows(g, p) > 0) ? p->stats_partial : nullptr;
+  tp.stat_part = stat_part;
+  tp.stat_rows = stat_part ? conv_fwd_tc_stats_rows(g, p) : 0;
 
   if (is_upsampled(g)) {
     AuxTable t;
@@ -568,6 +630,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
       }
       rc = encode_weight_map(&maps.w, (const bf16*)p->w_aux + c * cls_stride, (long long)t.rt * g.Cin, g.Cout, bk, bn);
       if (rc) return rc;
+      tp.stat_row_off = c * tp.tiles_w * tp.tiles_h * tp.tiles_d;
       rc = dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
       if (rc) return rc;
     }
@@ -576,7 +639,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
 
   if (is_plain(g)) {
     const HaloPlan hp = halo_plan(g.N, g.D, g.H, g.W, g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw);
-    if (hp.ok) return conv_halo_run(hp, p->x, p->x2, p->w_packed, p->bias, (const bf16*)p->residual, (bf16*)p->y, nullptr, 0, st);
+    if (hp.ok) return conv_halo_run(hp, p->x, p->x2, p->w_packed, p->bias, (const bf16*)p->residual, (bf16*)p->y, nullptr, 0, stat_part, st);
   }
   tp.Gd = g.Do; tp.Gh = g.Ho; tp.Gw = g.Wo;
   pick_tile(tp);
@@ -766,7 +829,7 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   if (!up) {
     // plain stride-1 conv of dY with the flipped filter: the halo-reuse kernel takes it when the shape qualifies
     const HaloPlan hp = halo_plan(g.N, g.Do, g.Ho, g.Wo, g.Cout, 0, g.Cin, g.kd, g.kh, g.kw);
-    if (hp.ok) return conv_halo_run(hp, p->dy, nullptr, wd, nullptr, nullptr, (bf16*)p->dx, (bf16*)p->dx2, tp.out_split, st);
+    if (hp.ok) return conv_halo_run(hp, p->dy, nullptr, wd, nullptr, nullptr, (bf16*)p->dx, (bf16*)p->dx2, tp.out_split, nullptr, st);
   }
   pick_tile(tp);
   tp.ntaps = g.taps;

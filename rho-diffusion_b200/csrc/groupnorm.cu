@@ -684,6 +684,60 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply8_kernel(const bf16* __
   for (; p < p1; p += rows) *reinterpret_cast<uint4*>(dst + p * C) = transform(__ldg(reinterpret_cast<const uint4*>(src + p * stride)));
 }
 
+// ------------------------------------------------------------------------------------------------
+// statistics from the per-tile channel sums a conv epilogue left behind (rho_conv_params.stats_partial): one CTA per
+// (sample, group); thread t accumulates rows t, t + 256, ... of the group's channels in double, the CTA reduces in a fixed
+// tree: deterministic, and no pass over the activations.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_from_partials_kernel(const float* __restrict__ part1, int rows1, int C1,
+                                                                     const float* __restrict__ part2, int rows2, int C2, int64_t S, int G,
+                                                                     float eps, float* __restrict__ stats) {
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = (C1 + C2) / G;
+  const int c_lo = g * cpg, c_hi = c_lo + cpg;
+  double s1 = 0.0, s2 = 0.0;
+  // the group's channels that live in x ...
+  {
+    const int a = min(c_lo, C1), b = min(c_hi, C1);
+    if (b > a) {
+      const int w = b - a;
+      const float* base = part1 + ((int64_t)n * rows1 * C1 + a) * 2;
+      for (int i = threadIdx.x; i < rows1 * w; i += 256) {
+        const int r = i / w, c = i - r * w;
+        const float2 v = *reinterpret_cast<const float2*>(base + ((int64_t)r * C1 + c) * 2);
+        s1 += (double)v.x; s2 += (double)v.y;
+      }
+    }
+  }
+  // ... and in the concat partner x2
+  {
+    const int a = max(c_lo, C1) - C1, b = max(c_hi, C1) - C1;
+    if (b > a && part2) {
+      const int w = b - a;
+      const float* base = part2 + ((int64_t)n * rows2 * C2 + a) * 2;
+      for (int i = threadIdx.x; i < rows2 * w; i += 256) {
+        const int r = i / w, c = i - r * w;
+        const float2 v = *reinterpret_cast<const float2*>(base + ((int64_t)r * C2 + c) * 2);
+        s1 += (double)v.x; s2 += (double)v.y;
+      }
+    }
+  }
+  __shared__ double sh1[256], sh2[256];
+  sh1[threadIdx.x] = s1; sh2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) { sh1[threadIdx.x] += sh1[threadIdx.x + off]; sh2[threadIdx.x] += sh2[threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = (double)S * cpg;
+    const double mean = sh1[0] / cnt;
+    const double var = fmax(sh2[0] / cnt - mean * mean, 0.0);
+    stats[((int64_t)n * G + g) * 2] = (float)mean;
+    stats[((int64_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 static int gn_chunks8(int N, int64_t S, int C) {
   const int rows = GN_THREADS / (C >> 3);
   int64_t target = (int64_t)sm_count() * 4;          // one resident wave: 4 CTAs per SM
@@ -947,6 +1001,20 @@ int rho_gn_stats(const rho_gn_params* p, rho_stream_t stream) {
   int NG = p->N * p->groups;
   gn_stats_finalize_kernel<<<(NG * 32 + 127) / 128, 128, 0, st>>>(partial, NG, p->groups, chunks, p->eps, p->stats);
   RHO_CHECK_LAUNCH("gn_stats_finalize");
+  return RHO_OK;
+}
+
+int rho_gn_stats_from_partials(const rho_gn_params* p, const float* part1, int32_t rows1, const float* part2, int32_t rows2,
+                               rho_stream_t stream) {
+  int rc = gn_validate(p, "gn_stats_from_partials");
+  if (rc) return rc;
+  RHO_REQUIRE(part1 && rows1 > 0, "gn_stats_from_partials: no statistics for x");
+  RHO_REQUIRE((p->C2 == 0) || (part2 && rows2 > 0), "gn_stats_from_partials: no statistics for x2");
+  RHO_REQUIRE(p->pre_add == nullptr, "gn_stats_from_partials: pre_add changes the per-group sums; use rho_gn_stats");
+  RHO_REQUIRE(p->N <= 65535, "gn_stats_from_partials: N too large");
+  gn_stats_from_partials_kernel<<<dim3(p->groups, p->N), 256, 0, as_stream(stream)>>>(part1, rows1, p->C1, part2, rows2, p->C2, p->S, p->groups,
+                                                                                      p->eps, p->stats);
+  RHO_CHECK_LAUNCH("gn_stats_from_partials");
   return RHO_OK;
 }
 

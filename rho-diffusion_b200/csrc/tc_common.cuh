@@ -162,6 +162,28 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// Column sums across a warp: every lane holds one ROW of 32 values; on return lane l holds sum_rows x[row][l] (s1) and the
+// sum of squares (s2).  Recursive halving: 2 * (16 + 8 + 4 + 2 + 1) shuffles, fixed order (deterministic).
+template <bool SQUARE>
+__device__ __forceinline__ float warp_colsum32_pass(const float (&x)[32], int lane) {
+  float a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = SQUARE ? x[j] * x[j] : x[j];
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int j = 0; j < w; ++j) {
+      const float keep = hi ? a[w + j] : a[j], send = hi ? a[j] : a[w + j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return a[0];
+}
+__device__ __forceinline__ void warp_colsum32(const float (&x)[32], int lane, float& s1, float& s2) {
+  s1 = warp_colsum32_pass<false>(x, lane);      // two passes: half the live registers of a fused one
+  s2 = warp_colsum32_pass<true>(x, lane);
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- UMMA shared-memory descriptors for 128-byte-swizzled tiles (rows of 128 bytes = 64 bf16) ------------------

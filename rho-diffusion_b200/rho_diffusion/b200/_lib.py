@@ -27,7 +27,7 @@ class ConvParams(C.Structure):
         ("ud", c_i32), ("uh", c_i32), ("uw", c_i32),
         ("act_dtype", c_i32), ("w_dtype", c_i32), ("engine", c_i32), ("y_f32", c_i32),
         ("x", c_vp), ("x2", c_vp), ("w_packed", c_vp), ("w_aux", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
-        ("workspace", c_vp), ("workspace_bytes", c_sz),
+        ("workspace", c_vp), ("workspace_bytes", c_sz), ("stats_partial", c_vp),
     ]
 
 
@@ -115,6 +115,7 @@ SIGNATURES = {
     "rho_conv_aux_weight_bytes": (c_sz, [P(ConvParams)]),
     "rho_conv_pack_weight_aux": (C.c_int, [P(ConvParams), c_vp, c_vp, c_vp]),
     "rho_conv_workspace_bytes": (c_sz, [P(ConvParams)]),
+    "rho_conv_stats_rows": (c_i32, [P(ConvParams)]),
     "rho_conv_fwd": (C.c_int, [P(ConvParams), c_vp]),
     "rho_conv_engine_for": (C.c_int, [P(ConvParams)]),
     "rho_conv_bwd_workspace_bytes": (c_sz, [P(ConvBwdParams)]),
@@ -122,6 +123,7 @@ SIGNATURES = {
     "rho_conv_wgrad": (C.c_int, [P(ConvBwdParams), c_vp]),
     "rho_gn_workspace_bytes": (c_sz, [P(GnParams)]),
     "rho_gn_stats": (C.c_int, [P(GnParams), c_vp]),
+    "rho_gn_stats_from_partials": (C.c_int, [P(GnParams), c_vp, c_i32, c_vp, c_i32, c_vp]),
     "rho_gn_apply": (C.c_int, [P(GnParams), c_vp]),
     "rho_gn_bwd_workspace_bytes": (c_sz, [P(GnBwdParams)]),
     "rho_gn_bwd": (C.c_int, [P(GnBwdParams), c_vp]),

@@ -231,10 +231,12 @@ class KernelProfiler:
 profiler: Optional[KernelProfiler] = None
 
 
-def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None):
+def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None, stats=None):
+    """``stats``: optional list that receives the fused GroupNorm statistics partials of the output, ``(tensor, rows)``
+    (rho_conv_params.stats_partial), when the launch can produce them."""
     if profiler is not None:
         ev = profiler.begin()
-        y = _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux)
+        y = _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux, stats)
         taps = 1
         for k in spec.kernel:
             taps *= k
@@ -245,10 +247,10 @@ def conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_
         tag = ("_s2" if max(spec.stride) > 1 else "") + ("_up" if max(spec.up) > 1 else "")
         profiler.end("conv", f"conv{spec.dims}d_k{spec.kernel[-1]}{tag}_{cin}->{Cout}", 2.0 * m * Cout * cin * taps, nbytes, ev)
         return y
-    return _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux)
+    return _conv_forward(x, x2, wp, bias, residual, spec, Cout, engine, y_f32, w_aux, stats)
 
 
-def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None):
+def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV_AUTO, y_f32=False, w_aux=None, stats=None):
     _need_cuda(x, x2, wp, bias, residual)
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous()) and (residual is None or residual.is_contiguous())
     out_dtype = torch.float32 if y_f32 else x.dtype
@@ -256,6 +258,12 @@ def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV
     if residual is not None:
         assert residual.shape == y.shape and residual.dtype == x.dtype
     p = _conv_params(x, x2, wp, bias, residual, y, spec, Cout, engine, y_f32, w_aux)
+    if stats is not None and x.dtype == torch.bfloat16 and not y_f32:
+        rows = int(L.lib().rho_conv_stats_rows(C.byref(p)))
+        if rows > 0:
+            part = torch.empty((x.shape[0], rows, Cout, 2), dtype=torch.float32, device=x.device)
+            p.stats_partial = part.data_ptr()
+            stats.append((part, rows))
     L.check(L.lib().rho_conv_fwd(C.byref(p), stream()), "conv_fwd")
     return y
 
@@ -289,10 +297,10 @@ class ConvFn(torch.autograd.Function):
     ``wp`` is the packed copy of ``weight`` (:func:`packed_weight`); ``weight`` itself only receives the gradient."""
 
     @staticmethod
-    def forward(ctx, x, x2, weight, wp, bias, residual, spec, engine, y_f32, w_aux=None):
+    def forward(ctx, x, x2, weight, wp, bias, residual, spec, engine, y_f32, w_aux=None, stats=None):
         Cout = weight.shape[0]
         b = bias.detach().float() if bias is not None else None
-        y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32, w_aux)
+        y = conv_forward(x, x2, wp, b, residual, spec, Cout, engine, y_f32, w_aux, stats)
         ctx.save_for_backward(x, x2, wp)
         ctx.spec, ctx.engine, ctx.has_bias, ctx.has_res = spec, engine, bias is not None, residual is not None
         ctx.w_shape = tuple(weight.shape)
@@ -307,7 +315,7 @@ class ConvFn(torch.autograd.Function):
         dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, ctx.w_shape[0], need_dx, ctx.needs_input_grad[2],
                                         ctx.has_bias and ctx.needs_input_grad[4], ctx.w_shape, ctx.engine)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
-        return dx, dx2, dw, None, db, dres, None, None, None, None
+        return dx, dx2, dw, None, db, dres, None, None, None, None, None
 
 
 def aux_weight(owner, weight, spec: ConvSpec, x, x2, wp, dtype):
@@ -338,7 +346,19 @@ def conv(owner, x, x2, weight, bias, residual, spec, dtype, engine=L.CONV_AUTO, 
     """conv_nd through the autograd tape; ``owner`` is the module that holds ``weight`` (packed-weight cache)."""
     wp = packed_weight(owner, weight, dtype)
     aux = aux_weight(owner, weight, spec, x, x2, wp, dtype) if engine != L.CONV_SIMT else None
-    return ConvFn.apply(x, x2, weight, wp, bias, residual, spec, engine, y_f32, aux)
+    stats = [] if (dtype == torch.bfloat16 and engine != L.CONV_SIMT and not y_f32) else None
+    y = ConvFn.apply(x, x2, weight, wp, bias, residual, spec, engine, y_f32, aux, stats)
+    if stats:
+        y._rho_part = stats[0]          # (per-tile channel sums, rows per sample): consumed by the next GroupNorm
+    return y
+
+
+def carry_stats(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """Propagates the fused-statistics side channel across a pure view (reshape) of a conv output."""
+    part = getattr(src, "_rho_part", None)
+    if part is not None and dst is not src:
+        dst._rho_part = part
+    return dst
 
 
 def cast(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -387,6 +407,22 @@ def gn_forward(x, x2, gamma, beta, film, pre_add, act, out_dtype, groups=32, eps
     stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
     y = torch.empty((*x.shape[:-1], Ct), dtype=out_dtype, device=x.device)
     p = _gn_params(x, x2, gamma, beta, film, pre_add, act, stats, y, groups, eps)
+    part1 = getattr(x, "_rho_part", None)
+    part2 = getattr(x2, "_rho_part", None) if x2 is not None else None
+    if pre_add is None and part1 is not None and (x2 is None or part2 is not None) and x.dtype == torch.bfloat16:
+        # statistics come from the producing convs' epilogues: no pass over x
+        if profiler is not None:
+            ev = profiler.begin()
+        L.check(L.lib().rho_gn_stats_from_partials(C.byref(p), part1[0].data_ptr(), part1[1], None if part2 is None else part2[0].data_ptr(),
+                                                   0 if part2 is None else part2[1], stream()), "gn_stats_from_partials")
+        if profiler is not None:
+            profiler.end("gn_stats", "gn_stats_fused", 0.0, 0.0, ev)
+            ev = profiler.begin()
+        L.check(L.lib().rho_gn_apply(C.byref(p), stream()), "gn_apply")
+        if profiler is not None:
+            in_bytes = x.numel() * x.element_size() + (x2.numel() * x2.element_size() if x2 is not None else 0)
+            profiler.end("gn_apply", "gn_apply", 0.0, in_bytes + y.numel() * y.element_size(), ev)
+        return y, stats
     ws = workspace(L.lib().rho_gn_workspace_bytes(C.byref(p)), x.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     if profiler is not None:

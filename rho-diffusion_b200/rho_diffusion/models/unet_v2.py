@@ -190,12 +190,12 @@ class AttentionBlock(nn.Module):
 
     def forward_cl(self, h, ctx: ExecCtx):
         shape = h.shape
-        xf = h.reshape(shape[0], -1, shape[-1])            # (N, T, C) view
+        xf = _ops().carry_stats(h.reshape(shape[0], -1, shape[-1]), h)            # (N, T, C) view
         a = self.norm.forward_cl(xf, ctx=ctx)
         qkv = self.qkv.forward_cl(a, ctx=ctx)              # (N, T, 3C)
         o = self.attention.forward_cl(qkv)
         out = self.proj_out.forward_cl(o, residual=xf, ctx=ctx)
-        return out.reshape(shape)
+        return _ops().carry_stats(out.reshape(shape), out)
 
     def forward(self, x):
         ops = _ops()

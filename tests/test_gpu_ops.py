@@ -369,3 +369,48 @@ def test_adamw_ema_kernel(ops):
     assert (pd.cpu() - p).abs().max() < 1e-6
     assert (sd.cpu() - sh).abs().max() < 1e-6
     assert rel_err(md, m) < 2e-6 and rel_err(vd, v) < 2e-6
+
+
+@pytest.mark.parametrize("case", [
+    # (dims, N, Cin, Cout, spatial, k, stride, up, residual, expect_fused)
+    (3, 2, 64, 64, (4, 20, 24), 3, 1, 1, True, True),            # halo-reuse kernel (Cout 64)
+    (3, 2, 64, 128, (2, 17, 16), 3, 1, 1, False, True),          # halo-reuse kernel (Cout 128)
+    (3, 2, 128, 256, (5, 9, 20), 3, 1, 1, True, True),           # generic kernel, ragged tiles, TMA-store epilogue
+    (3, 2, 128, 128, (3, 8, 16), 3, 1, (1, 2, 2), False, True),  # fused upsample: four parity-class launches
+    (3, 2, 64, 64, (3, 10, 12), 3, (1, 2, 2), 1, False, True),   # stride 2
+    (1, 2, 256, 256, (300,), 1, 1, 1, True, True),               # attention proj_out (k = 1) + residual
+    (2, 3, 64, 512, (24, 16), 3, 1, 1, False, True),             # two 256-channel blocks per tile
+    (3, 2, 64, 64, (2, 4, 4), 3, 1, 1, False, False),            # 32 positions per sample: tiles straddle samples -> not fused
+])
+def test_conv_epilogue_groupnorm_statistics(ops, case):
+    """The (mean, rstd) GroupNorm32 obtains from the channel sums a conv epilogue leaves behind equal those of the
+    streaming statistics kernel on the same bf16 tensor, alone and as either half of a channel concat."""
+    dims, N, Cin, Cout, sp, k, stride, up, use_res, expect = case
+    spec = ops.ConvSpec.make(dims, k, stride, up)
+    x = cl(randn(N, Cin, *sp, seed=20) * 1.5 + 0.7).bfloat16()
+    w = (randn(Cout, Cin, *([k] * dims), seed=21) / math.sqrt(Cin * k ** dims)).to(DEV)
+    b = (0.5 * randn(Cout, seed=22)).to(DEV)
+    holder = torch.nn.Module()
+    res = torch.randn(ops.conv_out_shape(x.shape, spec, Cout), device=DEV).bfloat16() if use_res else None
+    w2 = (randn(64, Cin, *([k] * dims), seed=23) / math.sqrt(Cin * k ** dims)).to(DEV)
+    with torch.inference_mode():
+        y = ops.conv(holder, x, None, w, b, res, spec, torch.bfloat16)
+        assert hasattr(y, "_rho_part") == expect
+        if not expect:
+            return
+        gamma, beta = torch.ones(Cout, device=DEV), torch.zeros(Cout, device=DEV)
+        out_f, st_f = ops.gn_forward(y, None, gamma, beta, None, None, 1, torch.bfloat16)
+        plain = y.clone()                                    # no side channel: the streaming kernel runs
+        out_k, st_k = ops.gn_forward(plain, None, gamma, beta, None, None, 1, torch.bfloat16)
+        assert (st_f[..., 0] - st_k[..., 0]).abs().max() < 2e-5 * (1 + st_k[..., 0].abs().max())
+        assert ((st_f[..., 1] - st_k[..., 1]).abs() / st_k[..., 1]).max() < 2e-4
+        assert rel_err(out_f, out_k) < 5e-3
+        # concat: y as x (fused) and a second conv output as x2 (fused), groups straddling the boundary when C1 % cpg != 0
+        y2 = ops.conv(torch.nn.Module(), x, None, w2, None, None, spec, torch.bfloat16)
+        Ct = Cout + 64
+        if Ct % 32 == 0 and hasattr(y2, "_rho_part"):
+            g2, b2 = torch.ones(Ct, device=DEV), torch.zeros(Ct, device=DEV)
+            _, st_cf = ops.gn_forward(y, y2, g2, b2, None, None, 1, torch.bfloat16)
+            _, st_ck = ops.gn_forward(y.clone(), y2.clone(), g2, b2, None, None, 1, torch.bfloat16)
+            assert (st_cf[..., 0] - st_ck[..., 0]).abs().max() < 2e-5 * (1 + st_ck[..., 0].abs().max())
+            assert ((st_cf[..., 1] - st_ck[..., 1]).abs() / st_ck[..., 1]).max() < 2e-4
