@@ -46,7 +46,8 @@ enum {
   RHO_ERR_WORKSPACE = -4
 };
 enum { RHO_F32 = 0, RHO_BF16 = 1 };
-enum { RHO_ACT_NONE = 0, RHO_ACT_SILU = 1, RHO_ACT_RELU = 2, RHO_ACT_TANH = 3, RHO_ACT_SIGMOID = 4, RHO_ACT_GELU = 5 };
+enum { RHO_ACT_NONE = 0, RHO_ACT_SILU = 1, RHO_ACT_RELU = 2, RHO_ACT_TANH = 3, RHO_ACT_SIGMOID = 4, RHO_ACT_GELU = 5,
+       RHO_ACT_SYMLOG = 6 /* SymmetricLog, rho_diffusion/activations.py:35-61: tanh(x) (1 + log(x tanh(x) + 1)) */ };
 /* conv engine selection */
 enum { RHO_CONV_AUTO = 0, RHO_CONV_SIMT = 1, RHO_CONV_TCGEN05 = 2 };
 
@@ -337,6 +338,20 @@ typedef struct rho_x0_step_params {
   const float* posterior_mean_coef1; const float* posterior_mean_coef2; const float* model_log_variance; /* mode 1 */
 } rho_x0_step_params;
 int rho_x0_step(const rho_x0_step_params* p, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * optional resampling / regularisation paths of the UNet (channels-last [N, D, H, W, C], C % 4 == 0):
+ *   rho_resample  mode 0: avg_pool_nd with kernel = stride = (fd, fh, fw), floor extents (layers.py:90-102;
+ *                         Downsample(use_conv=False), unet_v2.py:163-165; ResBlock(down=True), :224-225)
+ *                 mode 1: nearest upsample by (fd, fh, fw) (F.interpolate, unet_v2.py:124-131, without the conv)
+ *                 mode 2: sum over the (fd, fh, fw) children = adjoint of mode 1
+ *                 mode 3: adjoint of mode 0 (parent / window; positions the pooling dropped get 0)
+ *                 (D, H, W) are the extents of `src`, (Do, Ho, Wo) those of `dst`.
+ *   rho_dropout   nn.Dropout(p) of ResBlock.out_layers (unet_v2.py:239): y = x * [u >= p] / (1 - p) with u from
+ *                 Philox4x32-10(counter = i / 4, offset; key = seed); the same call on dy is the backward. */
+int rho_resample(const void* src, void* dst, int dtype, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t fd, int32_t fh,
+                 int32_t fw, int32_t mode, int32_t Do, int32_t Ho, int32_t Wo, rho_stream_t stream);
+int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, rho_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,9 +36,26 @@ UNET_CASES = {
         x_shape=(2, 1, 32, 32), cond="multi",
         parameter_space={"s": [0.25, 0.5, 1.0], "m": [1.0], "t": [400.0, 405.0, 410.0], "c": [0.0]},
     ),
+    # the optional structure of the reference UNet: resblock_updown=True (ResBlocks that pool / upsample, unet_v2.py:218-227,
+    # 263-268) with the registered SymmetricLog activation (activations.py:35-61), 3-D (depth is kept)
+    "updown3d": dict(
+        kwargs=dict(data_shape=[4, 16, 16], in_channels=1, model_channels=32, out_channels=1, num_res_blocks=1,
+                    attention_resolutions=[2], channel_mult=[1, 2, 2], dims=3, num_classes=20, num_heads=2,
+                    use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=True, activation="SymmetricLog"),
+        x_shape=(2, 1, 4, 16, 16), cond="same_shape",
+    ),
+    # conv_resample=False: average-pool Downsample / conv-less nearest Upsample (unet_v2.py:124-131, 163-165), additive
+    # embedding, GELU, 2-D with 3 input channels
+    "pool2d": dict(
+        kwargs=dict(data_shape=[12, 16], in_channels=3, model_channels=32, out_channels=3, num_res_blocks=1,
+                    attention_resolutions=[2], channel_mult=[1, 2], conv_resample=False, dims=2, num_heads=2,
+                    use_scale_shift_norm=False, activation="GELU"),
+        x_shape=(2, 3, 12, 16), cond=None,
+    ),
 }
 
-TIMESTEPS = {"ref2d": [0, 7], "film3d": [3, 999], "multi1d": [1, 500, 250], "galaxy2d": [17, 420]}
+TIMESTEPS = {"ref2d": [0, 7], "film3d": [3, 999], "multi1d": [1, 500, 250], "galaxy2d": [17, 420], "updown3d": [5, 640],
+             "pool2d": [11, 902]}
 
 
 def cond_values(case: str):

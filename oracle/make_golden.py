@@ -51,8 +51,10 @@ def case_inputs(case):
     return x, t, y
 
 
-def gen_unet(ref):
+def gen_unet(ref, only=None):
     for case in UNET_CASES:
+        if only is not None and case not in only:
+            continue
         torch.manual_seed(0)
         model, manifest = build_ref_unet(ref, case)
         x, t, y = case_inputs(case)
@@ -358,6 +360,9 @@ def main():
     ref = ref_loader.load()
     if len(sys.argv) > 1 and sys.argv[1] == "gaussian":     # regenerate one fixture only
         gen_gaussian(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1].startswith("unet:"):
+        gen_unet(ref, only=sys.argv[1][5:].split(","))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "sph_harm":
         gen_sph_harm(ref)

@@ -95,6 +95,7 @@ def load():
     ns = types.SimpleNamespace()
     ns.registry = importlib.import_module("rho_diffusion.registry").registry
     ns.layers = importlib.import_module("rho_diffusion.layers")
+    ns.activations = importlib.import_module("rho_diffusion.activations")      # registers SymmetricLog
     ns.common = importlib.import_module("rho_diffusion.models.common")
     ns.unet_v2 = importlib.import_module("rho_diffusion.models.unet_v2")
     ns.conditioning = importlib.import_module("rho_diffusion.models.conditioning")

@@ -118,8 +118,14 @@ def sample_from_discrete_parameter_space(space: dict, batch_size: int, random: b
 # UNetv2 forward  (rho_diffusion/models/unet_v2.py)
 # --------------------------------------------------------------------------------------------
 
+def symmetric_log(x):
+    """activations.py:60-61."""
+    t = torch.tanh(x)
+    return t + t * torch.log(x * t + 1)
+
+
 _ACTS = {
-    "SiLU": F.silu, "ReLU": F.relu, "Tanh": torch.tanh, "Sigmoid": torch.sigmoid, "GELU": F.gelu,
+    "SiLU": F.silu, "ReLU": F.relu, "Tanh": torch.tanh, "Sigmoid": torch.sigmoid, "GELU": F.gelu, "SymmetricLog": symmetric_log,
 }
 
 

@@ -76,6 +76,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case RHO_ACT_TANH: return tanhf(x);
     case RHO_ACT_SIGMOID: return sigmoidf_(x);
     case RHO_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case RHO_ACT_SYMLOG: { float t = tanhf(x); return t + t * logf(x * t + 1.0f); }     // activations.py:60-61
     default: return x;
   }
 }
@@ -89,6 +90,10 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     case RHO_ACT_GELU: {
       float c = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
       return c + x * 0.3989422804014327f * expf(-0.5f * x * x);
+    }
+    case RHO_ACT_SYMLOG: {
+      const float t = tanhf(x), dt = 1.0f - t * t, u = x * t + 1.0f;
+      return dt * (1.0f + logf(u)) + t * (t + x * dt) / u;
     }
     default: return 1.f;
   }

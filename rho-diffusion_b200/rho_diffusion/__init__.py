@@ -11,7 +11,7 @@ __version__ = "0.1.2+b200.r1"
 __all__ = []
 
 from rho_diffusion import registry as _registry  # noqa: F401,E402
-from rho_diffusion import layers, models, data, diffusion, ema, config, utils  # noqa: F401,E402
+from rho_diffusion import activations, layers, models, data, diffusion, ema, config, utils  # noqa: F401,E402
 
 try:
     from rho_diffusion import b200  # noqa: F401

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librho_b200.so")
 
 RHO_OK = 0
 F32, BF16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_GELU = range(6)
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_GELU, ACT_SYMLOG = range(7)
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
 
 c_i32, c_i64, c_u64, c_f32, c_vp, c_sz = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
@@ -148,6 +148,8 @@ SIGNATURES = {
     "rho_abs_quantile_workspace_bytes": (c_sz, [c_i32]),
     "rho_abs_quantile": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),
     "rho_x0_step": (C.c_int, [P(X0StepParams), c_vp]),
+    "rho_resample": (C.c_int, [c_vp, c_vp, C.c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "rho_dropout": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_f32, c_u64, c_u64, c_vp]),
 }
 
 _lib = None

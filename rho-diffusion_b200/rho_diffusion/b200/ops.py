@@ -21,7 +21,7 @@ F32, BF16 = L.F32, L.BF16
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 _ACT_BY_NAME = {
     None: L.ACT_NONE, "Identity": L.ACT_NONE, "SiLU": L.ACT_SILU, "ReLU": L.ACT_RELU, "Tanh": L.ACT_TANH,
-    "Sigmoid": L.ACT_SIGMOID, "GELU": L.ACT_GELU,
+    "Sigmoid": L.ACT_SIGMOID, "GELU": L.ACT_GELU, "SymmetricLog": L.ACT_SYMLOG,
 }
 
 
@@ -31,7 +31,7 @@ def act_code(act) -> int:
         return L.ACT_NONE if act is None else act
     name = act if isinstance(act, str) else (act.__name__ if isinstance(act, type) else type(act).__name__)
     if name not in _ACT_BY_NAME:
-        raise L.RhoB200Error(f"activation {name!r} has no fused B200 kernel (supported: SiLU, ReLU, Tanh, Sigmoid, GELU)")
+        raise L.RhoB200Error(f"activation {name!r} has no fused B200 kernel (supported: SiLU, ReLU, Tanh, Sigmoid, GELU, SymmetricLog)")
     if name == "GELU" and getattr(act, "approximate", "none") != "none":
         raise L.RhoB200Error("GELU(approximate='tanh') is not supported")
     return _ACT_BY_NAME[name]
@@ -752,3 +752,78 @@ def x0_step(model_out, x, tables: dict, mode: int, t=None, t_scalar=None, thresh
         setattr(p, k, tables[k].data_ptr())
     L.check(L.lib().rho_x0_step(C.byref(p), stream()), "x0_step")
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# optional resampling / dropout paths (conv_resample=False, resblock_updown=True, dropout > 0)
+# ------------------------------------------------------------------------------------------------
+def _resample(x, factors, mode, out_spatial):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    sp = _pad3(tuple(x.shape[1:-1]))
+    f = _pad3(tuple(factors))
+    osp = _pad3(tuple(out_spatial))
+    y = torch.empty((x.shape[0], *out_spatial, x.shape[-1]), dtype=x.dtype, device=x.device)
+    L.check(L.lib().rho_resample(x.data_ptr(), y.data_ptr(), dt(x), x.shape[0], sp[0], sp[1], sp[2], x.shape[-1], f[0], f[1], f[2], mode,
+                                 osp[0], osp[1], osp[2], stream()), "resample")
+    return y
+
+
+class ResampleFn(torch.autograd.Function):
+    """kind "avg": avg_pool_nd(kernel = stride = factors); kind "nearest": nearest upsample by ``factors`` (channels-last)."""
+
+    @staticmethod
+    def forward(ctx, x, kind, factors):
+        factors = tuple(int(v) for v in factors)
+        spatial = tuple(x.shape[1:-1])
+        assert len(factors) == len(spatial)
+        if kind == "avg":
+            out_sp = tuple(s // f for s, f in zip(spatial, factors))
+            y = _resample(x, factors, 0, out_sp)
+        else:
+            out_sp = tuple(s * f for s, f in zip(spatial, factors))
+            y = _resample(x, factors, 1, out_sp)
+        ctx.kind, ctx.factors, ctx.spatial = kind, factors, spatial
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = _resample(dy, ctx.factors, 3 if ctx.kind == "avg" else 2, ctx.spatial)
+        return dx, None, None
+
+
+def avg_pool(x, factors):
+    return ResampleFn.apply(x, "avg", factors)
+
+
+def upsample_nearest(x, factors):
+    return ResampleFn.apply(x, "nearest", factors)
+
+
+_dropout_calls = 0
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout(p) in training mode; the mask is a pure function of (seed, call index, element index)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        global _dropout_calls
+        _dropout_calls += 1
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        ctx.p, ctx.seed, ctx.offset = float(p), int(seed), _dropout_calls
+        L.check(L.lib().rho_dropout(x.data_ptr(), y.data_ptr(), dt(x), x.numel(), ctx.p, ctx.seed, ctx.offset, stream()), "dropout")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.check(L.lib().rho_dropout(dy.data_ptr(), dx.data_ptr(), dt(dy), dy.numel(), ctx.p, ctx.seed, ctx.offset, stream()), "dropout_bwd")
+        return dx, None, None
+
+
+def dropout(x, p: float, seed: int = 0):
+    return DropoutFn.apply(x, p, seed)

@@ -109,10 +109,33 @@ def conv_nd(dims, *args, **kwargs):
         raise ValueError(f"unsupported dimensions: {dims}") from None
 
 
+class AvgPoolNd(nn.Module):
+    """nn.AvgPool{1,2,3}d with kernel_size == stride and no padding (the only form the UNet builds, unet_v2.py:163-165)."""
+
+    def __init__(self, dims, kernel_size, stride=None, padding=0, **kwargs):
+        super().__init__()
+        stride = kernel_size if stride is None else stride
+        k = (kernel_size,) * dims if isinstance(kernel_size, int) else tuple(kernel_size)
+        s = (stride,) * dims if isinstance(stride, int) else tuple(stride)
+        if k != s or padding not in (0, (0,) * dims) or any(kwargs.get(a) for a in ("ceil_mode", "divisor_override")):
+            raise NotImplementedError("avg_pool_nd on B200 supports kernel_size == stride, no padding, floor mode")
+        self.dims, self.kernel_size, self.stride = dims, k, s
+
+    def forward_cl(self, h, ctx: ExecCtx = None):
+        return _ops().avg_pool(h, self.kernel_size)
+
+    def forward(self, x):
+        ops = _ops()
+        ctx = module_ctx(self)
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x, ctx.dtype), ctx), x.dtype)
+
+
 @registry.register_layer("avg_pool_nd")
 def avg_pool_nd(dims, *args, **kwargs):
-    """Average pooling is only reached with ``conv_resample=False`` / ``resblock_updown=True``."""
-    raise NotImplementedError("avg_pool_nd (conv_resample=False) is not part of the B200 hot path yet")
+    """Create a 1D, 2D, or 3D average pooling module (layers.py:90-102)."""
+    if dims not in (1, 2, 3):
+        raise ValueError(f"unsupported dimensions: {dims}")
+    return AvgPoolNd(dims, *args, **kwargs)
 
 
 @registry.register_layer("mean_flat")

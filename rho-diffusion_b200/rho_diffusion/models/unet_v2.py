@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from rho_diffusion.layers import ExecCtx, conv_nd, normalization, zero_module
+from rho_diffusion.layers import ExecCtx, avg_pool_nd, conv_nd, normalization, zero_module
 from rho_diffusion.models.common import sinosoidal_position_embedding
 from rho_diffusion.registry import registry
 
@@ -69,7 +69,7 @@ class Upsample(nn.Module):
     def forward_cl(self, h, ctx: ExecCtx):
         assert h.shape[-1] == self.channels
         if not self.use_conv:
-            raise NotImplementedError("Upsample(use_conv=False) is not part of the B200 hot path yet")
+            return _ops().upsample_nearest(h, (1, 2, 2) if self.dims == 3 else (2,) * self.dims)
         up = (1, 2, 2) if self.dims == 3 else 2
         return self.conv.forward_cl(h, up=up, ctx=ctx)
 
@@ -92,7 +92,8 @@ class Downsample(nn.Module):
         if use_conv:
             self.op = conv_nd(dims, self.channels, self.out_channels, 3, stride=stride, padding=1)
         else:
-            raise NotImplementedError("Downsample(use_conv=False) (average pooling) is not part of the B200 hot path yet")
+            assert self.channels == self.out_channels
+            self.op = avg_pool_nd(dims, kernel_size=stride, stride=stride)
 
     def forward_cl(self, h, ctx: ExecCtx):
         assert h.shape[-1] == self.channels
@@ -117,13 +118,18 @@ class ResBlock(TimestepBlock):
         self.use_conv = use_conv
         self.use_checkpoint = use_checkpoint
         self.use_scale_shift_norm = use_scale_shift_norm
-        if up or down:
-            raise NotImplementedError("resblock_updown=True is not part of the B200 hot path yet (SURVEY 8f rank 4)")
-        self.updown = False
+        self.updown = up or down
         self._act = _ops_act(activation)
 
         self.in_layers = nn.Sequential(normalization(channels), activation, conv_nd(dims, channels, self.out_channels, 3, padding=1))
-        self.h_upd = self.x_upd = nn.Identity()
+        if up:
+            self.h_upd = Upsample(channels, False, dims)
+            self.x_upd = Upsample(channels, False, dims)
+        elif down:
+            self.h_upd = Downsample(channels, False, dims)
+            self.x_upd = Downsample(channels, False, dims)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
         self.emb_layers = nn.Sequential(
             activation, nn.Linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm else self.out_channels))
         self.out_layers = nn.Sequential(
@@ -140,10 +146,13 @@ class ResBlock(TimestepBlock):
         """``h`` is a channels-last tensor or a pair (h, skip) standing for their channel concat."""
         ops = _ops()
         x, x2 = h if isinstance(h, tuple) else (h, None)
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training is not implemented on the B200 path yet")
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
         a = gn1.forward_cl(x, x2, act=self._act, ctx=ctx)
+        if self.updown:
+            # unet_v2.py:263-268: resample the activated features AND the skip input, then convolve
+            assert x2 is None
+            a = self.h_upd.forward_cl(a, ctx)
+            x = self.x_upd.forward_cl(x, ctx)
         hh = conv1.forward_cl(a, ctx=ctx)
         lin = self.emb_layers[1]
         e = ops.linear(emb, lin.weight, lin.bias, None, act_in=self._act)
@@ -152,6 +161,8 @@ class ResBlock(TimestepBlock):
             a2 = gn2.forward_cl(hh, film=e, act=self._act, ctx=ctx)
         else:
             a2 = gn2.forward_cl(hh, pre_add=e, act=self._act, ctx=ctx)
+        if self.training and self.dropout > 0:
+            a2 = ops.dropout(a2, self.dropout, seed=getattr(self, "_rho_dropout_seed", 0))      # unet_v2.py:239
         if isinstance(self.skip_connection, nn.Identity):
             assert x2 is None
             res = x
@@ -272,16 +283,13 @@ class UNet(nn.Module):
         if self.num_classes is not None:
             self.label_emb = None
 
-        def res(ch_in, ch_out):
+        def res(ch_in, ch_out, **updown):
             return ResBlock(ch_in, emb_dim, dropout, out_channels=ch_out, dims=dims, use_checkpoint=use_checkpoint,
-                            use_scale_shift_norm=use_scale_shift_norm, activation=activation)
+                            use_scale_shift_norm=use_scale_shift_norm, activation=activation, **updown)
 
         def attn(ch, heads):
             return AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=heads, num_head_channels=num_head_channels,
                                   use_new_attention_order=use_new_attention_order)
-
-        if resblock_updown:
-            raise NotImplementedError("resblock_updown=True is not part of the B200 hot path yet (SURVEY 8f rank 4)")
 
         ch = input_ch = int(channel_mult[0] * model_channels)
         self.input_blocks = nn.ModuleList([TimestepEmbedSequential(conv_nd(dims, in_channels, ch, 3, padding=1))])
@@ -298,7 +306,8 @@ class UNet(nn.Module):
                 self._feature_size += ch
                 skip_chans.append(ch)
             if level != len(channel_mult) - 1:
-                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                self.input_blocks.append(TimestepEmbedSequential(
+                    res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
                 skip_chans.append(ch)
                 ds *= 2
                 self._feature_size += ch
@@ -315,7 +324,7 @@ class UNet(nn.Module):
                 if ds in attention_resolutions:
                     layers.append(attn(ch, num_heads_upsample))
                 if level and i == num_res_blocks:
-                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=ch))
+                    layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, dims=dims, out_channels=ch))
                     ds //= 2
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
                 self._feature_size += ch

@@ -256,3 +256,27 @@ def test_training_loss_curve_tracks_oracle():
         fused.step()
         print(step, float(loss), float(loss_ref))
         assert float(loss) == pytest.approx(float(loss_ref), rel=5e-4)
+
+
+def test_optional_unet_structure_trains(ops=None):
+    """resblock_updown=True + dropout > 0 in training mode: forward/backward run, every parameter receives a finite
+    gradient, and eval mode ignores the dropout (equals the golden of the reference, which was captured in eval mode)."""
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.models.unet_v2 import UNet
+    spec = UNET_CASES["updown3d"]
+    g = load_golden("unet_updown3d.pt")
+    model = UNet(dropout=0.1, **spec["kwargs"])
+    model.load_state_dict(synth_state_dict(g["manifest"], seed=777), strict=True)
+    model = set_compute_dtype(model.to(DEV), torch.float32)
+    x = synth_input("updown3d.x", spec["x_shape"]).to(DEV)
+    t = torch.tensor(TIMESTEPS["updown3d"], dtype=torch.long).to(DEV)
+    y = synth_input("updown3d.y", (spec["x_shape"][0], 128), kind="rand").to(DEV)
+    model.eval()
+    with torch.inference_mode():
+        out = model(x, t, y)
+    assert nrm_err(out, g["out"])[0] < 1e-5
+    model.train()
+    out_t = model(x, t, y)
+    assert nrm_err(out_t, g["out"])[0] > 1e-3                  # dropout is active in training mode
+    out_t.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())

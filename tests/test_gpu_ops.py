@@ -414,3 +414,79 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
             _, st_ck = ops.gn_forward(y.clone(), y2.clone(), g2, b2, None, None, 1, torch.bfloat16)
             assert (st_cf[..., 0] - st_ck[..., 0]).abs().max() < 2e-5 * (1 + st_ck[..., 0].abs().max())
             assert ((st_cf[..., 1] - st_ck[..., 1]).abs() / st_ck[..., 1]).max() < 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["SymmetricLog", "GELU", "Tanh"])
+def test_groupnorm_registered_activations_fwd_bwd(ops, dtype, name):
+    """Activations other than SiLU go through the generic epilogue of the fused GroupNorm kernel, incl. the reference's own
+    SymmetricLog (rho_diffusion/activations.py:35-61)."""
+    from oracle.torch_oracle import _ACTS
+    N, C, sp = 2, 64, (5, 6)
+    x = randn(N, C, *sp, seed=31) * 1.3 + 0.2
+    gamma, beta = 1 + 0.1 * randn(C, seed=32), 0.1 * randn(C, seed=33)
+    dy = randn(N, C, *sp, seed=34)
+    q = (lambda t: t.to(dtype).float())
+    xr, gr, br = q(x).clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = _ACTS[name](F.group_norm(xr, 32, gr, br, 1e-5))
+    ref.backward(q(dy))
+    xd = cl(x).to(dtype).requires_grad_(True)
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = ops.GnActFn.apply(xd, None, gd, bd, None, None, ops.act_code(name), dtype, 32, 1e-5)
+    y.backward(cl(dy).to(dtype))
+    tol = TOL[dtype]
+    assert rel_err(nc(y), ref) < tol
+    assert rel_err(nc(xd.grad), xr.grad) < 4 * tol
+    assert rel_err(gd.grad, gr.grad) < 4 * tol and rel_err(bd.grad, br.grad) < 4 * tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,factors", [((2, 32, 9, 12), (2, 2)), ((2, 16, 3, 8, 10), (1, 2, 2)), ((3, 64, 33), (2,)),
+                                           ((1, 8, 4, 4, 4), (2, 2, 2))])
+def test_avg_pool_and_nearest_upsample_fwd_bwd(ops, dtype, shape, factors):
+    """avg_pool_nd (kernel = stride, floor extents) and the conv-less nearest upsample with their adjoints vs torch."""
+    dims = len(shape) - 2
+    x = randn(*shape, seed=41)
+    q = (lambda t: t.to(dtype).float())
+    pool = {1: F.avg_pool1d, 2: F.avg_pool2d, 3: F.avg_pool3d}[dims]
+    xr = q(x).clone().requires_grad_(True)
+    ref = pool(xr, factors, factors)
+    dy = q(randn(*ref.shape, seed=42))
+    ref.backward(dy)
+    xd = cl(x).to(dtype).requires_grad_(True)
+    y = ops.avg_pool(xd, factors)
+    y.backward(cl(dy).to(dtype))
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert tuple(nc(y).shape) == tuple(ref.shape)
+    assert rel_err(nc(y), ref) < tol and rel_err(nc(xd.grad), xr.grad) < tol
+    xr2 = q(x).clone().requires_grad_(True)
+    ref2 = F.interpolate(xr2, tuple(s * f for s, f in zip(shape[2:], factors)), mode="nearest")
+    dy2 = q(randn(*ref2.shape, seed=43))
+    ref2.backward(dy2)
+    xd2 = cl(x).to(dtype).requires_grad_(True)
+    y2 = ops.upsample_nearest(xd2, factors)
+    y2.backward(cl(dy2).to(dtype))
+    assert torch.equal(nc(y2).float().cpu(), ref2.detach())                  # a pure gather: exact
+    assert rel_err(nc(xd2.grad), xr2.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_mask_scaling_and_backward(ops, dtype):
+    """nn.Dropout(p) semantics: elements are zeroed with probability p, survivors scaled by 1 / (1 - p); the backward applies
+    the SAME mask; a fixed (seed, call index) reproduces the mask and successive calls draw fresh ones."""
+    from rho_diffusion.b200 import ops as O2
+    p = 0.3
+    x = (torch.rand(4, 1000, 37, device=DEV) + 0.5).to(dtype).requires_grad_(True)
+    O2._dropout_calls = 100
+    y = ops.dropout(x, p, seed=5)
+    y.backward(torch.ones_like(y))
+    keep = y.detach().float() != 0
+    frac = float((~keep).float().mean())
+    assert abs(frac - p) < 5e-3
+    assert rel_err(y.detach()[keep], x.detach()[keep].float() / (1 - p)) < (1e-6 if dtype == torch.float32 else 8e-3)
+    assert torch.equal(x.grad != 0, keep)
+    assert rel_err(x.grad[keep], torch.full_like(x.grad[keep], 1 / (1 - p))) < (1e-6 if dtype == torch.float32 else 8e-3)
+    O2._dropout_calls = 100
+    assert torch.equal(ops.dropout(x.detach(), p, seed=5), y.detach())       # same (seed, call index) -> same mask
+    assert not torch.equal(ops.dropout(x.detach(), p, seed=5) != 0, keep)    # next call index -> a different mask
+    assert torch.equal(ops.dropout(x.detach(), 0.0, seed=1), x.detach())
