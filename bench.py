@@ -56,7 +56,8 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines = gpu_index, None, []      # lines: (host time of receipt, csv row)
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -68,7 +69,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -77,7 +84,15 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # samples received inside the timed region (the sampler is started before the warm-up so that it is already
+        # streaming); a region shorter than the sampling period falls back to the samples nearest to it
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        hi = (self.t_end if self.t_end is not None else time.time()) + 0.05
+        rows = [ln for (ts, ln) in self.lines if lo <= ts <= hi]
+        if not rows and self.lines:
+            mid = 0.5 * (lo + hi)
+            rows = [ln for (_, ln) in sorted(self.lines, key=lambda r: abs(r[0] - mid))[:2]]
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -171,7 +186,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg(budget_s=30.0):
@@ -239,17 +254,19 @@ def run_b200(args):
 
         # ---- device-resident leg: K replays of the captured step (inputs already in HBM; the working set of one eval,
         #      >1 GB of activations + 326 MB of bf16 weights, is far larger than the 126 MB L2, so no flush is needed)
+        clocks = ClockSampler(local)
+        clocks.start()
         for _ in range(args.warmup):
             sampler.graph.replay()
         barrier()
-        clocks = ClockSampler(local)
-        clocks.start()
+        clocks.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             sampler.graph.replay()
         e1.record()
         barrier()
+        clocks.mark_end()
         ms = e0.elapsed_time(e1)
         clk = clocks.stop()
 
@@ -380,12 +397,30 @@ def run_b200(args):
             line["train"] = {"metric": "train samples/s", "value": world * train["batch"] * train["steps"] / (train["ms"] * 1e-3),
                              "unit": "samples/s", "ms_per_step": train["ms"] / train["steps"], "batch_per_gpu": train["batch"],
                              "steps": train["steps"], "last_loss": train["loss"], "collective": "NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything libraries print (the NCCL version banner, torchrun notices)
+    was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)           # fd 1 -> stderr for the rest of the process (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

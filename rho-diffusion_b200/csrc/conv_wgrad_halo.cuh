@@ -1,0 +1,258 @@
+// Halo-reuse weight gradient (included by conv_wgrad_tc.cu) for stride-1 3x3(x3) convs with 64 / 128 output channels on
+// wide planes -- the layers where the per-tap kernel is L2 -> shared-memory bound (two X boxes + one dY box = 48 KB of TMA
+// traffic per 8 N=64 MMAs, 3.7x what the TMA path sustains).
+//
+// As in conv_halo.cuh a plane is indexed by the padded-flat position q = h * (W + 1) + w + 1.  One TMA slab of X (rows
+// [q0 - Wp - 1, q0 + CH + Wp + 1), 64 input channels) and one slab of dY (rows [q0, q0 + CH), 64 output channels; the w = -1
+// column is zero-filled, so padding positions contribute nothing) serve ALL NINE in-plane taps of one depth offset:
+//     dW[dd, dh, dw][ci][co] += sum_q X[q + dh * Wp + dw][ci] * dY[q][co]
+// Both operands are MN-major (the reduction index q is the row; the swizzle is a function of the absolute shared-memory
+// address, so an operand may start at any 128-byte row).  An M = 128 MMA pairs two taps: its second 64-channel atom is the
+// same slab (shift_b - shift_a) rows further (leading-dimension byte offset of the descriptor).  Five tap pairs x 64
+// columns of TMEM accumulate over a contiguous range of position chunks (split-K over chunks); the fp32 partials use the
+// layout of the per-tap kernel ([split][tap][ci][co]) and are reduced by the same deterministic kernels.
+#pragma once
+
+namespace rho {
+
+constexpr int WH_CH = 256;        // flat positions per chunk
+constexpr int WH_PAIRS = 5;       // 9 in-plane taps -> 5 M = 128 pairs (the last one half used)
+
+struct WgHaloParams {
+  int N, D, H, W, Wp;
+  int C1, C2, Cin, Cout;
+  int kd, pd;
+  int cibs, cobs;              // 64-channel blocks of the input / output channels
+  int units;                   // kd * cibs * cobs
+  int splits;                  // CTAs per unit
+  int chunks_per_plane;
+  long long chunks_total, chunks_per_split;
+  int Rx, Ry;                  // slab rows of the X / dY boxes
+  int x_bytes, y_bytes;        // stage sizes (1024-aligned)
+};
+
+struct WgHaloMaps {
+  CUtensorMap x[2];            // x, x2 (concat partner)
+  CUtensorMap dy;
+};
+
+__global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const __grid_constant__ WgHaloParams p,
+                                                                 float* __restrict__ partial) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                          // [2 stages]
+  uint8_t* sY = smem + 2 * (size_t)p.x_bytes;  // [2 stages]
+  __shared__ uint64_t full_bar[2], empty_bar[2], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int u = blockIdx.x / p.splits;
+  const int split = blockIdx.x - u * p.splits;
+  const int cob = u % p.cobs; u /= p.cobs;
+  const int cib = u % p.cibs;
+  const int dd = u / p.cibs;
+  const long long c_begin = (long long)split * p.chunks_per_split;
+  const long long c_end = min(p.chunks_total, c_begin + p.chunks_per_split);
+  const int xc = cib * 64;
+  const int src = xc >= p.C1 ? 1 : 0;
+  const int xcc = src ? xc - p.C1 : xc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // chunk -> (sample, plane, first flat position); chunks whose X plane (d + dd - pd) is outside the volume contribute nothing
+  auto decode = [&](long long c, int& n, int& d, int& q0, bool& live) {
+    const int cp = (int)(c % p.chunks_per_plane);
+    const long long plane = c / p.chunks_per_plane;
+    d = (int)(plane % p.D);
+    n = (int)(plane / p.D);
+    q0 = cp * WH_CH;
+    const int xd = d + dd - p.pd;
+    live = xd >= 0 && xd < p.D;
+  };
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long c = c_begin; c < c_end; ++c) {
+      int n, d, q0; bool live;
+      decode(c, n, d, q0, live);
+      if (!live) continue;
+      const int hx = (q0 + p.Wp - 1) / p.Wp - 2;          // floor((q0 - Wp - 1) / Wp)
+      const int hy = q0 / p.Wp;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[stage], (uint32_t)((p.Rx + p.Ry) * p.Wp * 128));
+        tma_load_5d(sX + (size_t)stage * p.x_bytes, &maps.x[src], &full_bar[stage], xcc, -1, hx, d + dd - p.pd, n);
+        tma_load_5d(sY + (size_t)stage * p.y_bytes, &maps.dy, &full_bar[stage], cob * 64, -1, hy, d, n);
+      }
+      __syncwarp();
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // D fp32, A / B bf16, both MN-major, M = 128, N = 64
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long c = c_begin; c < c_end; ++c) {
+      int n, d, q0; bool live;
+      decode(c, n, d, q0, live);
+      if (!live) continue;
+      const int hx = (q0 + p.Wp - 1) / p.Wp - 2;
+      const int hy = q0 / p.Wp;
+      const int xrow = q0 - hx * p.Wp, yrow = q0 - hy * p.Wp;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t xa = smem_u32(sX + (size_t)stage * p.x_bytes), ya = smem_u32(sY + (size_t)stage * p.y_bytes);
+      if (elect_one()) {
+#pragma unroll 1
+        for (int pi = 0; pi < WH_PAIRS; ++pi) {
+          const int ta = 2 * pi, tb = 2 * pi + 1;
+          const int sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
+          const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;     // unused half of the last pair: any valid rows
+          const uint32_t lbo = (uint32_t)(sb - sa) * 128u;
+#pragma unroll
+          for (int k = 0; k < WH_CH / 16; ++k) {
+            const uint64_t a = wg_desc_mn(xa + (uint32_t)(xrow + sa + k * 16) * 128u, lbo);
+            const uint64_t b = wg_desc_mn(ya + (uint32_t)(yrow + k * 16) * 128u, 1024u);
+            umma_f16(tmem_base + (uint32_t)(pi * 64), a, b, idesc, !(first && k == 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(&accum_bar);
+    __syncwarp();
+  } else {
+    // epilogue: accumulator row r = (atom a = r / 64 -> tap 2 * pi + a, ci = r % 64), 64 output channels per pair
+    bool any = false;
+    for (long long c = c_begin; c < c_end; ++c) {
+      int n, d, q0; bool live;
+      decode(c, n, d, q0, live);
+      any = any || live;
+    }
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const int a = r >> 6, ci = xc + (r & 63);
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int taps = p.kd * 9;
+#pragma unroll 1
+    for (int pi = 0; pi < WH_PAIRS; ++pi) {
+      const int t9 = 2 * pi + a;
+      if (t9 >= 9) continue;                        // warp-uniform (a is constant per warp)
+      float* dst = partial + ((((long long)split * taps + (dd * 9 + t9)) * p.Cin + ci) * p.Cout) + cob * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        if (any) tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(pi * 64 + c0), v);
+        else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(dst + c0 + e) =
+              make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+struct WgHaloPlan {
+  bool ok;
+  WgHaloParams p;
+  size_t smem;
+};
+
+static WgHaloPlan wg_halo_plan(const ConvGeom& g) {
+  WgHaloPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("RHO_WGRAD_HALO"); mode = e ? atoi(e) : 1; }
+  if (!mode) return pl;
+  const bool plain = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1;
+  if (!plain || g.kh != 3 || g.kw != 3 || (g.kd != 1 && g.kd != 3)) return pl;
+  if (g.C1 % 64 != 0 || g.C2 % 64 != 0 || (g.Cout != 64 && g.Cout != 128)) return pl;
+  if (g.W < 16 || g.W > 255 || (long long)g.H * (g.W + 1) < 2 * WH_CH) return pl;
+  WgHaloParams& p = pl.p;
+  p.N = g.N; p.D = g.D; p.H = g.H; p.W = g.W; p.Wp = g.W + 1;
+  p.C1 = g.C1; p.C2 = g.C2; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.kd = g.kd; p.pd = g.kd / 2;
+  p.cibs = g.Cin / 64; p.cobs = g.Cout / 64;
+  p.units = p.kd * p.cibs * p.cobs;
+  p.chunks_per_plane = (int)ceil_div((long long)g.H * p.Wp, WH_CH);
+  p.chunks_total = (long long)g.N * g.D * p.chunks_per_plane;
+  int splits = std::max(1, sm_count() / p.units);
+  splits = (int)std::min<long long>(splits, std::max<long long>(1, p.chunks_total / 4));
+  splits = std::min(splits, 64);
+  p.chunks_per_split = ceil_div(p.chunks_total, (long long)splits);
+  p.splits = (int)ceil_div(p.chunks_total, p.chunks_per_split);
+  int Rx = 0, Ry = 0;
+  for (int c = 0; c < p.chunks_per_plane; ++c) {
+    const int q0 = c * WH_CH;
+    const int hx = (q0 + p.Wp - 1) / p.Wp - 2;
+    Rx = std::max(Rx, (q0 + WH_CH - 1 + p.Wp + 1) / p.Wp - hx + 1);
+    Ry = std::max(Ry, (q0 + WH_CH - 1) / p.Wp - q0 / p.Wp + 1);
+  }
+  if (Rx > 256 || Ry > 256) return pl;
+  p.Rx = Rx; p.Ry = Ry;
+  p.x_bytes = (int)align_up((size_t)Rx * p.Wp * 128, 1024);
+  p.y_bytes = (int)align_up((size_t)Ry * p.Wp * 128, 1024);
+  pl.smem = 2 * ((size_t)p.x_bytes + p.y_bytes) + 1024;
+  if (pl.smem > 227 * 1024 - 2048) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+static int wg_halo_encode(CUtensorMap* m, const void* base, int C, const WgHaloParams& p, int rows) {
+  auto enc = get_encode();
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * p.W, (cuuint64_t)C * 2 * p.W * p.H, (cuuint64_t)C * 2 * p.W * p.H * p.D};
+  cuuint32_t bdim[5] = {64, (cuuint32_t)p.Wp, (cuuint32_t)rows, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo) failed: %d", (int)r);
+  return RHO_OK;
+}
+
+static int conv_wgrad_halo_run(const WgHaloPlan& pl, const ConvGeom& g, const rho_conv_bwd_params* bp, float* partial, cudaStream_t st) {
+  const WgHaloParams& p = pl.p;
+  WgHaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = wg_halo_encode(&maps.x[0], bp->fwd.x, g.C1, p, p.Rx);
+  if (!rc && g.C2) rc = wg_halo_encode(&maps.x[1], bp->fwd.x2, g.C2, p, p.Rx);
+  if (!rc) rc = wg_halo_encode(&maps.dy, bp->dy, g.Cout, p, p.Ry);
+  if (rc) return rc;
+  static size_t attr_bytes = 0;
+  if (pl.smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_wgrad_halo: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
+    attr_bytes = pl.smem;
+  }
+  conv_wgrad_halo_kernel<<<(unsigned)(p.units * p.splits), 192, pl.smem, st>>>(maps, p, partial);
+  RHO_CHECK_LAUNCH("conv_wgrad_halo_tcgen05");
+  return RHO_OK;
+}
+
+}  // namespace rho

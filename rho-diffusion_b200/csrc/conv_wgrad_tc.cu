@@ -222,6 +222,10 @@ __global__ void wgrad_tc_reduce_flat_kernel(const float* __restrict__ partial, i
   }
 }
 
+}  // namespace rho
+#include "conv_wgrad_halo.cuh"
+namespace rho {
+
 static int wg_pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int wg_ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -311,6 +315,10 @@ static void wg_plan(const ConvGeom& g, WgParams& wp) {
 
 size_t conv_wgrad_tc_workspace(const ConvGeom& g, const rho_conv_bwd_params* p) {
   if (!conv_wgrad_tc_supported(g, p)) return 0;
+  {
+    const WgHaloPlan hp = wg_halo_plan(g);
+    if (hp.ok) return (size_t)hp.p.splits * g.Cout * g.Cin * g.taps * sizeof(float);
+  }
   WgParams wp;
   wg_plan(g, wp);
   return (size_t)wp.splits * g.Cout * g.Cin * g.taps * sizeof(float);
@@ -348,7 +356,19 @@ static int wg_launch(const WgMaps& maps, const WgParams& wp, float* partial, cud
   return RHO_OK;
 }
 
+static int wg_reduce(const ConvGeom& g, const float* partial, int splits, float* dw, cudaStream_t st);
+
 int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  {
+    const WgHaloPlan hp = wg_halo_plan(g);
+    if (hp.ok) {
+      const size_t need_h = (size_t)hp.p.splits * g.Cout * g.Cin * g.taps * sizeof(float);
+      if (!p->workspace || p->workspace_bytes < need_h) return fail(RHO_ERR_WORKSPACE, "conv_wgrad_halo: workspace %zu < %zu", p->workspace_bytes, need_h);
+      int rc = conv_wgrad_halo_run(hp, g, p, (float*)p->workspace, st);
+      if (rc) return rc;
+      return wg_reduce(g, (const float*)p->workspace, hp.p.splits, p->dw, st);
+    }
+  }
   WgParams wp;
   wg_plan(g, wp);
   const size_t need = (size_t)wp.splits * g.Cout * g.Cin * g.taps * sizeof(float);
@@ -382,14 +402,19 @@ int conv_wgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   else if (bn == 128) rc = wg_launch<128, 3>(maps, wp, partial, st);
   else rc = wg_launch<64, 4>(maps, wp, partial, st);
   if (rc) return rc;
+  return wg_reduce(g, partial, wp.splits, p->dw, st);
+}
+
+// dw[co][ci][tap] = sum over splits of partial[split][tap][ci][co], fixed order
+static int wg_reduce(const ConvGeom& g, const float* partial, int splits, float* dw, cudaStream_t st) {
   const int cit = std::max(1, std::min(g.Cin, 256 / g.taps));
   dim3 rgrid((unsigned)ceil_div(g.Cout, 32), (unsigned)ceil_div(g.Cin, cit));
   if ((long long)rgrid.x * rgrid.y >= 2ll * sm_count()) {
-    wgrad_tc_reduce_kernel<<<rgrid, 256, (size_t)cit * g.taps * 33 * sizeof(float), st>>>(partial, wp.splits, g.Cout, g.Cin, g.taps, cit, p->dw);
+    wgrad_tc_reduce_kernel<<<rgrid, 256, (size_t)cit * g.taps * 33 * sizeof(float), st>>>(partial, splits, g.Cout, g.Cin, g.taps, cit, dw);
   } else {
     const long long total = (long long)g.Cout * g.Cin * g.taps;
     wgrad_tc_reduce_flat_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8), 256, 0, st>>>(
-        partial, wp.splits, g.Cout, g.Cin, g.taps, p->dw);
+        partial, splits, g.Cout, g.Cin, g.taps, dw);
   }
   RHO_CHECK_LAUNCH("wgrad_tc_reduce");
   return RHO_OK;
