@@ -308,6 +308,31 @@ def run_b200(args):
                     fh.write(f"{kind},{name},{r[0]},{r[1]:.4f},{r[2] / (r[1] * 1e-3) / 1e12 if r[1] else 0:.2f},{r[3] / (r[1] * 1e-3) / 1e9 if r[1] else 0:.1f}\n")
         ops.profiler = None
 
+    # ---- x0-prediction DDIM sampler (GaussianDiffusionPipeline.generate, the loop scripts/inference.py runs): same UNet,
+    #      plus the per-sample |x0| quantile and the fused DDIM update, one CUDA graph per step
+    ddim = None
+    if args.ddim_steps > 0:
+        from rho_diffusion.b200.sampler import X0Sampler
+        from rho_diffusion.diffusion.gaussian_diffusion import sampler_tables
+        with torch.inference_mode():
+            tab = sampler_tables(T_STEPS, device)
+            xs = X0Sampler(ddpm.backbone, (B, 1, 64, 64, 64), device, tab, 0.9, cond_example=cond_dev, use_cuda_graph=True)
+            xs._capture()
+            xs.x.copy_(x_dev)
+            xs.tt.fill_(T_STEPS - 1)
+            xs.t_scalar.fill_(T_STEPS - 1)
+            for _ in range(3):
+                xs.graph.replay()
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(args.ddim_steps):
+                xs.graph.replay()
+            h1.record()
+            barrier()
+            ddim = h0.elapsed_time(h1)
+            del xs
+
     # ---- training leg (samples/s): q_sample -> UNet fwd/bwd -> fused AdamW (+ flat-gradient all-reduce for N > 1)
     train = None
     if args.train_steps > 0:
@@ -347,6 +372,8 @@ def run_b200(args):
 
     ms = max_over_ranks(ms)
     ms_e2e = max_over_ranks(ms_e2e)
+    if ddim is not None:
+        ddim = max_over_ranks(ddim)
     if train is not None:
         train["ms"] = max_over_ranks(train["ms"])
 
@@ -391,6 +418,10 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clk, "roofline": roofline,
         }
+        if ddim is not None:
+            line["ddim"] = {"metric": "UNet denoise evals/s, GaussianDiffusionPipeline DDIM step (x0 prediction + dynamic thresholding)",
+                            "value": world * B * args.ddim_steps / (ddim * 1e-3), "unit": "evals/s", "steps": args.ddim_steps,
+                            "ms_per_step": ddim / args.ddim_steps}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if train is not None:
@@ -430,6 +461,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--train-steps", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_STEPS", "3")))
     ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "4")))
+    ap.add_argument("--ddim-steps", type=int, default=int(os.environ.get("RHO_BENCH_DDIM_STEPS", "5")),
+                    help="timed steps of the GaussianDiffusionPipeline DDIM sampler (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-table", default=None, help="write a per-kernel-shape table (CUDA-event times of one eager eval) to this CSV")
     args = ap.parse_args()

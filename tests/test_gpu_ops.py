@@ -490,3 +490,63 @@ def test_dropout_mask_scaling_and_backward(ops, dtype):
     assert torch.equal(ops.dropout(x.detach(), p, seed=5), y.detach())       # same (seed, call index) -> same mask
     assert not torch.equal(ops.dropout(x.detach(), p, seed=5) != 0, keep)    # next call index -> a different mask
     assert torch.equal(ops.dropout(x.detach(), 0.0, seed=1), x.detach())
+
+
+def _fuzz_conv_cases(n, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < n:
+        dims = rng.choice([1, 2, 3, 3])
+        k = rng.choice([1, 3, 3, 3])
+        C1 = rng.choice([32, 64, 64, 96, 128, 192, 256, 320])
+        C2 = rng.choice([0, 0, 0, 32, 64, 128])
+        Cout = rng.choice([32, 64, 64, 96, 128, 128, 256, 384])
+        mode = rng.choice(["plain", "plain", "plain", "stride", "up"]) if k == 3 else "plain"
+        if mode != "plain":
+            C2 = 0
+        if dims == 1:
+            sp = (rng.randint(5, 300),)
+        elif dims == 2:
+            sp = (rng.randint(3, 40), rng.randint(3, 70))
+        else:
+            sp = (rng.randint(1, 5), rng.randint(3, 24), rng.randint(3, 40))
+        stride = ((1, 2, 2) if dims == 3 else 2) if mode == "stride" else 1
+        up = ((1, 2, 2) if dims == 3 else 2) if mode == "up" else 1
+        N = rng.randint(1, 3)
+        if N * math.prod(sp) * (C1 + C2) > 3_000_000:
+            continue
+        cases.append((dims, N, C1, C2, Cout, sp, k, stride, up, rng.random() < 0.3 and mode == "plain"))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_conv_cases(48, seed=20261018), ids=lambda c: "-".join(str(v) for v in c[:5]) + "-" + "x".join(map(str, c[5])))
+def test_conv_engines_agree_on_random_shapes(ops, case):
+    """Seeded shape fuzz: forward, data gradient and weight gradient of the tensor-core engines (generic per-tap, halo-reuse,
+    fused-upsample, strided, their weight-gradient counterparts) against the CUDA-core engine on the same bf16 inputs --
+    odd / ragged extents, odd counts of 64-channel blocks, concat inputs, residuals."""
+    from rho_diffusion.b200 import _lib
+    dims, N, C1, C2, Cout, sp, k, stride, up, use_res = case
+    spec = ops.ConvSpec.make(dims, k, stride, up)
+    x1 = cl(randn(N, C1, *sp, seed=50)).bfloat16()
+    x2 = cl(randn(N, C2, *sp, seed=51)).bfloat16() if C2 else None
+    w = (randn(Cout, C1 + C2, *([k] * dims), seed=52) / math.sqrt((C1 + C2) * k ** dims)).to(DEV)
+    b = (0.1 * randn(Cout, seed=53)).to(DEV)
+    holder = torch.nn.Module()
+    wp = ops.packed_weight(holder, w, torch.bfloat16)
+    aux = ops.aux_weight(holder, w, spec, x1, x2, wp, torch.bfloat16)
+    oshape = ops.conv_out_shape(x1.shape, spec, Cout)
+    res = (0.5 * torch.randn(oshape, device=DEV)).bfloat16() if use_res else None
+    y_a = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_AUTO, w_aux=aux)
+    y_s = ops.conv_forward(x1, x2, wp, b, res, spec, Cout, engine=_lib.CONV_SIMT)
+    assert rel_err(y_a, y_s) < 1.5e-2
+    assert float((y_a.float() - y_s.float()).abs().mean() / y_s.float().abs().mean()) < (5e-3 if max(spec.up) > 1 else 1e-3)
+    dy = torch.randn(oshape, device=DEV).bfloat16()
+    ga = ops.conv_backward(x1, x2, wp, dy, spec, Cout, True, True, True, tuple(w.shape), engine=_lib.CONV_AUTO)
+    gs = ops.conv_backward(x1, x2, wp, dy, spec, Cout, True, True, True, tuple(w.shape), engine=_lib.CONV_SIMT)
+    for a, s, name in zip(ga, gs, ("dx", "dx2", "dw", "db")):
+        if s is None:
+            assert a is None
+            continue
+        assert rel_err(a, s) < 2e-2, name
+        assert float((a.float() - s.float()).abs().mean() / s.float().abs().mean().clamp_min(1e-12)) < 3e-3, name
