@@ -245,6 +245,11 @@ def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     (1, 1000, 4, 64, 0),    # tcgen05 engine (bf16): 8 key tiles, ragged last tile, legacy order
     (2, 300, 2, 128, 1),    # tcgen05 engine (bf16): head dim 128, 3 key tiles
     (1, 128, 1, 64, 1),     # exactly one tile
+    (2, 1, 2, 64, 0),       # a single position (the softmax of one logit)
+    (1, 63, 2, 64, 1),      # one short of a key tile
+    (1, 65, 1, 128, 0),     # one past a key tile
+    (1, 4097, 2, 64, 1),    # 33 query blocks, one-row tail, long enough for lazy-max rescales
+    (3, 257, 4, 128, 0),    # three samples, legacy order, head dim 128, odd T
 ])
 def test_attention_fwd_bwd(ops, dtype, N, T, heads, ch, order):
     q = (lambda t: t.to(dtype).float())
