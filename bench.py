@@ -350,6 +350,13 @@ def run_b200(args):
             fused.step()
             return loss
 
+        mode = "eager"
+        if args.train_graph and world == 1:
+            # the whole step (q_sample .. fused AdamW) as one replayed CUDA graph (rho_diffusion.b200.GraphedTrainStep)
+            from rho_diffusion.b200 import GraphedTrainStep
+            graphed = GraphedTrainStep(ddpm, fused, xt, yt)
+            train_step = lambda: graphed(xt, yt)      # noqa: E731
+            mode = "cuda_graph"
         for _ in range(min(args.warmup, 2)):
             train_step()
         barrier()
@@ -360,7 +367,7 @@ def run_b200(args):
         g1.record()
         barrier()
         ms_train = g0.elapsed_time(g1)
-        train = {"ms": ms_train, "batch": Bt, "steps": args.train_steps, "loss": float(loss.detach())}
+        train = {"ms": ms_train, "batch": Bt, "steps": args.train_steps, "loss": float(loss.detach()), "mode": mode}
 
     # ---- reduce over ranks (max time)
     def max_over_ranks(v):
@@ -427,7 +434,7 @@ def run_b200(args):
         if train is not None:
             line["train"] = {"metric": "train samples/s", "value": world * train["batch"] * train["steps"] / (train["ms"] * 1e-3),
                              "unit": "samples/s", "ms_per_step": train["ms"] / train["steps"], "batch_per_gpu": train["batch"],
-                             "steps": train["steps"], "last_loss": train["loss"], "collective": "NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none"}
+                             "steps": train["steps"], "last_loss": train["loss"], "launch": train["mode"], "collective": "NCCL all-reduce of the flat fp32 gradient buffer" if world > 1 else "none"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -463,6 +470,8 @@ def main():
     ap.add_argument("--train-batch", type=int, default=int(os.environ.get("RHO_BENCH_TRAIN_BATCH", "4")))
     ap.add_argument("--ddim-steps", type=int, default=int(os.environ.get("RHO_BENCH_DDIM_STEPS", "5")),
                     help="timed steps of the GaussianDiffusionPipeline DDIM sampler (0 = skip)")
+    ap.add_argument("--no-train-graph", dest="train_graph", action="store_false",
+                    help="run the training leg eagerly instead of through GraphedTrainStep (single-GPU runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-table", default=None, help="write a per-kernel-shape table (CUDA-event times of one eager eval) to this CSV")
     args = ap.parse_args()

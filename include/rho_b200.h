@@ -294,6 +294,12 @@ typedef struct rho_adamw_params {
   int32_t step;              /* 1-based */
   float ema_decay_t;         /* d * (1 - exp(-step/2000)) */
   float grad_scale;
+  /* optional device-resident step counter (so that a CUDA graph holding the whole training step can be replayed):
+   * a 64-byte device buffer whose first int32 is the number of steps taken so far.  When non-NULL the call increments it
+   * on the device and derives the bias corrections and the EMA warm-up factor (ema_decay * (1 - exp(-step / 2000)),
+   * ema.py:33) from it; `step` and `ema_decay_t` are ignored. */
+  int32_t* step_dev;
+  float ema_decay;
 } rho_adamw_params;
 int rho_adamw_ema_step(const rho_adamw_params* p, rho_stream_t stream);
 /* stand-alone ExponentialMovingAverage.update for one tensor (ema.py:52-57): shadow -= one_minus_decay * (shadow - p) */

@@ -11,7 +11,32 @@ struct AdamScalars {
   float decay, step_size, beta1, omb1, beta2, omb2, bc2_sqrt, eps, one_minus_d, grad_scale;
 };
 
-__global__ void __launch_bounds__(256) adamw_ema_kernel(rho_adamw_params a, AdamScalars k) {
+__host__ __device__ inline AdamScalars adam_scalars(double lr, double beta1, double beta2, double eps, double wd, int step, float ema_decay_t,
+                                                    float grad_scale) {
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars k;
+  k.decay = (float)(1.0 - lr * wd);
+  k.step_size = (float)(lr / bc1);
+  k.beta1 = (float)beta1; k.omb1 = (float)(1.0 - beta1);
+  k.beta2 = (float)beta2; k.omb2 = (float)(1.0 - beta2);
+  k.bc2_sqrt = (float)sqrt(bc2);
+  k.eps = (float)eps;
+  k.one_minus_d = 1.0f - ema_decay_t;
+  k.grad_scale = grad_scale;
+  return k;
+}
+
+// device-resident step: ++step, scalars for this step -> buf + 16 bytes (one thread; doubles, like the host path)
+__global__ void adamw_scalars_kernel(rho_adamw_params a) {
+  const int step = a.step_dev[0] + 1;
+  a.step_dev[0] = step;
+  const float d_t = a.shadow ? (float)((double)a.ema_decay * (1.0 - exp(-(double)step / 2000.0))) : 0.f;
+  *reinterpret_cast<AdamScalars*>(a.step_dev + 4) = adam_scalars(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, step, d_t, a.grad_scale);
+}
+
+__global__ void __launch_bounds__(256) adamw_ema_kernel(rho_adamw_params a, AdamScalars k_host) {
+  const AdamScalars k = a.step_dev ? *reinterpret_cast<const AdamScalars*>(a.step_dev + 4) : k_host;
   const int64_t n4 = a.n >> 2;
   const float one_minus_d = k.one_minus_d;
   // torch.optim.AdamW (single-tensor form): p *= 1 - lr*wd; m.lerp_(g, 1-b1); v = b2*v + (1-b2)*g*g;
@@ -71,18 +96,15 @@ extern "C" int rho_ema_update(float* shadow, const float* p, int64_t n, float on
 }
 
 extern "C" int rho_adamw_ema_step(const rho_adamw_params* p, rho_stream_t stream) {
-  RHO_REQUIRE(p && p->p && p->g && p->m && p->v && p->n > 0 && p->step >= 1, "adamw_ema_step: bad args");
-  const double bc1 = 1.0 - pow(p->beta1, (double)p->step);
-  const double bc2 = 1.0 - pow(p->beta2, (double)p->step);
+  RHO_REQUIRE(p && p->p && p->g && p->m && p->v && p->n > 0 && (p->step >= 1 || p->step_dev), "adamw_ema_step: bad args");
   AdamScalars k;
-  k.decay = (float)(1.0 - p->lr * p->weight_decay);
-  k.step_size = (float)(p->lr / bc1);
-  k.beta1 = (float)p->beta1; k.omb1 = (float)(1.0 - p->beta1);
-  k.beta2 = (float)p->beta2; k.omb2 = (float)(1.0 - p->beta2);
-  k.bc2_sqrt = (float)sqrt(bc2);
-  k.eps = (float)p->eps;
-  k.one_minus_d = 1.0f - p->ema_decay_t;
-  k.grad_scale = p->grad_scale;
+  memset(&k, 0, sizeof(k));
+  if (p->step_dev) {
+    adamw_scalars_kernel<<<1, 1, 0, as_stream(stream)>>>(*p);
+    RHO_CHECK_LAUNCH("adamw_scalars");
+  } else {
+    k = adam_scalars(p->lr, p->beta1, p->beta2, p->eps, p->weight_decay, p->step, p->ema_decay_t, p->grad_scale);
+  }
   int blocks = (int)std::min<int64_t>(ceil_div(p->n / 4 + 1, 256), (int64_t)sm_count() * 8);
   adamw_ema_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p, k);
   RHO_CHECK_LAUNCH("adamw_ema_step");

@@ -23,7 +23,7 @@ from rho_diffusion.utils import ddp_setup  # noqa: F401  (re-export: the backend
 
 from . import _lib, ops  # noqa: F401
 
-__all__ = ["optimize", "ddp_setup", "FusedAdamW", "set_compute_dtype", "is_available"]
+__all__ = ["optimize", "ddp_setup", "FusedAdamW", "GraphedTrainStep", "set_compute_dtype", "is_available"]
 
 
 def is_available() -> bool:
@@ -82,6 +82,7 @@ class FusedAdamW:
         self.flat_shadow = self.flat_p.clone() if self.ema_decay > 0 else None
         self._bind_grads()
         self.step_id = 0
+        self.step_dev = None          # set by enable_device_step(): the step counter lives on the device (graph replay)
         ops.bump_weights_epoch()
 
     @classmethod
@@ -129,6 +130,18 @@ class FusedAdamW:
             out[k] = self.flat_shadow[hit[0]:hit[0] + v.numel()].view_as(v).clone() if hit else v.clone()
         return out
 
+    def enable_device_step(self):
+        """Moves the step counter to device memory so that ``step()`` can be captured in a CUDA graph and replayed: the
+        kernel increments it and derives the bias corrections / EMA warm-up factor itself."""
+        if self.step_dev is None:
+            self.step_dev = torch.zeros(16, dtype=torch.int32, device=self.flat_p.device)
+            self.step_dev[0] = self.step_id
+        return self
+
+    @property
+    def steps_taken(self) -> int:
+        return int(self.step_dev[0]) if self.step_dev is not None else self.step_id
+
     @torch.no_grad()
     def step(self):
         g = self.param_groups[0]
@@ -141,7 +154,76 @@ class FusedAdamW:
         self.step_id += 1
         d_t = self.ema_decay * (1.0 - math.exp(-self.step_id / 2000.0)) if self.flat_shadow is not None else 0.0
         ops.adamw_ema_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_shadow, self.step_id, g["lr"], g["betas"],
-                           g["eps"], g["weight_decay"], ema_decay_t=d_t, grad_scale=1.0 / world)
+                           g["eps"], g["weight_decay"], ema_decay_t=d_t, grad_scale=1.0 / world, step_dev=self.step_dev,
+                           ema_decay=self.ema_decay)
+
+
+class GraphedTrainStep:
+    """One whole training step -- q_sample, UNet forward, loss, backward, gradient gather (and all-reduce), fused
+    AdamW(+EMA) -- captured ONCE in a CUDA graph and replayed: ~1500 kernel launches and the Python autograd walk per step
+    become one ``cudaGraphLaunch``.  The per-step inputs live in static buffers: the batch, the labels, the timesteps (drawn
+    on the CPU generator like ``random_timesteps``, abstract_diffusion.py:163-169) and the noise (one Philox launch outside
+    the graph, so every step sees fresh noise).
+
+        step = GraphedTrainStep(model, optimizer, example_data, example_labels)
+        for data, labels in loader:
+            loss = step(data, labels)          # a 0-d device tensor, valid until the next call
+
+    Semantics are those of ``optimizer.zero_grad(); loss = model.training_step([data, labels]); loss.backward();
+    optimizer.step()`` (tests/test_gpu_model.py::test_graphed_train_step_matches_eager)."""
+
+    def __init__(self, pipeline, optimizer: "FusedAdamW", data: torch.Tensor, labels: torch.Tensor = None, warmup: int = 2):
+        self.pipeline, self.optimizer = pipeline, optimizer
+        dev = data.device
+        self.data = data.clone()
+        self.labels = labels.clone() if labels is not None else None
+        self.t = torch.zeros((data.shape[0],), dtype=torch.int64, device=dev)
+        self.noise = torch.zeros(data.shape, dtype=torch.float32, device=dev)
+        self._t_pin = torch.zeros((data.shape[0],), dtype=torch.int64).pin_memory()
+        optimizer.enable_device_step()
+        self._draw()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):           # allocator pools, packed-weight caches, kernel attributes
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.steps = warmup                   # optimizer steps already taken by the warm-up
+
+    def _batch(self):
+        return [self.data, self.labels] if self.labels is not None else self.data
+
+    def _body(self):
+        self.optimizer.zero_grad()
+        loss = self.pipeline.training_step(self._batch(), t=self.t, noise=self.noise)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _draw(self):
+        self._t_pin.copy_(self.pipeline.random_timesteps(self.data.shape[0]))
+        self.t.copy_(self._t_pin, non_blocking=True)
+        fresh = self.pipeline.noise(self.data)
+        self.noise.copy_(fresh)
+
+    def __call__(self, data: torch.Tensor, labels: torch.Tensor = None, t: torch.Tensor = None, noise: torch.Tensor = None):
+        self.data.copy_(data, non_blocking=True)
+        if self.labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+        if t is None or noise is None:
+            self._draw()
+        if t is not None:
+            self.t.copy_(t, non_blocking=True)
+        if noise is not None:
+            self.noise.copy_(noise, non_blocking=True)
+        self.graph.replay()
+        self.steps += 1
+        ops.bump_weights_epoch()              # eager users of the modules (sampling, eval) must re-pack the new weights
+        return self.loss
 
 
 def optimize(model: nn.Module, optimizer=None, dtype: torch.dtype = torch.bfloat16, ema_decay: float = 0.0, engine: int = 0,

@@ -86,7 +86,7 @@ class AdamWParams(C.Structure):
     _fields_ = [
         ("p", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("shadow", c_vp), ("n", c_i64),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
-        ("step", c_i32), ("ema_decay_t", c_f32), ("grad_scale", c_f32),
+        ("step", c_i32), ("ema_decay_t", c_f32), ("grad_scale", c_f32), ("step_dev", c_vp), ("ema_decay", c_f32),
     ]
 
 

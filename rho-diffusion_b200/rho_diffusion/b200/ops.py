@@ -682,11 +682,13 @@ class MseLossFn(torch.autograd.Function):
         return g, None
 
 
-def adamw_ema_step(p, g, m, v, shadow, step, lr, betas, eps, weight_decay, ema_decay_t=0.0, grad_scale=1.0):
+def adamw_ema_step(p, g, m, v, shadow, step, lr, betas, eps, weight_decay, ema_decay_t=0.0, grad_scale=1.0, step_dev=None, ema_decay=0.0):
+    """``step_dev``: optional 16-element int32 device tensor holding the step count (graph-replayable form, see rho_b200.h)."""
     a = L.AdamWParams()
     a.p, a.g, a.m, a.v, a.shadow, a.n = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ptr(shadow), p.numel()
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, betas[0], betas[1], eps, weight_decay
     a.step, a.ema_decay_t, a.grad_scale = step, ema_decay_t, grad_scale
+    a.step_dev, a.ema_decay = ptr(step_dev), ema_decay
     L.check(L.lib().rho_adamw_ema_step(C.byref(a), stream()), "adamw_ema_step")
     bump_weights_epoch()
 

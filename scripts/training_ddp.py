@@ -43,6 +43,8 @@ def main():
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--num-workers", type=int, default=8)
     parser.add_argument("--save", default="model.pth", help="checkpoint file written by rank 0 at the end")
+    parser.add_argument("--cuda-graph", action="store_true",
+                        help="capture the whole step in a CUDA graph (single process; drops the last partial batch)")
     args = parser.parse_args()
 
     from rho_diffusion import b200 as accel          # raises loudly if the CUDA extension is missing on a GPU box
@@ -60,7 +62,8 @@ def main():
         sampler = torch.utils.data.distributed.DistributedSampler(dataset=dset, num_replicas=world, rank=rank)
         loader = DataLoader(dset, batch_size=config.training.batch_size, sampler=sampler, num_workers=args.num_workers, pin_memory=True)
     else:
-        loader = DataLoader(dset, batch_size=config.training.batch_size, shuffle=True, num_workers=args.num_workers, pin_memory=True)
+        loader = DataLoader(dset, batch_size=config.training.batch_size, shuffle=True, num_workers=args.num_workers, pin_memory=True,
+                            drop_last=args.cuda_graph)
 
     param_space_embeddings = parameter_space_to_embeddings(config.inference.parameter_space).to(device)
     model = diffusion.DDPM(backbone=config.model.name, backbone_kwargs=config.model.kwargs, schedule=schedule,
@@ -75,14 +78,19 @@ def main():
                                       ema_decay=config.training.ema_decay)
     model.train()
 
-    steps, t0 = 0, time.time()
+    steps, t0, graphed = 0, time.time(), None
     for epoch in range(args.epochs):
         for step, data in enumerate(loader):
             inputs, labels = data[0].to(device, non_blocking=True), data[1].to(device, non_blocking=True)
-            optimizer.zero_grad()
-            loss = model.training_step([inputs, labels])
-            loss.backward()
-            optimizer.step()
+            if args.cuda_graph and world == 1:
+                if graphed is None:
+                    graphed = accel.GraphedTrainStep(model, optimizer, inputs, labels)
+                loss = graphed(inputs, labels)
+            else:
+                optimizer.zero_grad()
+                loss = model.training_step([inputs, labels])
+                loss.backward()
+                optimizer.step()
             steps += 1
             if rank == 0 and (step % 10 == 0 or steps == args.max_steps):
                 print("Epoch: %d/%d, NP: %d, step: %d, loss: %.5f, %.1f samples/s" % (
