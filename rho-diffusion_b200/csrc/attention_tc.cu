@@ -32,8 +32,8 @@ struct AttnTcParams {
   float scale;               // ch^-1/2
 };
 
-template <int CH, int POLY_MASK>
-__global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
+template <int CH, int POLY_MASK, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 320 : 192, CH == 64 ? 2 : 1)
     attn_tc_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap kv_map, const AttnTcParams p,
                    bf16* __restrict__ out, float* __restrict__ lse) {
   constexpr int KB = CH / 64;                   // 64-channel K blocks of Q / K, N atoms of V
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
   uint8_t* sP = sV + 2 * KV_BYTES;              // [2 buffers]
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_ready[2], p_ready[2], o_done, o_final;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float sL[2][AT_BM];                // SPLIT: the two column halves' partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, n = blockIdx.z;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       mbar_init(&s_ready[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], SPLIT ? 256 : 128);
     }
     mbar_init(&o_done, 1);
     mbar_init(&o_final, 1);
@@ -146,6 +147,127 @@ __global__ void __launch_bounds__(192, CH == 64 ? 2 : 1)
       }
       __syncwarp();
     }
+  } else if constexpr (SPLIT) {
+    // ===== softmax / correction / epilogue, TWO threads per query row (warps 2-5: S columns [0, 32), warps 6-9: [32, 64)):
+    // twice the warps keep the MUFU busy while partner warps sit in TMEM loads, fences and barrier waits.  Both threads of
+    // a row reduce the FULL row maximum (the other half of S is loaded for that alone), so they take identical rescale
+    // decisions without talking to each other; the row sum is kept in two halves and joined once, in the epilogue.
+    const int half = (warp - 2) >> 2;
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+    constexpr float AT_TAU = 8.0f;
+    constexpr int OC = CH / 2;                    // O columns owned by this thread: [half * OC, +OC)
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      mbar_wait(&s_ready[s], (uint32_t)(j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_s + (uint32_t)(s * AT_BN);
+      uint8_t* pbuf = sP + s * P_TILE;
+      const int kvalid = p.T - j * AT_BN;
+      const bool full = kvalid >= AT_BN;
+      uint32_t v[32], u[32];
+      tmem_ld32_async(ts + lane_addr + (uint32_t)(half * 32), v);
+      tmem_ld32_async(ts + lane_addr + (uint32_t)((half ^ 1) * 32), u);
+      tmem_wait_ld();
+      const int c = half * 32, co = (half ^ 1) * 32;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[e]), __uint_as_float(u[e])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[e + 1]), __uint_as_float(u[e + 1])));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          mx0 = fmaxf(mx0, c + e < kvalid ? __uint_as_float(v[e]) : -INFINITY);
+          mx1 = fmaxf(mx1, co + e < kvalid ? __uint_as_float(u[e]) : -INFINITY);
+        }
+      }
+      const float mx = fmaxf(mx0, mx1);
+      if (j == 0) {
+        m = mx;
+      } else if (__any_sync(0xffffffffu, (mx - m) * p.scale_log2 > AT_TAU)) {
+        // a row of this warp outgrew the stale max by more than 2^AT_TAU: rescale this thread's half of the O row once
+        // every PV issued so far (tiles < j) has completed (the partner warp takes the same branch for the other half)
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx((m - m_new) * p.scale_log2);
+        mbar_wait(&o_done, (uint32_t)(j - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < OC; cc += 32) {
+          uint32_t w[32];
+          tmem_ld32(tmem_o + lane_addr + (uint32_t)(half * OC + cc), w);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) w[e] = __float_as_uint(__uint_as_float(w[e]) * alpha);
+          tmem_st32(tmem_o + lane_addr + (uint32_t)(half * OC + cc), w);
+        }
+        l *= alpha;
+        m = m_new;
+      }
+      const float mb = m * p.scale_log2;
+      const uint64_t negmb2 = pack2(-mb, -mb);
+      uint64_t ls01 = 0ull, ls23 = 0ull;
+      uint32_t packed[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const uint64_t x2 = fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), scale2, negmb2);
+        float x0, x1;
+        unpack2(x2, x0, x1);
+        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        if (!full) {
+          p0 = c + e < kvalid ? p0 : 0.f;
+          p1 = c + e + 1 < kvalid ? p1 : 0.f;
+        }
+        const uint64_t p2 = pack2(p0, p1);
+        if (e & 2) ls23 = add2(ls23, p2); else ls01 = add2(ls01, p2);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      uint8_t* rowp = pbuf + r * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int chunk = (half * 4 + i) ^ (r & 7);
+        *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      }
+      float a0, a1, a2, a3;
+      unpack2(ls01, a0, a1);
+      unpack2(ls23, a2, a3);
+      l += (a0 + a1) + (a2 + a3);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[s]);
+    }
+    // ---- epilogue: join the two halves of the row sum, then O / l -> bf16 -> global (each thread its OC columns)
+    sL[half][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float ltot = sL[0][r] + sL[1][r];
+    mbar_wait(&o_final, 0);
+    tc_fence_after();
+    const int q = q0 + r;
+    const float inv = 1.0f / ltot;
+    bf16* orow = out + ((long long)n * p.T + q) * p.C + h * CH + half * OC;
+#pragma unroll 1
+    for (int cc = 0; cc < OC; cc += 32) {
+      uint32_t w[32];
+      tmem_ld32(tmem_o + lane_addr + (uint32_t)(half * OC + cc), w);
+      if (q < p.T) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          __nv_bfloat162 h2;
+          h2 = __floats2bfloat162_rn(__uint_as_float(w[e]) * inv, __uint_as_float(w[e + 1]) * inv); o.x = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(w[e + 2]) * inv, __uint_as_float(w[e + 3]) * inv); o.y = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(w[e + 4]) * inv, __uint_as_float(w[e + 5]) * inv); o.z = *reinterpret_cast<uint32_t*>(&h2);
+          h2 = __floats2bfloat162_rn(__uint_as_float(w[e + 6]) * inv, __uint_as_float(w[e + 7]) * inv); o.w = *reinterpret_cast<uint32_t*>(&h2);
+          *reinterpret_cast<uint4*>(orow + cc + e) = o;
+        }
+      }
+    }
+    if (half == 0 && lse && q < p.T) lse[((long long)n * p.heads + h) * p.T + q] = m * p.scale + logf(ltot);
   } else {
     // ===== softmax / correction / epilogue: thread <-> query row =====
     const int lane_base = 32 * (warp & 3);
@@ -322,11 +444,11 @@ bool attention_fwd_tc_supported(const rho_attn_params* p) {
   return get_encode() != nullptr;
 }
 
-template <int CH, int POLY_MASK>
+template <int CH, int POLY_MASK, bool SPLIT>
 static int launch_attn_tc(const CUtensorMap& qmap, const CUtensorMap& kvmap, const AttnTcParams& ap, const rho_attn_params* p, cudaStream_t st) {
   constexpr int KB = CH / 64;
   constexpr size_t SMEM = (size_t)KB * 16384 + 4 * (size_t)KB * 8192 + 2 * 16384 + 1024;
-  auto kern = attn_tc_kernel<CH, POLY_MASK>;
+  auto kern = attn_tc_kernel<CH, POLY_MASK, SPLIT>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -334,7 +456,7 @@ static int launch_attn_tc(const CUtensorMap& qmap, const CUtensorMap& kvmap, con
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div(p->T, AT_BM), p->heads, p->N);
-  kern<<<grid, 192, SMEM, st>>>(qmap, kvmap, ap, (bf16*)p->out, p->lse);
+  kern<<<grid, SPLIT ? 320 : 192, SMEM, st>>>(qmap, kvmap, ap, (bf16*)p->out, p->lse);
   RHO_CHECK_LAUNCH("attention_fwd_tcgen05");
   return RHO_OK;
 }
@@ -366,15 +488,24 @@ int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
   // stays 0 (all exponentials on the MUFU); the hook is kept for re-tuning.
   static int poly = -1;
   if (poly < 0) { const char* e = getenv("RHO_ATTN_POLY"); poly = e ? atoi(e) : 0; }
-  if (p->ch == 64) {
-    if (poly == 0) return launch_attn_tc<64, 0x00>(map, kvmap, ap, p, st);
-    if (poly == 2) return launch_attn_tc<64, 0x22>(map, kvmap, ap, p, st);
-    if (poly == 4) return launch_attn_tc<64, 0xAA>(map, kvmap, ap, p, st);
-    if (poly == 3) return launch_attn_tc<64, 0x4A>(map, kvmap, ap, p, st);
-    return launch_attn_tc<64, 0x00>(map, kvmap, ap, p, st);
+  // two threads per query row (320-thread CTAs): RHO_ATTN_SPLIT = 1 | 0.  Measured on B200 (T = 16384, ch = 64, N = 8): 687 vs
+  // 724 TFLOP/s for the one-thread-per-row kernel, 153.6 vs 156.9 evals/s end to end -- the sweep is MUFU-bound, more warps
+  // only add the second row-max reduction and TMEM reads.  Default off; kept as a tuning hook.
+  static int split = -1;
+  if (split < 0) { const char* e = getenv("RHO_ATTN_SPLIT"); split = e ? atoi(e) : 0; }
+  if (split && poly == 0) {
+    if (p->ch == 64) return launch_attn_tc<64, 0x00, true>(map, kvmap, ap, p, st);
+    return launch_attn_tc<128, 0x00, true>(map, kvmap, ap, p, st);
   }
-  if (poly != 0) return launch_attn_tc<128, 0x22>(map, kvmap, ap, p, st);
-  return launch_attn_tc<128, 0x00>(map, kvmap, ap, p, st);
+  if (p->ch == 64) {
+    if (poly == 0) return launch_attn_tc<64, 0x00, false>(map, kvmap, ap, p, st);
+    if (poly == 2) return launch_attn_tc<64, 0x22, false>(map, kvmap, ap, p, st);
+    if (poly == 4) return launch_attn_tc<64, 0xAA, false>(map, kvmap, ap, p, st);
+    if (poly == 3) return launch_attn_tc<64, 0x4A, false>(map, kvmap, ap, p, st);
+    return launch_attn_tc<64, 0x00, false>(map, kvmap, ap, p, st);
+  }
+  if (poly != 0) return launch_attn_tc<128, 0x22, false>(map, kvmap, ap, p, st);
+  return launch_attn_tc<128, 0x00, false>(map, kvmap, ap, p, st);
 }
 
 }  // namespace rho
