@@ -1,0 +1,121 @@
+"""Two-GPU NCCL run of the data-parallel trainer and the batch-sharded sampler (skipped on single-GPU boxes).
+
+Invariants checked: after K steps on DIFFERENT data shards every rank holds bit-identical weights (the flat-gradient
+all-reduce + identical fused AdamW), those weights equal a single-process run on the concatenated batch to fp32 rounding
+(mean of the shard gradients == gradient of the mean loss), and the sharded sampler of rank r reproduces rows
+[lo_r, hi_r) of the unsharded batch."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import PKG, ROOT  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(device):
+    from oracle.cases import UNET_CASES
+    from oracle.synth import synth_state_dict
+    from rho_diffusion.b200 import optimize
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    spec = UNET_CASES["film3d"]
+    ddpm = DDPM("UNetv2", dict(spec["kwargs"]), LinearSchedule(50, 1e-3, 0.02), "MSELoss", timesteps=50, optimizer="AdamW",
+                opt_kwargs={"lr": 1e-4})
+    manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+    ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+    ddpm = ddpm.to(device)
+    return ddpm, spec
+
+
+def _data(spec, n):
+    from oracle.synth import synth_input
+    x = synth_input("multi.x", (n, *spec["x_shape"][1:]), kind="rand")
+    y = synth_input("multi.y", (n, 128), kind="rand")
+    g = torch.Generator().manual_seed(9)
+    steps = [(torch.randint(0, 50, (n,), generator=g), torch.randn((n, *spec["x_shape"][1:]), generator=g)) for _ in range(3)]
+    return x, y, steps
+
+
+def _train(ddpm, fused, x, y, steps, rows, device):
+    ddpm.train()
+    for t, noise in steps:
+        fused.zero_grad()
+        loss = ddpm.training_step([x[rows].to(device), y[rows].to(device)], t=t[rows], noise=noise[rows].to(device))
+        loss.backward()
+        fused.step()
+    return fused.flat_p.detach().cpu().clone()
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update({"WORLD_SIZE": str(world), "RANK": str(rank), "LOCAL_RANK": str(rank), "MASTER_ADDR": "127.0.0.1",
+                       "MASTER_PORT": str(port)})
+    os.environ.pop("PMI_SIZE", None)
+    import torch.distributed as dist
+    from rho_diffusion.b200 import optimize
+    from rho_diffusion.b200.sampler import shard_range
+    from rho_diffusion.utils import ddp_setup
+    w, r, lr = ddp_setup(port=port)
+    device = torch.device("cuda", lr)
+    torch.cuda.set_device(device)
+    ddpm, spec = _build(device)
+    x, y, steps = _data(spec, 4)
+    opt = ddpm.configure_optimizers(1)["optimizer"]        # lr NOT scaled: compare with the single-process run below
+    ddpm, fused = optimize(ddpm, optimizer=opt, dtype=torch.float32)
+    lo, hi = shard_range(4, w, r)
+    flat = _train(ddpm, fused, x, y, steps, slice(lo, hi), device)
+    # sharded sampling: rank r's slice of the batch with per-step shared noise
+    ddpm.eval()
+    g = torch.Generator().manual_seed(3)
+    x_init = torch.randn((4, *spec["x_shape"][1:]), generator=g)
+    noises = {t: torch.randn((4, *spec["x_shape"][1:]), generator=g) for t in range(50)}
+    res = ddpm.reverse_process(torch.zeros((hi - lo, *spec["x_shape"][1:]), device=device), conditions=y[lo:hi].to(device),
+                               x_init=x_init[lo:hi].to(device), noises={t: z[lo:hi] for t, z in noises.items()}, num_steps=8)
+    out[rank] = (flat, res["denoised"].cpu(), lo, hi)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_two_gpu_data_parallel_training_and_sharded_sampling():
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    flat0, den0, lo0, hi0 = out[0]
+    flat1, den1, lo1, hi1 = out[1]
+    assert torch.equal(flat0, flat1)                                  # replicas stay bit-identical
+    # single process, whole batch, same (t, noise): the data-parallel result to fp32 rounding
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from rho_diffusion.b200 import optimize
+    device = torch.device("cuda", 0)
+    ddpm, spec = _build(device)
+    x, y, steps = _data(spec, 4)
+    opt = ddpm.configure_optimizers(1)["optimizer"]
+    ddpm, fused = optimize(ddpm, optimizer=opt, dtype=torch.float32)
+    flat = _train(ddpm, fused, x, y, steps, slice(0, 4), device)
+    # AdamW's first steps are ~ lr * sign(g): elements with |g| ~ eps amplify fp32 summation-order noise to a fraction of lr,
+    # so bound the max by a fraction of 3 * lr and the mean tightly
+    assert (flat - flat0).abs().max() < 0.2 * 3 * 1e-4 and (flat - flat0).abs().mean() < 2e-7
+    ddpm.eval()
+    g = torch.Generator().manual_seed(3)
+    x_init = torch.randn((4, *spec["x_shape"][1:]), generator=g)
+    noises = {t: torch.randn((4, *spec["x_shape"][1:]), generator=g) for t in range(50)}
+    # the sampler of the single-process model uses ITS weights; sharded runs used flat0 == flat1 ~= flat
+    full = ddpm.reverse_process(torch.zeros((4, *spec["x_shape"][1:]), device=device), conditions=y.to(device), x_init=x_init.to(device),
+                                noises=noises, num_steps=8)["denoised"].cpu()
+    assert (full[lo0:hi0] - den0).abs().max() < 1e-4 and (full[lo1:hi1] - den1).abs().max() < 1e-4
