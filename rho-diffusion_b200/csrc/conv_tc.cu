@@ -300,11 +300,28 @@ static int pick_block_k(int C1, int C2) {
   }
   return 0;
 }
+// N tile for a launch with `tiles` M tiles: the widest tile that still gives the grid ~2/3 of the SMs (deep UNet levels at
+// batch 1-2 have only 32-128 M tiles), never narrower than 64 when a 64-multiple divides Cout
+static int pick_block_n_for_grid(int Cout, long long tiles);
+
 static int pick_block_n(int Cout) {
   for (int bn : {256, 128, 64, 32}) {
     if (Cout % bn == 0) return bn;
   }
   return 0;
+}
+
+static int pick_block_n_for_grid(int Cout, long long tiles) {
+  const int widest = pick_block_n(Cout);
+  if (widest <= 64) return widest;
+  const long long want = (long long)sm_count() * 2 / 3;
+  int best = widest;
+  for (int bn : {256, 128, 64}) {
+    if (bn > widest || Cout % bn != 0) continue;
+    best = bn;
+    if (tiles * (Cout / bn) >= want) break;
+  }
+  return best;
 }
 
 struct ActView {
@@ -594,13 +611,21 @@ int conv_fwd_tc_stats_rows(const ConvGeom& g, const rho_conv_params* p) {
 }
 
 int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
-  const int bk = pick_block_k(g.C1, g.C2), bn = pick_block_n(g.Cout);
+  const int bk = pick_block_k(g.C1, g.C2);
+  int bn = pick_block_n(g.Cout);
   TcParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.N = g.N;
   tp.os_d = tp.os_h = tp.os_w = 1;
   tp.Do = g.Do; tp.Ho = g.Ho; tp.Wo = g.Wo;
   tp.Cout = g.Cout; tp.C1 = g.C1; tp.C2 = g.C2;
+  {
+    // grid-aware N tile (same tile shape for every launch of this conv: the class grid of a fused upsample is g.D/H/W)
+    TcParams probe = tp;
+    if (is_upsampled(g)) { probe.Gd = g.D; probe.Gh = g.H; probe.Gw = g.W; } else { probe.Gd = g.Do; probe.Gh = g.Ho; probe.Gw = g.Wo; }
+    pick_tile(probe);
+    bn = pick_block_n_for_grid(g.Cout, (long long)probe.tiles_w * probe.tiles_h * probe.tiles_d * probe.tiles_n);
+  }
   tp.n_blocks = g.Cout / bn;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -779,7 +804,8 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
     RHO_CHECK_LAUNCH("pack_dgrad");
   }
   const bool up = is_upsampled(g);
-  const int bk = pick_block_k(g.Cout, 0), bn = pick_block_n(g.Cin);
+  const int bk = pick_block_k(g.Cout, 0);
+  int bn = pick_block_n(g.Cin);
   TcParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.N = g.N;
@@ -787,6 +813,11 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   tp.os_d = tp.os_h = tp.os_w = 1;
   tp.Do = g.Du; tp.Ho = g.Hu; tp.Wo = g.Wu;
   tp.Cout = g.Cin; tp.C1 = g.Cout; tp.C2 = 0;
+  if (!is_strided(g)) {
+    TcParams probe = tp;
+    pick_tile(probe);
+    bn = pick_block_n_for_grid(g.Cin, (long long)probe.tiles_w * probe.tiles_h * probe.tiles_d * probe.tiles_n);
+  }
   tp.n_blocks = g.Cin / bn;
   tp.out_split = (!up && g.C2 > 0) ? g.C1 : 0;
   if (is_strided(g)) {
