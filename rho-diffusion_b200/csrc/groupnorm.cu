@@ -738,6 +738,56 @@ __global__ void __launch_bounds__(256) gn_stats_from_partials_kernel(const float
   }
 }
 
+// small-work variant (few tiles per sample: many-sample 1-D / 2-D batches): one WARP per (sample, group), eight per CTA; lanes
+// stride over the (row, channel) pairs, then a fixed xor-shuffle tree in double
+__global__ void __launch_bounds__(256) gn_stats_from_partials_warp_kernel(const float* __restrict__ part1, int rows1, int C1,
+                                                                          const float* __restrict__ part2, int rows2, int C2, int64_t S,
+                                                                          int G, int NG, float eps, float* __restrict__ stats) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= NG) return;
+  const int n = i / G, g = i - n * G;
+  const int cpg = (C1 + C2) / G;
+  const int c_lo = g * cpg, c_hi = c_lo + cpg;
+  double s1 = 0.0, s2 = 0.0;
+  {
+    const int a = min(c_lo, C1), b = min(c_hi, C1);
+    if (b > a) {
+      const int w = b - a;
+      const float* base = part1 + ((int64_t)n * rows1 * C1 + a) * 2;
+      for (int k = lane; k < rows1 * w; k += 32) {
+        const int r = k / w, c = k - r * w;
+        const float2 v = *reinterpret_cast<const float2*>(base + ((int64_t)r * C1 + c) * 2);
+        s1 += (double)v.x; s2 += (double)v.y;
+      }
+    }
+  }
+  {
+    const int a = max(c_lo, C1) - C1, b = max(c_hi, C1) - C1;
+    if (b > a && part2) {
+      const int w = b - a;
+      const float* base = part2 + ((int64_t)n * rows2 * C2 + a) * 2;
+      for (int k = lane; k < rows2 * w; k += 32) {
+        const int r = k / w, c = k - r * w;
+        const float2 v = *reinterpret_cast<const float2*>(base + ((int64_t)r * C2 + c) * 2);
+        s1 += (double)v.x; s2 += (double)v.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  if (lane == 0) {
+    const double cnt = (double)S * cpg;
+    const double mean = s1 / cnt;
+    const double var = fmax(s2 / cnt - mean * mean, 0.0);
+    stats[(int64_t)i * 2] = (float)mean;
+    stats[(int64_t)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 static int gn_chunks8(int N, int64_t S, int C) {
   const int rows = GN_THREADS / (C >> 3);
   int64_t target = (int64_t)sm_count() * 4;          // one resident wave: 4 CTAs per SM
@@ -1012,8 +1062,16 @@ int rho_gn_stats_from_partials(const rho_gn_params* p, const float* part1, int32
   RHO_REQUIRE((p->C2 == 0) || (part2 && rows2 > 0), "gn_stats_from_partials: no statistics for x2");
   RHO_REQUIRE(p->pre_add == nullptr, "gn_stats_from_partials: pre_add changes the per-group sums; use rho_gn_stats");
   RHO_REQUIRE(p->N <= 65535, "gn_stats_from_partials: N too large");
-  gn_stats_from_partials_kernel<<<dim3(p->groups, p->N), 256, 0, as_stream(stream)>>>(part1, rows1, p->C1, part2, rows2, p->C2, p->S, p->groups,
-                                                                                      p->eps, p->stats);
+  const int cpg = (p->C1 + p->C2) / p->groups;
+  const long long work = (long long)std::max(rows1, rows2) * cpg;        // (row, channel) pairs per (sample, group)
+  if (work <= 1024) {
+    const int NG = p->N * p->groups;
+    gn_stats_from_partials_warp_kernel<<<(NG * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(part1, rows1, p->C1, part2, rows2, p->C2, p->S,
+                                                                                           p->groups, NG, p->eps, p->stats);
+  } else {
+    gn_stats_from_partials_kernel<<<dim3(p->groups, p->N), 256, 0, as_stream(stream)>>>(part1, rows1, p->C1, part2, rows2, p->C2, p->S,
+                                                                                        p->groups, p->eps, p->stats);
+  }
   RHO_CHECK_LAUNCH("gn_stats_from_partials");
   return RHO_OK;
 }

@@ -386,6 +386,7 @@ def test_adamw_ema_kernel(ops):
     (1, 2, 256, 256, (300,), 1, 1, 1, True, True),               # attention proj_out (k = 1) + residual
     (2, 3, 64, 512, (24, 16), 3, 1, 1, False, True),             # two 256-channel blocks per tile
     (3, 2, 64, 64, (2, 4, 4), 3, 1, 1, False, False),            # 32 positions per sample: tiles straddle samples -> not fused
+    (3, 1, 64, 256, (4, 64, 65), 3, 1, 1, False, True),          # > 1024 (tile, channel) pairs per group: the CTA-wide merge kernel
 ])
 def test_conv_epilogue_groupnorm_statistics(ops, case):
     """The (mean, rstd) GroupNorm32 obtains from the channel sums a conv epilogue leaves behind equal those of the

@@ -50,3 +50,37 @@ for name, (kw, shape, batches, sp) in CONFIGS.items():
         print(f"{name}: batch {B:4d}  {ms:8.3f} ms/step  {B / ms * 1e3:9.1f} evals/s", flush=True)
         del s
     del ddpm
+
+if len(sys.argv) > 1 and sys.argv[1] == "table":
+    # per-kernel-shape table (CUDA events around every conv / GN / attention launch of one eager eval)
+    from rho_diffusion.b200 import ops
+    for name, (kw, shape, batches, sp) in CONFIGS.items():
+        if not name.startswith(tuple(sys.argv[2:] or ["B", "C"])):
+            continue
+        T = 1000
+        extra = dict(cond_fn="MultiEmbeddings", cond_fn_kwargs={"parameter_space": sp, "embedding_dim": 4 * kw["model_channels"]}) if sp else {}
+        ddpm = DDPM("UNetv2", dict(kw), LinearSchedule(T, 1e-3, 0.02), "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4}, **extra)
+        manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+        ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=777))
+        ddpm = set_compute_dtype(ddpm.to(dev).eval(), torch.bfloat16)
+        B = batches[-1]
+        cond = torch.tensor([[0.5, 1.0, 400.0 + 5 * (i % 21), 0.0] for i in range(B)], device=dev) if sp else \
+            synth_input("cfg.y", (B, 4 * kw["model_channels"]), kind="rand").to(dev)
+        x = synth_input("cfg.x", (B, *shape)).to(dev)
+        tt = torch.full((B,), 500, dtype=torch.int64, device=dev)
+        with torch.inference_mode():
+            for _ in range(2):
+                ddpm.backbone(x, tt, cond)
+            torch.cuda.synchronize()
+            ops.profiler = ops.KernelProfiler()
+            ddpm.backbone(x, tt, cond)
+            ops.profiler.summary()
+            rows = {}
+            for kind, nm, flops, nbytes, s0, s1 in ops.profiler.records:
+                r = rows.setdefault((kind, nm), [0, 0.0, 0.0, 0.0])
+                r[0] += 1; r[1] += s0.elapsed_time(s1); r[2] += flops; r[3] += nbytes
+            ops.profiler = None
+        tot = sum(r[1] for r in rows.values())
+        print(f"== {name} batch {B}: {tot:.3f} ms in profiled kernels")
+        for (kind, nm), r in sorted(rows.items(), key=lambda kv: -kv[1][1])[:18]:
+            print(f"  {r[1]:7.3f} ms x{r[0]:3d}  {r[2] / (r[1] * 1e-3) / 1e12 if r[1] else 0:8.1f} TFLOP/s {r[3] / (r[1] * 1e-3) / 1e9 if r[1] else 0:8.1f} GB/s  {nm}")
