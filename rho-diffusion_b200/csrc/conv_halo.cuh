@@ -40,11 +40,12 @@ struct HaloMaps {
   CUtensorMap w;
 };
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int BLOCK_K>
 __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
                                                            const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                            bf16* __restrict__ y, bf16* __restrict__ y2) {
-  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int ROW_BYTES = BLOCK_K * 2;          // one position's channels of a K block: 128 B (64 ch) or 64 B (32 ch)
+  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * MT * BLOCK_N;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   __shared__ float sstat[4][BLOCK_N][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.Cin >> 6;
+  const int KB = p.Cin / BLOCK_K;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -95,13 +96,13 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
       int nb, q0, mt_here, d, n, h_lo;
       decode(item, nb, q0, mt_here, d, n, h_lo);
       for (int kb = 0; kb < KB; ++kb) {
-        const int c = kb * 64;
+        const int c = kb * BLOCK_K;
         const int src = c >= p.C1 ? 1 : 0;
         const int cc = src ? c - p.C1 : c;
         for (int dd = 0; dd < p.kd; ++dd) {
           mbar_wait(&a_empty[sa], pha ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&a_full[sa], (uint32_t)(p.R * p.Wp * 128));
+            mbar_expect_tx(&a_full[sa], (uint32_t)(p.R * p.Wp * ROW_BYTES));
             tma_load_5d(sA + (size_t)sa * p.a_stage_bytes, &maps.a[src], &a_full[sa], cc, -1, h_lo, d + dd - p.pd, n);
           }
           __syncwarp();
@@ -139,14 +140,14 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
             const int shift = (t9 / 3 - 1) * p.Wp + (t9 % 3 - 1);
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
-            const uint64_t bdesc = at_desc_kmajor<128>(smem_u32(sB + sb * B_BYTES));
+            const uint64_t bdesc = umma_desc<ROW_BYTES>(smem_u32(sB + sb * B_BYTES));
             if (elect_one()) {
 #pragma unroll
               for (int i = 0; i < MT; ++i) {
                 if (i < mt_here) {
-                  const uint64_t adesc = at_desc_kmajor<128>(a_addr + (uint32_t)(row_base + i * 128 + shift) * 128u);
+                  const uint64_t adesc = umma_desc<ROW_BYTES>(a_addr + (uint32_t)(row_base + i * 128 + shift) * (uint32_t)ROW_BYTES);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
+                  for (int k = 0; k < BLOCK_K / 16; ++k)
                     umma_f16(tacc + (uint32_t)(i * BLOCK_N), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, !(first && k == 0));
                 }
               }
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
 // ---- host ---------------------------------------------------------------------------------------------------------
 struct HaloPlan {
   bool ok;
-  int bn, mt;
+  int bn, mt, bk;
   HaloParams p;
   size_t smem;
 };
@@ -280,10 +281,12 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   memset(&pl, 0, sizeof(pl));
   if (halo_mode() == 0 || tc_disabled()) return pl;
   if (kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return pl;
-  if (C1 % 64 != 0 || C2 % 64 != 0 || (Cout != 64 && Cout != 128)) return pl;
+  const int bk = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : ((C1 % 32 == 0 && C2 % 32 == 0) ? 32 : 0);
+  if (bk == 0 || (Cout != 32 && Cout != 64 && Cout != 128) || (Cout == 128 && bk != 64)) return pl;
   if (W < 16 || W > 255 || (long long)H * (W + 1) < 256) return pl;
   pl.bn = Cout;
-  pl.mt = Cout == 64 ? 4 : 2;
+  pl.bk = bk;
+  pl.mt = Cout == 32 ? 8 : (Cout == 64 ? 4 : 2);
   HaloParams& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Wp = W + 1;
   p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
@@ -301,10 +304,10 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   }
   if (R > 256) return pl;
   p.R = R;
-  p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * 128, 1024);
+  p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * (size_t)(2 * bk), 1024);
   const size_t budget = 227 * 1024 - 3072 /* static: barriers, bias, statistics scratch */ - 1024 /* alignment slack */ - 1024;
-  const size_t b_bytes = (size_t)pl.bn * 128;
-  p.SB = pl.bn == 64 ? 5 : 4;
+  const size_t b_bytes = (size_t)pl.bn * (size_t)(2 * bk);
+  p.SB = pl.bn <= 64 ? 5 : 4;
   long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
   if (sa < 2) return pl;
   p.SA = (int)std::min<long long>(sa, 3);
@@ -316,9 +319,9 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   return pl;
 }
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int BLOCK_K>
 static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bias, const bf16* residual, bf16* y, bf16* y2, cudaStream_t st) {
-  auto kern = conv_halo_kernel<BLOCK_N, MT>;
+  auto kern = conv_halo_kernel<BLOCK_N, MT, BLOCK_K>;
   static size_t attr_bytes = 0;
   if (pl.smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -340,7 +343,7 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
   p.stat_part = stat_part;
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const int box[5] = {64, p.Wp, p.R, 1, 1};
+  const int box[5] = {pl.bk, p.Wp, p.R, 1, 1};
   for (int s = 0; s < 2; ++s) {
     const int C = s ? p.C2 : p.C1;
     if (C == 0) continue;
@@ -348,13 +351,14 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
     v.base = s ? x2 : x;
     v.dim[0] = C; v.dim[1] = p.W; v.dim[2] = p.H; v.dim[3] = p.D; v.dim[4] = p.N;
     v.stride[0] = (long long)C * 2; v.stride[1] = v.stride[0] * p.W; v.stride[2] = v.stride[1] * p.H; v.stride[3] = v.stride[2] * p.D;
-    int rc = encode_view(&maps.a[s], v, box, 64);
+    int rc = encode_view(&maps.a[s], v, box, pl.bk);
     if (rc) return rc;
   }
-  int rc = encode_weight_map(&maps.w, w, (long long)p.kd * 9 * p.Cin, p.Cout, 64, pl.bn);
+  int rc = encode_weight_map(&maps.w, w, (long long)p.kd * 9 * p.Cin, p.Cout, pl.bk, pl.bn);
   if (rc) return rc;
-  if (pl.bn == 64) return launch_halo<64, 4>(maps, pl, bias, residual, y, y2, st);
-  return launch_halo<128, 2>(maps, pl, bias, residual, y, y2, st);
+  if (pl.bn == 32) return pl.bk == 64 ? launch_halo<32, 8, 64>(maps, pl, bias, residual, y, y2, st) : launch_halo<32, 8, 32>(maps, pl, bias, residual, y, y2, st);
+  if (pl.bn == 64) return pl.bk == 64 ? launch_halo<64, 4, 64>(maps, pl, bias, residual, y, y2, st) : launch_halo<64, 4, 32>(maps, pl, bias, residual, y, y2, st);
+  return launch_halo<128, 2, 64>(maps, pl, bias, residual, y, y2, st);
 }
 
 }  // namespace rho

@@ -165,6 +165,13 @@ CONV_CASES = [
     (3, 1, 512, 512, 512, (2, 4, 4), 3, 1, 1, False),
     (3, 1, 256, 64, 64, (2, 8, 8), 3, 1, 1, False),            # 320 = 5 K blocks
     (3, 1, 192, 0, 64, (2, 8, 8), 1, 1, 1, False),             # 1x1x1 skip conv on 3 K blocks
+    # halo-reuse kernel with 32-channel K blocks (64-byte rows, SWIZZLE_64B) and 32 output channels (the full-resolution
+    # levels of the 2-D deep-galaxy config, mc = 32)
+    (2, 3, 32, 0, 32, (40, 48), 3, 1, 1, True),
+    (2, 2, 64, 32, 32, (30, 33), 3, 1, 1, False),              # concat 64 + 32: three 32-channel K blocks
+    (2, 2, 32, 0, 64, (24, 40), 3, 1, 1, False),
+    (3, 1, 32, 0, 32, (3, 20, 24), 3, 1, 1, False),
+    (2, 1, 64, 0, 32, (128, 128), 3, 1, 1, False),             # 64-channel K block, 32 outputs, the real 128^2 plane (17 groups)
 ]
 
 
@@ -211,7 +218,7 @@ def test_conv_fwd_bwd(ops, dtype, case):
         assert rel_err(nc(resd.grad), dy) < 1e-6
 
 
-@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20, 30, 31, 32, 33, 34, 35)])
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20, 30, 31, 32, 33, 34, 35, 45, 46, 47, 48, 49)])
 def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     """The bf16 shapes above must run on the tcgen05 engine (forced: an unsupported shape would raise), and agree with
     the CUDA-core engine on the same inputs to fp32-accumulation rounding."""
@@ -387,6 +394,7 @@ def test_adamw_ema_kernel(ops):
     (2, 3, 64, 512, (24, 16), 3, 1, 1, False, True),             # two 256-channel blocks per tile
     (3, 2, 64, 64, (2, 4, 4), 3, 1, 1, False, False),            # 32 positions per sample: tiles straddle samples -> not fused
     (3, 1, 64, 256, (4, 64, 65), 3, 1, 1, False, True),          # > 1024 (tile, channel) pairs per group: the CTA-wide merge kernel
+    (2, 3, 32, 32, (40, 48), 3, 1, 1, True, True),               # 32-channel halo kernel (one channel per group)
 ])
 def test_conv_epilogue_groupnorm_statistics(ops, case):
     """The (mean, rstd) GroupNorm32 obtains from the channel sums a conv epilogue leaves behind equal those of the
