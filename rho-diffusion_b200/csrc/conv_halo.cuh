@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   constexpr int ROW_BYTES = BLOCK_K * 2;          // one position's channels of a K block: 128 B (64 ch) or 64 B (32 ch)
   constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * MT * BLOCK_N;
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two >= 32");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -286,31 +286,37 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   if (W < 16 || W > 255 || (long long)H * (W + 1) < 256) return pl;
   pl.bn = Cout;
   pl.bk = bk;
-  pl.mt = Cout == 32 ? 8 : (Cout == 64 ? 4 : 2);
   HaloParams& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Wp = W + 1;
   p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
   p.kd = kd; p.pd = kd / 2;
   p.n_blocks = 1;
   p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
-  p.groups_per_plane = (int)ceil_div(p.tiles_per_plane, pl.mt);
-  p.total_items = (long long)N * D * p.groups_per_plane * p.n_blocks;
-  int R = 0;
-  for (int g = 0; g < p.groups_per_plane; ++g) {
-    const int q0 = g * pl.mt * 128;
-    const int h_lo = (q0 + p.Wp - 1) / p.Wp - 2;
-    const int last = q0 + pl.mt * 128 - 1 + p.Wp + 1;          // highest flat row any tap of the group touches
-    R = std::max(R, last / p.Wp - h_lo + 1);
-  }
-  if (R > 256) return pl;
-  p.R = R;
-  p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * (size_t)(2 * bk), 1024);
   const size_t budget = 227 * 1024 - 3072 /* static: barriers, bias, statistics scratch */ - 1024 /* alignment slack */ - 1024;
   const size_t b_bytes = (size_t)pl.bn * (size_t)(2 * bk);
-  p.SB = pl.bn <= 64 ? 5 : 4;
-  long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
-  if (sa < 2) return pl;
-  p.SA = (int)std::min<long long>(sa, 3);
+  // tiles per work item: as many as TMEM (2 x MT x BLOCK_N <= 512 columns) and two slab stages in shared memory allow
+  bool fits = false;
+  for (int mt = 256 / Cout; mt >= 1 && !fits; mt >>= 1) {
+    pl.mt = mt;
+    p.groups_per_plane = (int)ceil_div(p.tiles_per_plane, mt);
+    int R = 0;
+    for (int g = 0; g < p.groups_per_plane; ++g) {
+      const int q0 = g * mt * 128;
+      const int h_lo = (q0 + p.Wp - 1) / p.Wp - 2;
+      const int last = q0 + mt * 128 - 1 + p.Wp + 1;          // highest flat row any tap of the group touches
+      R = std::max(R, last / p.Wp - h_lo + 1);
+    }
+    if (R > 256) continue;
+    p.R = R;
+    p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * (size_t)(2 * bk), 1024);
+    p.SB = pl.bn <= 64 ? 5 : 4;
+    const long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
+    if (sa < 2) continue;
+    p.SA = (int)std::min<long long>(sa, 3);
+    fits = true;
+  }
+  if (!fits) return pl;
+  p.total_items = (long long)N * D * p.groups_per_plane * p.n_blocks;
   // spend what is left on a deeper weight ring
   long long extra = ((long long)budget - (long long)p.SA * p.a_stage_bytes) / (long long)b_bytes;
   p.SB = (int)std::min<long long>(HALO_MAX_STAGES, std::max<long long>(p.SB, extra));
@@ -356,9 +362,15 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
   }
   int rc = encode_weight_map(&maps.w, w, (long long)p.kd * 9 * p.Cin, p.Cout, pl.bk, pl.bn);
   if (rc) return rc;
-  if (pl.bn == 32) return pl.bk == 64 ? launch_halo<32, 8, 64>(maps, pl, bias, residual, y, y2, st) : launch_halo<32, 8, 32>(maps, pl, bias, residual, y, y2, st);
-  if (pl.bn == 64) return pl.bk == 64 ? launch_halo<64, 4, 64>(maps, pl, bias, residual, y, y2, st) : launch_halo<64, 4, 32>(maps, pl, bias, residual, y, y2, st);
-  return launch_halo<128, 2, 64>(maps, pl, bias, residual, y, y2, st);
+#define RHO_HALO(BN, MT, BK) \
+  if (pl.bn == BN && pl.mt == MT && pl.bk == BK) return launch_halo<BN, MT, BK>(maps, pl, bias, residual, y, y2, st)
+  RHO_HALO(32, 8, 32); RHO_HALO(32, 4, 32); RHO_HALO(32, 2, 32); RHO_HALO(32, 1, 32);
+  RHO_HALO(32, 8, 64); RHO_HALO(32, 4, 64); RHO_HALO(32, 2, 64); RHO_HALO(32, 1, 64);
+  RHO_HALO(64, 4, 32); RHO_HALO(64, 2, 32); RHO_HALO(64, 1, 32);
+  RHO_HALO(64, 4, 64); RHO_HALO(64, 2, 64); RHO_HALO(64, 1, 64);
+  RHO_HALO(128, 2, 64); RHO_HALO(128, 1, 64);
+#undef RHO_HALO
+  return fail(RHO_ERR_UNSUPPORTED, "conv_halo: no kernel for BLOCK_N=%d MT=%d BLOCK_K=%d", pl.bn, pl.mt, pl.bk);
 }
 
 }  // namespace rho
