@@ -22,7 +22,8 @@ struct WgHaloParams {
   int N, D, H, W, Wp;
   int C1, C2, Cin, Cout;
   int kd, pd;
-  int cibs, cobs;              // 64-channel blocks of the input / output channels
+  int ck, cn;                  // channels per input / output block: 64 or 32 (32: 64-byte rows, SWIZZLE_64B)
+  int cibs, cobs;              // blocks of the input / output channels
   int units;                   // kd * cibs * cobs
   int splits;                  // CTAs per unit
   int chunks_per_plane;
@@ -36,8 +37,26 @@ struct WgHaloMaps {
   CUtensorMap dy;
 };
 
+// MN-major operand, rows of ROW_BYTES (128: SWIZZLE_128B, 64: SWIZZLE_64B), eight-row atoms contiguous
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t wgh_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
+  return d;
+}
+
+// CK input channels per unit: 64 -> an M = 128 MMA pairs two taps (WH_PAIRS groups); 32 -> it takes the three dw taps of one
+// dh (atoms one row apart) plus an unused fourth (3 groups).  CN output channels per unit (N of the MMA).
+template <int CK, int CN>
 __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const __grid_constant__ WgHaloParams p,
                                                                  float* __restrict__ partial) {
+  constexpr int XROW = CK * 2, YROW = CN * 2;
+  constexpr int GROUPS = CK == 64 ? WH_PAIRS : 3;
+  static_assert(GROUPS * CN <= 512, "accumulators exceed TMEM");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;                          // [2 stages]
@@ -53,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
   const int dd = u / p.cibs;
   const long long c_begin = (long long)split * p.chunks_per_split;
   const long long c_end = min(p.chunks_total, c_begin + p.chunks_per_split);
-  const int xc = cib * 64;
+  const int xc = cib * CK;
   const int src = xc >= p.C1 ? 1 : 0;
   const int xcc = src ? xc - p.C1 : xc;
 
@@ -93,16 +112,16 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       const int hy = q0 / p.Wp;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], (uint32_t)((p.Rx + p.Ry) * p.Wp * 128));
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.Rx * p.Wp * XROW + p.Ry * p.Wp * YROW));
         tma_load_5d(sX + (size_t)stage * p.x_bytes, &maps.x[src], &full_bar[stage], xcc, -1, hx, d + dd - p.pd, n);
-        tma_load_5d(sY + (size_t)stage * p.y_bytes, &maps.dy, &full_bar[stage], cob * 64, -1, hy, d, n);
+        tma_load_5d(sY + (size_t)stage * p.y_bytes, &maps.dy, &full_bar[stage], cob * CN, -1, hy, d, n);
       }
       __syncwarp();
       if (++stage == 2) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // D fp32, A / B bf16, both MN-major, M = 128, N = 64
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // D fp32, A / B bf16, both MN-major, M = 128, N = CN
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -118,16 +137,23 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       const uint32_t xa = smem_u32(sX + (size_t)stage * p.x_bytes), ya = smem_u32(sY + (size_t)stage * p.y_bytes);
       if (elect_one()) {
 #pragma unroll 1
-        for (int pi = 0; pi < WH_PAIRS; ++pi) {
-          const int ta = 2 * pi, tb = 2 * pi + 1;
-          const int sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
-          const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;     // unused half of the last pair: any valid rows
-          const uint32_t lbo = (uint32_t)(sb - sa) * 128u;
+        for (int gi = 0; gi < GROUPS; ++gi) {
+          int sa;
+          uint32_t lbo;
+          if (CK == 64) {
+            const int ta = 2 * gi, tb = 2 * gi + 1;
+            sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
+            const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;     // unused half of the last pair: any valid rows
+            lbo = (uint32_t)(sb - sa) * (uint32_t)XROW;
+          } else {
+            sa = (gi - 1) * p.Wp - 1;          // atoms: (dh, dw = -1), (dh, 0), (dh, +1), one unused row further
+            lbo = (uint32_t)XROW;
+          }
 #pragma unroll
           for (int k = 0; k < WH_CH / 16; ++k) {
-            const uint64_t a = wg_desc_mn(xa + (uint32_t)(xrow + sa + k * 16) * 128u, lbo);
-            const uint64_t b = wg_desc_mn(ya + (uint32_t)(yrow + k * 16) * 128u, 1024u);
-            umma_f16(tmem_base + (uint32_t)(pi * 64), a, b, idesc, !(first && k == 0));
+            const uint64_t a = wgh_desc_mn<XROW>(xa + (uint32_t)(xrow + sa + k * 16) * (uint32_t)XROW, lbo);
+            const uint64_t b = wgh_desc_mn<YROW>(ya + (uint32_t)(yrow + k * 16) * (uint32_t)YROW, 1024u);
+            umma_f16(tmem_base + (uint32_t)(gi * CN), a, b, idesc, !(first && k == 0));
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -148,27 +174,29 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
     }
     const int lane_base = 32 * (warp & 3);
     const int r = lane_base + lane;
-    const int a = r >> 6, ci = xc + (r & 63);
+    const int a = r / CK, ci = xc + (r % CK);     // atom (tap within the group) and input channel of this accumulator row
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int taps = p.kd * 9;
 #pragma unroll 1
-    for (int pi = 0; pi < WH_PAIRS; ++pi) {
-      const int t9 = 2 * pi + a;
-      if (t9 >= 9) continue;                        // warp-uniform (a is constant per warp)
-      float* dst = partial + ((((long long)split * taps + (dd * 9 + t9)) * p.Cin + ci) * p.Cout) + cob * 64;
+    for (int gi = 0; gi < GROUPS; ++gi) {
+      const int t9 = CK == 64 ? 2 * gi + a : 3 * gi + a;
+      const bool used = CK == 64 ? t9 < 9 : a < 3;                // warp-uniform (a is constant per warp)
+      float* dst = partial + ((((long long)split * taps + (dd * 9 + (used ? t9 : 0))) * p.Cin + ci) * p.Cout) + cob * CN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int c0 = 0; c0 < CN; c0 += 32) {
         uint32_t v[32];
-        if (any) tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(pi * 64 + c0), v);
+        if (any) tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(gi * CN + c0), v);
         else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
         }
+        if (used) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4*>(dst + c0 + e) =
-              make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + c0 + e) =
+                make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
       }
     }
   }
@@ -192,13 +220,16 @@ static WgHaloPlan wg_halo_plan(const ConvGeom& g) {
   if (!mode) return pl;
   const bool plain = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1;
   if (!plain || g.kh != 3 || g.kw != 3 || (g.kd != 1 && g.kd != 3)) return pl;
-  if (g.C1 % 64 != 0 || g.C2 % 64 != 0 || (g.Cout != 64 && g.Cout != 128)) return pl;
+  const int ck = (g.C1 % 64 == 0 && g.C2 % 64 == 0) ? 64 : ((g.C1 % 32 == 0 && g.C2 % 32 == 0) ? 32 : 0);
+  if (ck == 0 || (g.Cout != 32 && g.Cout != 64 && g.Cout != 128)) return pl;
+  const int cn = g.Cout == 32 ? 32 : 64;
   if (g.W < 16 || g.W > 255 || (long long)g.H * (g.W + 1) < 2 * WH_CH) return pl;
   WgHaloParams& p = pl.p;
   p.N = g.N; p.D = g.D; p.H = g.H; p.W = g.W; p.Wp = g.W + 1;
   p.C1 = g.C1; p.C2 = g.C2; p.Cin = g.Cin; p.Cout = g.Cout;
   p.kd = g.kd; p.pd = g.kd / 2;
-  p.cibs = g.Cin / 64; p.cobs = g.Cout / 64;
+  p.ck = ck; p.cn = cn;
+  p.cibs = g.Cin / ck; p.cobs = g.Cout / cn;
   p.units = p.kd * p.cibs * p.cobs;
   p.chunks_per_plane = (int)ceil_div((long long)g.H * p.Wp, WH_CH);
   p.chunks_total = (long long)g.N * g.D * p.chunks_per_plane;
@@ -216,22 +247,23 @@ static WgHaloPlan wg_halo_plan(const ConvGeom& g) {
   }
   if (Rx > 256 || Ry > 256) return pl;
   p.Rx = Rx; p.Ry = Ry;
-  p.x_bytes = (int)align_up((size_t)Rx * p.Wp * 128, 1024);
-  p.y_bytes = (int)align_up((size_t)Ry * p.Wp * 128, 1024);
+  p.x_bytes = (int)align_up((size_t)Rx * p.Wp * (size_t)(2 * ck), 1024);
+  p.y_bytes = (int)align_up((size_t)Ry * p.Wp * (size_t)(2 * cn), 1024);
   pl.smem = 2 * ((size_t)p.x_bytes + p.y_bytes) + 1024;
   if (pl.smem > 227 * 1024 - 2048) return pl;
   pl.ok = true;
   return pl;
 }
 
-static int wg_halo_encode(CUtensorMap* m, const void* base, int C, const WgHaloParams& p, int rows) {
+static int wg_halo_encode(CUtensorMap* m, const void* base, int C, const WgHaloParams& p, int rows, int cb) {
   auto enc = get_encode();
   cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
   cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * p.W, (cuuint64_t)C * 2 * p.W * p.H, (cuuint64_t)C * 2 * p.W * p.H * p.D};
-  cuuint32_t bdim[5] = {64, (cuuint32_t)p.Wp, (cuuint32_t)rows, 1, 1};
+  cuuint32_t bdim[5] = {(cuuint32_t)cb, (cuuint32_t)p.Wp, (cuuint32_t)rows, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad halo) failed: %d", (int)r);
   return RHO_OK;
 }
@@ -240,19 +272,25 @@ static int conv_wgrad_halo_run(const WgHaloPlan& pl, const ConvGeom& g, const rh
   const WgHaloParams& p = pl.p;
   WgHaloMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = wg_halo_encode(&maps.x[0], bp->fwd.x, g.C1, p, p.Rx);
-  if (!rc && g.C2) rc = wg_halo_encode(&maps.x[1], bp->fwd.x2, g.C2, p, p.Rx);
-  if (!rc) rc = wg_halo_encode(&maps.dy, bp->dy, g.Cout, p, p.Ry);
+  int rc = wg_halo_encode(&maps.x[0], bp->fwd.x, g.C1, p, p.Rx, p.ck);
+  if (!rc && g.C2) rc = wg_halo_encode(&maps.x[1], bp->fwd.x2, g.C2, p, p.Rx, p.ck);
+  if (!rc) rc = wg_halo_encode(&maps.dy, bp->dy, g.Cout, p, p.Ry, p.cn);
   if (rc) return rc;
-  static size_t attr_bytes = 0;
-  if (pl.smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_wgrad_halo: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e));
-    attr_bytes = pl.smem;
+#define RHO_WGH(CK, CN)                                                                                                       \
+  if (p.ck == CK && p.cn == CN) {                                                                                             \
+    static size_t attr_bytes = 0;                                                                                             \
+    if (pl.smem > attr_bytes) {                                                                                               \
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel<CK, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
+      if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_wgrad_halo: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e)); \
+      attr_bytes = pl.smem;                                                                                                   \
+    }                                                                                                                         \
+    conv_wgrad_halo_kernel<CK, CN><<<(unsigned)(p.units * p.splits), 192, pl.smem, st>>>(maps, p, partial);                   \
+    RHO_CHECK_LAUNCH("conv_wgrad_halo_tcgen05");                                                                              \
+    return RHO_OK;                                                                                                            \
   }
-  conv_wgrad_halo_kernel<<<(unsigned)(p.units * p.splits), 192, pl.smem, st>>>(maps, p, partial);
-  RHO_CHECK_LAUNCH("conv_wgrad_halo_tcgen05");
-  return RHO_OK;
+  RHO_WGH(64, 64) RHO_WGH(64, 32) RHO_WGH(32, 64) RHO_WGH(32, 32)
+#undef RHO_WGH
+  return fail(RHO_ERR_UNSUPPORTED, "conv_wgrad_halo: no kernel for ck=%d cn=%d", p.ck, p.cn);
 }
 
 }  // namespace rho

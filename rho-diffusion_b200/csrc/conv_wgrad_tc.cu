@@ -242,6 +242,7 @@ bool conv_wgrad_tc_supported(const ConvGeom& g, const rho_conv_bwd_params* p) {
   const bool strided = g.sd == 1 && (g.sh == 2 || g.sw == 2) && g.ud == 1 && g.uh == 1 && g.uw == 1;
   const bool upsampled = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && (g.uh == 2 || g.uw == 2);
   if (!(plain || strided || upsampled)) return false;
+  if (plain && g.taps <= 28 && get_encode() != nullptr && wg_halo_plan(g).ok) return true;     // halo kernel (takes 32-channel blocks)
   if (!plain && g.C2 != 0) return false;
   if (strided && ((g.sh == 2 && g.H < 2) || (g.sw == 2 && g.W < 2))) return false;   // an empty parity view cannot be encoded
   if (g.Cin % 64 != 0 || g.C1 % 64 != 0 || wg_block_n(g.Cout) == 0) return false;
