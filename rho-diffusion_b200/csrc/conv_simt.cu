@@ -341,6 +341,15 @@ int wgrad_splits(const ConvGeom& g) {
   return (int)s;
 }
 
+// RHO_TRACE_SIMT=1: one stderr line per launch of a CUDA-core conv engine, to find the layers that fall off the tensor-core path
+static void trace_simt(const char* what, const ConvGeom& g) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("RHO_TRACE_SIMT"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on)
+    fprintf(stderr, "[rho] %s on CUDA cores: N=%d DHW=%dx%dx%d C1=%d C2=%d Cout=%d k=%dx%dx%d s=%d%d%d u=%d%d%d\n", what, g.N, g.D, g.H, g.W,
+            g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw, g.sd, g.sh, g.sw, g.ud, g.uh, g.uw);
+}
+
 template <typename TA, typename TW, typename TO>
 static int launch_fwd_t(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.Cout, BN));
@@ -356,6 +365,7 @@ static int launch_fwd_t(const ConvGeom& g, const rho_conv_params* p, cudaStream_
 }
 
 int conv_fwd_simt(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
+  trace_simt("conv fwd", g);
   const int a = p->act_dtype, w = p->w_dtype, f = p->y_f32;
   if (a == RHO_F32 && w == RHO_F32) return launch_fwd_t<float, float, float>(g, p, st);
   if (a == RHO_BF16 && w == RHO_BF16 && !f) return launch_fwd_t<bf16, bf16, bf16>(g, p, st);
@@ -381,6 +391,7 @@ static int launch_dgrad_t(const ConvGeom& g, const rho_conv_bwd_params* p, cudaS
 }
 
 int conv_dgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t st) {
+  trace_simt("conv dgrad", g);
   const int a = p->fwd.act_dtype, w = p->fwd.w_dtype;
   if (a == RHO_F32 && w == RHO_F32) return launch_dgrad_t<float, float>(g, p, st);
   if (a == RHO_BF16 && w == RHO_BF16) return launch_dgrad_t<bf16, bf16>(g, p, st);
@@ -402,6 +413,7 @@ int conv_wgrad_simt(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_
   float* partial = (float*)p->workspace;
   float* bias_ws = (float*)((char*)p->workspace + align_up((size_t)splits * g.Cout * g.Ktot * sizeof(float), 256));
   if (p->dw) {
+    trace_simt("conv wgrad", g);
     RHO_REQUIRE(p->fwd.x, "conv_wgrad: x required");
     long long per_split = ceil_div(ceil_div(g.M, splits), BK) * BK;
     dim3 grid((unsigned)ceil_div(g.Cout, BM), (unsigned)(g.taps * ceil_div(g.Cin, BN)), (unsigned)splits);

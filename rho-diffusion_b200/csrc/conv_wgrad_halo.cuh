@@ -22,6 +22,7 @@ struct WgHaloParams {
   int N, D, H, W, Wp;
   int C1, C2, Cin, Cout;
   int kd, pd;
+  int k1;                      // 1x1(x1) conv: one tap, shift 0 (first atom of group 0; the rest of the MMA rows are unused)
   int ck, cn;                  // channels per input / output block: 64 or 32 (32: 64-byte rows, SWIZZLE_64B)
   int cibs, cobs;              // blocks of the input / output channels
   int units;                   // kd * cibs * cobs
@@ -136,11 +137,15 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       tc_fence_after();
       const uint32_t xa = smem_u32(sX + (size_t)stage * p.x_bytes), ya = smem_u32(sY + (size_t)stage * p.y_bytes);
       if (elect_one()) {
+        const int ngroups = p.k1 ? 1 : GROUPS;
 #pragma unroll 1
-        for (int gi = 0; gi < GROUPS; ++gi) {
+        for (int gi = 0; gi < ngroups; ++gi) {
           int sa;
           uint32_t lbo;
-          if (CK == 64) {
+          if (p.k1) {
+            sa = 0;
+            lbo = (uint32_t)XROW;
+          } else if (CK == 64) {
             const int ta = 2 * gi, tb = 2 * gi + 1;
             sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
             const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;     // unused half of the last pair: any valid rows
@@ -177,11 +182,12 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
     const int a = r / CK, ci = xc + (r % CK);     // atom (tap within the group) and input channel of this accumulator row
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const int taps = p.kd * 9;
+    const int taps = p.k1 ? 1 : p.kd * 9;
+    const int ngroups = p.k1 ? 1 : GROUPS;
 #pragma unroll 1
-    for (int gi = 0; gi < GROUPS; ++gi) {
-      const int t9 = CK == 64 ? 2 * gi + a : 3 * gi + a;
-      const bool used = CK == 64 ? t9 < 9 : a < 3;                // warp-uniform (a is constant per warp)
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int t9 = p.k1 ? 0 : (CK == 64 ? 2 * gi + a : 3 * gi + a);
+      const bool used = p.k1 ? a == 0 : (CK == 64 ? t9 < 9 : a < 3);   // warp-uniform (a is constant per warp)
       float* dst = partial + ((((long long)split * taps + (dd * 9 + (used ? t9 : 0))) * p.Cin + ci) * p.Cout) + cob * CN;
 #pragma unroll 1
       for (int c0 = 0; c0 < CN; c0 += 32) {
@@ -219,7 +225,10 @@ static WgHaloPlan wg_halo_plan(const ConvGeom& g) {
   if (mode < 0) { const char* e = getenv("RHO_WGRAD_HALO"); mode = e ? atoi(e) : 1; }
   if (!mode) return pl;
   const bool plain = g.sd == 1 && g.sh == 1 && g.sw == 1 && g.ud == 1 && g.uh == 1 && g.uw == 1;
-  if (!plain || g.kh != 3 || g.kw != 3 || (g.kd != 1 && g.kd != 3)) return pl;
+  const bool k1 = g.kd == 1 && g.kh == 1 && g.kw == 1;
+  if (!plain || !(k1 || (g.kh == 3 && g.kw == 3 && (g.kd == 1 || g.kd == 3)))) return pl;
+  // 1x1 layers with 64-channel blocks stay on the per-tap kernel (no halo to reuse); the 32-channel ones only fit here
+  if (k1 && g.C1 % 64 == 0 && g.C2 % 64 == 0 && g.Cout % 64 == 0) return pl;
   const int ck = (g.C1 % 64 == 0 && g.C2 % 64 == 0) ? 64 : ((g.C1 % 32 == 0 && g.C2 % 32 == 0) ? 32 : 0);
   if (ck == 0 || (g.Cout != 32 && g.Cout != 64 && g.Cout != 128)) return pl;
   const int cn = g.Cout == 32 ? 32 : 64;
@@ -228,6 +237,7 @@ static WgHaloPlan wg_halo_plan(const ConvGeom& g) {
   p.N = g.N; p.D = g.D; p.H = g.H; p.W = g.W; p.Wp = g.W + 1;
   p.C1 = g.C1; p.C2 = g.C2; p.Cin = g.Cin; p.Cout = g.Cout;
   p.kd = g.kd; p.pd = g.kd / 2;
+  p.k1 = k1 ? 1 : 0;
   p.ck = ck; p.cn = cn;
   p.cibs = g.Cin / ck; p.cobs = g.Cout / cn;
   p.units = p.kd * p.cibs * p.cobs;

@@ -172,6 +172,11 @@ CONV_CASES = [
     (2, 2, 32, 0, 64, (24, 40), 3, 1, 1, False),
     (3, 1, 32, 0, 32, (3, 20, 24), 3, 1, 1, False),
     (2, 1, 64, 0, 32, (128, 128), 3, 1, 1, False),             # 64-channel K block, 32 outputs, the real 128^2 plane (17 groups)
+    # 1x1 skip convs with 32-channel blocks: weight gradient on the halo kernel's one-tap mode
+    (2, 2, 32, 32, 32, (40, 48), 1, 1, 1, False),
+    (2, 2, 64, 32, 64, (30, 33), 1, 1, 1, False),
+    (2, 1, 32, 0, 64, (64, 64), 1, 1, 1, False),
+    (3, 1, 64, 32, 32, (2, 24, 24), 1, 1, 1, False),
 ]
 
 

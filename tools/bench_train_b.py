@@ -43,6 +43,18 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f"config B train: batch {B}  {ms:.2f} ms/step  {B / ms * 1e3:.1f} samples/s")
+if "graph" in sys.argv[1:]:
+    from rho_diffusion.b200 import GraphedTrainStep
+    gstep = GraphedTrainStep(ddpm, fused, x, y)
+    for _ in range(3):
+        gstep(x, y)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        gstep(x, y)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"config B train (whole-step CUDA graph): batch {B}  {ms:.2f} ms/step  {B / ms * 1e3:.1f} samples/s")
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
