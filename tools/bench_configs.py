@@ -18,8 +18,11 @@ CONFIGS = {
     "A 3-D 32^3 mc64": (dict(dims=3, model_channels=64, data_shape=[32, 32, 32], num_classes=20, **common), (1, 32, 32, 32), [32, 100], None),
     "B 2-D 128^2 mc32": (dict(dims=2, model_channels=32, data_shape=[128, 128], num_classes=25, **common), (1, 128, 128), [64, 256], space),
     "C 1-D 1024 mc64": (dict(dims=1, model_channels=64, data_shape=[1024], num_classes=20, **common), (1, 1024), [64, 512], None),
+    "E 3-D 128^3 mc64": (dict(dims=3, model_channels=64, data_shape=[128, 128, 128], num_classes=20, **common), (1, 128, 128, 128), [1, 2], None),
 }
 for name, (kw, shape, batches, sp) in CONFIGS.items():
+    if len(sys.argv) > 2 and not name.startswith(tuple(sys.argv[2:])):      # e.g. `bench_configs.py run E`
+        continue
     T = 1000
     extra = dict(cond_fn="MultiEmbeddings", cond_fn_kwargs={"parameter_space": sp, "embedding_dim": 4 * kw["model_channels"]}) if sp else {}
     ddpm = DDPM("UNetv2", dict(kw), LinearSchedule(T, 1e-3, 0.02), "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4}, **extra)
@@ -42,7 +45,7 @@ for name, (kw, shape, batches, sp) in CONFIGS.items():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            K = 20
+            K = 20 if B * shape[-1] ** len(shape[1:]) < 1 << 21 else 4
             for _ in range(K):
                 s.graph.replay()
             e1.record(); torch.cuda.synchronize()
