@@ -72,6 +72,94 @@ __global__ void linear_bwd_dw_kernel(rho_linear_params p, const float* __restric
   dw[idx] = s;
 }
 
+// Batches of 32 rows and more (config C samples 512 sequences at a time) turn the GEMVs above into real GEMMs: the warp-per-output
+// kernels re-read a weight row per (b, o) from L2.  One tiled fp32 kernel serves the three products
+//     forward   y[b][o]  = sum_i act(x[b][i]) w[o][i]  (+ bias, + add)      M = B, N = O, K = I   A, B contiguous along K
+//     dx        dx[b][i] = act'(x[b][i]) sum_o dy[b][o] w[o][i]              M = B, N = I, K = O   A along K, B along N
+//     dw        dw[o][i] = sum_b dy[b][o] act(x[b][i])                       M = O, N = I, K = B   A along M, B along N
+// 64 x 64 tile, K step 16, 256 threads with 4 x 4 register tiles; the K order is fixed, so results do not depend on the grid.
+enum { LIN_FWD = 0, LIN_DX = 1, LIN_DW = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256) linear_tiled_kernel(rho_linear_params p, const float* __restrict__ dy, int dy_stride,
+                                                           float* __restrict__ out, int out_stride) {
+  constexpr int T = 64, KS = 16, LD = T + 4;
+  __shared__ float As[KS][LD], Bs[KS][LD];
+  const int M = MODE == LIN_DW ? p.O : p.B;
+  const int N = MODE == LIN_FWD ? p.O : p.I;
+  const int K = MODE == LIN_FWD ? p.I : (MODE == LIN_DX ? p.O : p.B);
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += KS) {
+    // ---- A tile -> As[k][m] ----
+    if (MODE == LIN_DW) {                      // A(m, k) = dy[k][m]: contiguous along m
+      const int k = k0 + (t >> 4), m = m0 + (t & 15) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[t >> 4][(t & 15) * 4 + j] = (k < K && m + j < M) ? dy[(long long)k * dy_stride + m + j] : 0.f;
+    } else {                                   // contiguous along k: act(x[m][k]) resp. dy[m][k]
+      const int m = m0 + (t >> 2), k = k0 + (t & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        if (m < M && k + j < K) v = MODE == LIN_FWD ? apply_act(p.x[(long long)m * p.x_stride + k + j], p.act_in) : dy[(long long)m * dy_stride + k + j];
+        As[(t & 3) * 4 + j][t >> 2] = v;
+      }
+    }
+    // ---- B tile -> Bs[k][n] ----
+    if (MODE == LIN_FWD) {                     // B(k, n) = w[n][k]: contiguous along k
+      const int n = n0 + (t >> 2), k = k0 + (t & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Bs[(t & 3) * 4 + j][t >> 2] = (n < N && k + j < K) ? p.w[(long long)n * p.I + k + j] : 0.f;
+    } else {                                   // contiguous along n: w[k][n] resp. act(x[k][n])
+      const int k = k0 + (t >> 4), n = n0 + (t & 15) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        if (k < K && n + j < N) v = MODE == LIN_DX ? p.w[(long long)k * p.I + n + j] : apply_act(p.x[(long long)k * p.x_stride + n + j], p.act_in);
+        Bs[t >> 4][(t & 15) * 4 + j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (MODE == LIN_FWD) {
+        if (p.b) v += p.b[n];
+        if (p.add) v += p.add[(long long)m * p.add_stride + n];
+      } else if (MODE == LIN_DX) {
+        v *= act_grad(p.x[(long long)m * p.x_stride + n], p.act_in);
+      }
+      out[(long long)m * out_stride + n] = v;
+    }
+  }
+}
+
+constexpr int LIN_TILED_MIN_B = 32;
+
 __global__ void linear_bwd_db_kernel(int B, int O, const float* __restrict__ dy, int dy_stride, float* __restrict__ db) {
   int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= O) return;
@@ -130,6 +218,12 @@ int rho_timestep_embedding(const int64_t* t, int32_t B, int32_t dim, const float
 
 int rho_linear_fwd(const rho_linear_params* p, rho_stream_t stream) {
   RHO_REQUIRE(p && p->x && p->w && p->y && p->B > 0 && p->I > 0 && p->O > 0, "linear_fwd: bad args");
+  if (p->B >= LIN_TILED_MIN_B) {
+    linear_tiled_kernel<LIN_FWD><<<dim3((unsigned)ceil_div(p->O, 64), (unsigned)ceil_div(p->B, 64)), 256, 0, as_stream(stream)>>>(
+        *p, nullptr, 0, p->y, p->y_stride);
+    RHO_CHECK_LAUNCH("linear_fwd_tiled");
+    return RHO_OK;
+  }
   long long warps = (long long)p->B * p->O;
   linear_fwd_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, as_stream(stream)>>>(*p);
   RHO_CHECK_LAUNCH("linear_fwd");
@@ -140,11 +234,18 @@ int rho_linear_bwd(const rho_linear_params* p, const float* dy, int32_t dy_strid
                    rho_stream_t stream) {
   RHO_REQUIRE(p && p->x && p->w && dy && p->B > 0 && p->I > 0 && p->O > 0, "linear_bwd: bad args");
   cudaStream_t st = as_stream(stream);
-  if (dx) {
+  const bool tiled = p->B >= LIN_TILED_MIN_B;
+  if (dx && tiled) {
+    linear_tiled_kernel<LIN_DX><<<dim3((unsigned)ceil_div(p->I, 64), (unsigned)ceil_div(p->B, 64)), 256, 0, st>>>(*p, dy, dy_stride, dx, dx_stride);
+    RHO_CHECK_LAUNCH("linear_bwd_dx_tiled");
+  } else if (dx) {
     linear_bwd_dx_kernel<<<dim3((unsigned)ceil_div(p->I, 32), (unsigned)p->B), 256, 0, st>>>(*p, dy, dy_stride, dx, dx_stride);
     RHO_CHECK_LAUNCH("linear_bwd_dx");
   }
-  if (dw) {
+  if (dw && tiled) {
+    linear_tiled_kernel<LIN_DW><<<dim3((unsigned)ceil_div(p->I, 64), (unsigned)ceil_div(p->O, 64)), 256, 0, st>>>(*p, dy, dy_stride, dw, p->I);
+    RHO_CHECK_LAUNCH("linear_bwd_dw_tiled");
+  } else if (dw) {
     linear_bwd_dw_kernel<<<(unsigned)ceil_div((long long)p->O * p->I, 128), 128, 0, st>>>(*p, dy, dy_stride, dw);
     RHO_CHECK_LAUNCH("linear_bwd_dw");
   }

@@ -316,6 +316,33 @@ def test_embedding_path(ops):
     assert torch.equal(gt[:, 0], torch.tensor([2.0, 1.0]))
 
 
+@pytest.mark.parametrize("B,I,O,act", [(32, 48, 96, "silu"), (100, 130, 70, "none"), (512, 256, 1024, "silu"), (33, 7, 5, "silu"), (64, 64, 64, "none")])
+def test_linear_large_batch_tiled(ops, B, I, O, act):
+    """Batches >= 32 take the tiled fp32 GEMM kernels (config C feeds 512 rows to every emb_layers Linear): forward with the fused
+    input activation / bias / add, dx, dw, db against torch, ragged tile edges included; a 512-row batch row-for-row equals the
+    same rows pushed through as a batch of 33 (the K order does not depend on the grid)."""
+    from rho_diffusion.b200 import _lib
+    code = _lib.ACT_SILU if act == "silu" else _lib.ACT_NONE
+    f = F.silu if act == "silu" else (lambda v: v)
+    x = randn(B, I, seed=40).requires_grad_(True)
+    w = (randn(O, I, seed=41) / math.sqrt(I)).requires_grad_(True)
+    b = randn(O, seed=42).requires_grad_(True)
+    add = randn(B, O, seed=43).requires_grad_(True)
+    ref = F.linear(f(x), w, b) + add
+    dy = randn(B, O, seed=44)
+    ref.backward(dy)
+    xd, wd, bd, ad = (v.detach().to(DEV).requires_grad_(True) for v in (x, w, b, add))
+    y = ops.linear(xd, wd, bd, ad, act_in=code)
+    y.backward(dy.to(DEV))
+    assert rel_err(y, ref) < 1e-5
+    for got, want in ((xd.grad, x.grad), (wd.grad, w.grad), (bd.grad, b.grad), (ad.grad, add.grad)):
+        assert rel_err(got, want) < 1e-5
+    with torch.no_grad():
+        sub = ops.linear(xd[:33].contiguous(), wd, bd, ad[:33].contiguous(), act_in=code)
+    if B >= 33:
+        assert torch.equal(sub, y[:33])
+
+
 def test_philox_bit_exact_and_normals(ops):
     import ctypes as C
     from rho_diffusion.b200 import _lib
