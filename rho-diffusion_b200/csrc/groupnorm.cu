@@ -429,19 +429,32 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const float* 
   }
 }
 
-__global__ void gn_bwd_param_kernel(const float* __restrict__ sums, int N, int C, const float* __restrict__ scale, int film_stride,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// dgamma / dbeta: sums over the batch of the per-sample channel sums.  CTA = 32 channels x 8 sample lanes (sample n goes to lane
+// n % 8, so config C's 512-sample batches are not walked by one thread); the lanes meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ sums, int N, int C, const float* __restrict__ scale,
+                                                           int film_stride, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float dg = 0.f, db = 0.f;
-  for (int n = 0; n < N; ++n) {
-    float sc = scale ? scale[(int64_t)n * film_stride + c] : 0.f;
-    const float* so = sums + ((int64_t)n * C + c) * 3;
-    dg += (1.f + sc) * so[1];
-    db += (1.f + sc) * so[0];
+  if (c < C) {
+    for (int n = ty; n < N; n += 8) {
+      float sc = scale ? scale[(int64_t)n * film_stride + c] : 0.f;
+      const float* so = sums + ((int64_t)n * C + c) * 3;
+      dg += (1.f + sc) * so[1];
+      db += (1.f + sc) * so[0];
+    }
   }
-  if (dgamma) dgamma[c] = dg;
-  if (dbeta) dbeta[c] = db;
+  red[0][ty][tx] = dg;
+  red[1][ty][tx] = db;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g += red[0][k][tx]; b += red[1][k][tx]; }
+    if (dgamma) dgamma[c] = g;
+    if (dbeta) dbeta[c] = b;
+  }
 }
 
 template <typename TI, typename TO>
@@ -1173,7 +1186,7 @@ int rho_gn_bwd(const rho_gn_bwd_params* p, rho_stream_t stream) {
                                                    sums, gmean, p->dscale, p->dshift, p->dfilm_stride, p->dpre_add);
   RHO_CHECK_LAUNCH("gn_bwd_reduce");
   if (p->dgamma || p->dbeta) {
-    gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, f.N, C, f.scale, f.film_stride, p->dgamma, p->dbeta);
+    gn_bwd_param_kernel<<<(C + 31) / 32, 256, 0, st>>>(sums, f.N, C, f.scale, f.film_stride, p->dgamma, p->dbeta);
     RHO_CHECK_LAUNCH("gn_bwd_param");
   }
   if (fast) {
