@@ -41,7 +41,7 @@ struct HaloMaps {
 };
 
 template <int BLOCK_N, int MT, int BLOCK_K>
-__global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
+__global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
                                                            const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                            bf16* __restrict__ y, bf16* __restrict__ y2) {
   constexpr int ROW_BYTES = BLOCK_K * 2;          // one position's channels of a K block: 128 B (64 ch) or 64 B (32 ch)
@@ -56,14 +56,14 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[128];
-  __shared__ float sstat[4][BLOCK_N][2];
+  __shared__ float sstat[8][BLOCK_N][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.Cin / BLOCK_K;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -167,8 +167,13 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
       if (++ab == 2) { ab = 0; phacc ^= 1; }
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. + 31 =====
-    const int et = threadIdx.x - 64;
+    // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31, warps 2..5 take the even tiles of an item and
+    // warps 6..9 the odd ones (two warps per scheduler: one hides the other's tcgen05.ld / store latency).  The fused
+    // GroupNorm statistics are accumulated per lane (= per row) over the warp's tiles and transposed across the warp once
+    // per item and 32-channel chunk. =====
+    const int et = threadIdx.x - 64;            // 0 .. 255
+    const int ew = warp - 2;                    // 0 .. 7
+    const int set = ew >> 2;
     const int lane_base = 32 * (warp & 3);
     const int r = lane_base + lane;
     int ab = 0;
@@ -178,77 +183,83 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(const __grid_constant
       int nb, q0, mt_here, d, n, h_lo;
       decode(item, nb, q0, mt_here, d, n, h_lo);
       if (nb != nb_loaded) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < BLOCK_N; i += 128) sbias[i] = bias ? bias[nb * BLOCK_N + i] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < BLOCK_N; i += 256) sbias[i] = bias ? bias[nb * BLOCK_N + i] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         nb_loaded = nb;
       }
       mbar_wait(&acc_full[ab], phacc);
       tc_fence_after();
       const long long plane_pos = ((long long)n * p.D + d) * p.H * p.W;
-      float st1[BLOCK_N / 32], st2[BLOCK_N / 32];       // lane l: sums of channel c0 + l over this warp's rows of the item
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float a1[32], a2[32];                   // this lane's row sums / sums of squares of channels c0 .. c0 + 31
 #pragma unroll
-      for (int c = 0; c < BLOCK_N / 32; ++c) { st1[c] = 0.f; st2[c] = 0.f; }
-      for (int i = 0; i < mt_here; ++i) {
-        const int q = q0 + i * 128 + r;
-        const int h = q / p.Wp, wq = q - h * p.Wp;
-        const bool valid = wq != 0 && h < p.H;
-        const long long pos = plane_pos + (long long)h * p.W + (wq - 1);
-        const uint32_t tsrc = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((ab * MT + i) * BLOCK_N);
-#pragma unroll
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int j = 0; j < 32; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+        const int ch = nb * BLOCK_N + c0;
+#pragma unroll 1
+        for (int i = set; i < mt_here; i += 2) {
+          const int q = q0 + i * 128 + r;
+          const int h = q / p.Wp, wq = q - h * p.Wp;
+          const bool valid = wq != 0 && h < p.H;
+          const long long pos = plane_pos + (long long)h * p.W + (wq - 1);
           uint32_t v[32];
-          tmem_ld32(tsrc + (uint32_t)c0, v);
-          float xs[32];
-          const int ch = nb * BLOCK_N + c0;
+          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)((ab * MT + i) * BLOCK_N + c0), v);
           bf16* dst;
           if (p.out_split > 0 && ch >= p.out_split) dst = y2 + pos * (p.Cout - p.out_split) + (ch - p.out_split);
           else dst = y + pos * (p.out_split > 0 ? p.out_split : p.Cout) + ch;
           const bf16* res = (residual && valid) ? residual + pos * p.Cout + ch : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float o[8];
+          for (int j = 0; j < 32; j += 16) {
+            uint4 w4[2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]) + sbias[c0 + j + e];
-            if (res) {
-              const uint4 qv = __ldg(reinterpret_cast<const uint4*>(res + j));
-              const uint32_t u[4] = {qv.x, qv.y, qv.z, qv.w};
+            for (int hf = 0; hf < 2; ++hf) {
+              const int jj = j + hf * 8;
+              float o[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[jj + e]) + sbias[c0 + jj + e];
+              if (res) {
+                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(res + jj));
+                const uint32_t u[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { o[2 * e] += __uint_as_float(u[e] << 16); o[2 * e + 1] += __uint_as_float(u[e] & 0xffff0000u); }
+              }
+              __nv_bfloat162 h2;
+              h2 = __floats2bfloat162_rn(o[0], o[1]); w4[hf].x = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[2], o[3]); w4[hf].y = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[4], o[5]); w4[hf].z = *reinterpret_cast<uint32_t*>(&h2);
+              h2 = __floats2bfloat162_rn(o[6], o[7]); w4[hf].w = *reinterpret_cast<uint32_t*>(&h2);
             }
-            uint4 w4;
-            __nv_bfloat162 h2;
-            h2 = __floats2bfloat162_rn(o[0], o[1]); w4.x = *reinterpret_cast<uint32_t*>(&h2);
-            h2 = __floats2bfloat162_rn(o[2], o[3]); w4.y = *reinterpret_cast<uint32_t*>(&h2);
-            h2 = __floats2bfloat162_rn(o[4], o[5]); w4.z = *reinterpret_cast<uint32_t*>(&h2);
-            h2 = __floats2bfloat162_rn(o[6], o[7]); w4.w = *reinterpret_cast<uint32_t*>(&h2);
-            if (valid) *reinterpret_cast<uint4*>(dst + j) = w4;
-            if (p.stat_part) {
-              const uint32_t u[4] = {valid ? w4.x : 0u, valid ? w4.y : 0u, valid ? w4.z : 0u, valid ? w4.w : 0u};
+            if (valid) {
+              st_global_256(dst + j, w4[0], w4[1]);       // a full 32-byte sector per lane (rows are >= 64 bytes apart)
+              if (p.stat_part) {                // statistics of the bf16-rounded outputs, exactly what the next GroupNorm reads
+                const uint32_t u[8] = {w4[0].x, w4[0].y, w4[0].z, w4[0].w, w4[1].x, w4[1].y, w4[1].z, w4[1].w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { xs[j + 2 * e] = __uint_as_float(u[e] << 16); xs[j + 2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u); }
+                for (int e = 0; e < 8; ++e) {
+                  const float x0 = __uint_as_float(u[e] << 16), x1 = __uint_as_float(u[e] & 0xffff0000u);
+                  a1[j + 2 * e] += x0; a2[j + 2 * e] = fmaf(x0, x0, a2[j + 2 * e]);
+                  a1[j + 2 * e + 1] += x1; a2[j + 2 * e + 1] = fmaf(x1, x1, a2[j + 2 * e + 1]);
+                }
+              }
             }
           }
-          if (p.stat_part) {
-            float s1, s2;
-            warp_colsum32(xs, lane, s1, s2);
-            st1[c0 >> 5] += s1;
-            st2[c0 >> 5] += s2;
-          }
+        }
+        if (p.stat_part) {
+          sstat[ew][c0 + lane][0] = warp_colsum32_pass<false>(a1, lane);
+          sstat[ew][c0 + lane][1] = warp_colsum32_pass<false>(a2, lane);
         }
       }
       if (p.stat_part) {
-        // the four warps' sums in a fixed order -> one row of stat_part per item
-#pragma unroll
-        for (int c = 0; c < BLOCK_N / 32; ++c) { sstat[warp & 3][c * 32 + lane][0] = st1[c]; sstat[warp & 3][c * 32 + lane][1] = st2[c]; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // the eight warps' sums in a fixed order -> one row of stat_part per item
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et < BLOCK_N) {
-          const float a1 = (sstat[0][et][0] + sstat[1][et][0]) + (sstat[2][et][0] + sstat[3][et][0]);
-          const float a2 = (sstat[0][et][1] + sstat[1][et][1]) + (sstat[2][et][1] + sstat[3][et][1]);
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { t1 += sstat[k][et][0]; t2 += sstat[k][et][1]; }
           const long long row = item / p.n_blocks;       // (sample, plane, group) in launch order = n * rows_per_sample + ...
-          *reinterpret_cast<float2*>(p.stat_part + (row * p.Cout + nb * BLOCK_N + et) * 2) = make_float2(a1, a2);
+          *reinterpret_cast<float2*>(p.stat_part + (row * p.Cout + nb * BLOCK_N + et) * 2) = make_float2(t1, t2);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
@@ -292,7 +303,7 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   p.kd = kd; p.pd = kd / 2;
   p.n_blocks = 1;
   p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
-  const size_t budget = 227 * 1024 - 3072 /* static: barriers, bias, statistics scratch */ - 1024 /* alignment slack */ - 1024;
+  const size_t budget = 227 * 1024 - 9216 /* static: barriers, bias, statistics scratch (8 warps x 128 channels) */ - 1024 /* alignment slack */ - 1024;
   const size_t b_bytes = (size_t)pl.bn * (size_t)(2 * bk);
   // tiles per work item: as many as TMEM (2 x MT x BLOCK_N <= 512 columns) and two slab stages in shared memory allow
   bool fits = false;
@@ -335,7 +346,7 @@ static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bi
     attr_bytes = pl.smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(pl.p.total_items, (long long)sm_count());
-  kern<<<grid, 192, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
+  kern<<<grid, 320, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
   RHO_CHECK_LAUNCH("conv_halo_tcgen05");
   return RHO_OK;
 }

@@ -184,6 +184,12 @@ __device__ __forceinline__ void warp_colsum32(const float (&x)[32], int lane, fl
   s1 = warp_colsum32_pass<false>(x, lane);      // two passes: half the live registers of a fused one
   s2 = warp_colsum32_pass<true>(x, lane);
 }
+// 32-byte global store (sm_100: STG.E.ENL2.256): one full sector per lane even when consecutive lanes write different rows
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- UMMA shared-memory descriptors for 128-byte-swizzled tiles (rows of 128 bytes = 64 bf16) ------------------
