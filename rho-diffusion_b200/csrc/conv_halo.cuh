@@ -303,7 +303,8 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   p.kd = kd; p.pd = kd / 2;
   p.n_blocks = 1;
   p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
-  const size_t budget = 227 * 1024 - 9216 /* static: barriers, bias, statistics scratch (8 warps x 128 channels) */ - 1024 /* alignment slack */ - 1024;
+  // static shared memory: statistics scratch (8 warps x BLOCK_N channels x 2 floats), bias, barriers; 1 KB alignment slack, 1 KB reserve
+  const size_t budget = 227 * 1024 - ((size_t)64 * pl.bn + 1536) - 1024 - 1024;
   const size_t b_bytes = (size_t)pl.bn * (size_t)(2 * bk);
   // tiles per work item: as many as TMEM (2 x MT x BLOCK_N <= 512 columns) and two slab stages in shared memory allow
   bool fits = false;
@@ -320,11 +321,14 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
     if (R > 256) continue;
     p.R = R;
     p.a_stage_bytes = (int)align_up((size_t)R * p.Wp * (size_t)(2 * bk), 1024);
-    p.SB = pl.bn <= 64 ? 5 : 4;
-    const long long sa = ((long long)budget - (long long)p.SB * (long long)b_bytes) / p.a_stage_bytes;
-    if (sa < 2) continue;
-    p.SA = (int)std::min<long long>(sa, 3);
-    fits = true;
+    // weight ring: 5 (4) stages preferred, 3 at least, before giving up tiles per item
+    for (int sb = pl.bn <= 64 ? 5 : 4; sb >= 3 && !fits; --sb) {
+      const long long sa = ((long long)budget - (long long)sb * (long long)b_bytes) / p.a_stage_bytes;
+      if (sa < 2) continue;
+      p.SB = sb;
+      p.SA = (int)std::min<long long>(sa, 3);
+      fits = true;
+    }
   }
   if (!fits) return pl;
   p.total_items = (long long)N * D * p.groups_per_plane * p.n_blocks;
