@@ -54,6 +54,7 @@ struct TcParams {
 struct TcMaps {
   CUtensorMap a[TC_MAX_MAPS][2];
   CUtensorMap w;
+  CUtensorMap w_half;      // the same weights boxed BLOCK_N / 2 rows at a time (cluster launches: each CTA multicasts its half)
   CUtensorMap y[2];        // output view(s) of this launch (TMA-store epilogue): y, and y2 for a split output
 };
 
@@ -78,7 +79,10 @@ __device__ __forceinline__ uint32_t umma_idesc() {
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int BLOCK_K, int STAGES, typename TOut>
+// CL = 2: launched as clusters of two CTAs that own neighbouring M tiles of the same output-channel block.  Each CTA loads half of
+// the weight tile and multicasts it to both, so the weight bytes cross the L2 -> shared-memory path once per pair; a stage is free
+// again when BOTH CTAs' MMAs have retired it (their commits arrive on both CTAs' empty barriers).
+template <int BLOCK_N, int BLOCK_K, int STAGES, typename TOut, int CL = 1>
 __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
                                                       const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                       TOut* __restrict__ y, TOut* __restrict__ y2) {
@@ -95,8 +99,10 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
   __shared__ float sstat[2][4][64][2];   // fused GroupNorm statistics: [chunk parity][epilogue warp][channel][sum, sum of squares]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb = blockIdx.x % p.n_blocks;
-  int mt = blockIdx.x / p.n_blocks;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+  const int bx = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nb = bx % p.n_blocks;
+  int mt = CL == 2 ? (bx / p.n_blocks) * 2 + (int)crank : bx / p.n_blocks;      // an odd tile count leaves one all-out-of-range tile
   const int tw = mt % p.tiles_w; mt /= p.tiles_w;
   const int th = mt % p.tiles_h; mt /= p.tiles_h;
   const int td = mt % p.tiles_d; mt /= p.tiles_d;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
   const int num_kb = p.ntaps * kb_per_tap;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     mbar_init(&accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -134,7 +141,11 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_5d(sa, &maps.a[tap.map][src], &full_bar[stage], cc, w0 + tap.dw, h0 + tap.dh, d0 + tap.dd, n0 + tap.dn);
-          tma_load_2d(sa + A_BYTES, &maps.w, &full_bar[stage], tap.kofs + c, nb * BLOCK_N);
+          if (CL == 2)     // this CTA's half of the weight tile, to both CTAs
+            tma_load_2d_multicast(sa + A_BYTES + crank * (B_BYTES / 2), &maps.w_half, &full_bar[stage], tap.kofs + c,
+                                  nb * BLOCK_N + (int)crank * (BLOCK_N / 2), (uint16_t)3);
+          else
+            tma_load_2d(sa + A_BYTES, &maps.w, &full_bar[stage], tap.kofs + c, nb * BLOCK_N);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -157,7 +168,8 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
           umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);
+        if (CL == 2) umma_commit_multicast(&empty_bar[stage], (uint16_t)3);
+        else umma_commit(&empty_bar[stage]);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
             tma_store_5d(&maps.y[second ? 1 : 0], smem + cc * (TC_BM * 128), second ? ch - p.out_split : ch, w0, h0, d0, n0);
             bulk_commit_group();
           }
-          if (p.stat_part && et < 64) {
+          if (p.stat_part && et < 64 && tn < p.tiles_n) {
             // the four warps' partial sums in a fixed order; one row of stat_part per (sample, tile)
             const float a1 = (sstat[cc & 1][0][et][0] + sstat[cc & 1][1][et][0]) + (sstat[cc & 1][2][et][0] + sstat[cc & 1][3][et][0]);
             const float a2 = (sstat[cc & 1][0][et][1] + sstat[cc & 1][1][et][1]) + (sstat[cc & 1][2][et][1] + sstat[cc & 1][3][et][1]);
@@ -275,6 +287,7 @@ __global__ void __launch_bounds__(192, 2) conv_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N));
   }
@@ -369,21 +382,48 @@ static void pick_tile(TcParams& p) {
   p.tiles_n = (int)ceil_div(p.N, p.bn);
 }
 
-template <int BLOCK_N, int BLOCK_K, typename TOut>
+// RHO_CONV_CLUSTER=1: CTA pairs share the weight tile of BLOCK_N >= 128 launches through TMA multicast (default off)
+static int cluster_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RHO_CONV_CLUSTER"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* w, long long Ktot, int rows, int bk, int block_n);
+static int encode_weight_maps(TcMaps& maps, const void* w, long long Ktot, int rows, int bk, int bn) {
+  int rc = encode_weight_map(&maps.w, w, Ktot, rows, bk, bn);
+  if (!rc && cluster_mode() && bn >= 128) rc = encode_weight_map(&maps.w_half, w, Ktot, rows, bk, bn / 2);
+  return rc;
+}
+
+template <int BLOCK_N, int BLOCK_K, typename TOut, int CL = 1>
 static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2, cudaStream_t st) {
   constexpr int STAGE_BYTES = (TC_BM + BLOCK_N) * BLOCK_K * 2;
   // ring depth: fill ~96 KB so that two CTAs fit in one SM's 227 KB
   constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2 : ((96 * 1024 / STAGE_BYTES) > 8 ? 8 : (96 * 1024 / STAGE_BYTES));
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, TOut>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, TOut, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_blocks;
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  long long tiles = (CL == 2 ? 2 * ((m_tiles + 1) / 2) : m_tiles) * p.n_blocks;
   if (tiles > 2147483647LL) return fail(RHO_ERR_UNSUPPORTED, "conv_tc: grid too large");
+  if (CL == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)tiles); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, p, bias, residual, y, y2);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_tc: cluster launch: %s", cudaGetErrorString(e));
+    return RHO_OK;
+  }
   kern<<<(unsigned)tiles, 192, SMEM, st>>>(maps, p, bias, residual, y, y2);
   RHO_CHECK_LAUNCH("conv_fwd_tcgen05");
   return RHO_OK;
@@ -421,6 +461,14 @@ static int dispatch_tc(int bn, int bk, const TcMaps& maps_in, const TcParams& p_
     p.tma_store = 1;
   }
   if (!p.tma_store) p.stat_part = nullptr;       // (conv_fwd_tc_stats_rows only offers statistics when this path is taken)
+  if constexpr (sizeof(TOut) == 2) {
+    if (cluster_mode() && bn >= 128) {
+#define RHO_TC2(BN, BK) \
+  if (bn == BN && bk == BK) return launch_tc<BN, BK, TOut, 2>(maps, p, bias, residual, y, y2, st)
+      RHO_TC2(256, 64); RHO_TC2(128, 64); RHO_TC2(256, 32); RHO_TC2(128, 32);
+#undef RHO_TC2
+    }
+  }
 #define RHO_TC(BN, BK) \
   if (bn == BN && bk == BK) return launch_tc<BN, BK, TOut>(maps, p, bias, residual, y, y2, st)
   RHO_TC(256, 64); RHO_TC(128, 64); RHO_TC(64, 64); RHO_TC(32, 64);
@@ -653,7 +701,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
         tp.taps[r].dn = 0; tp.taps[r].dd = t.off[c][r][0]; tp.taps[r].dh = t.off[c][r][1]; tp.taps[r].dw = t.off[c][r][2];
         tp.taps[r].map = 0; tp.taps[r].kofs = r * g.Cin;
       }
-      rc = encode_weight_map(&maps.w, (const bf16*)p->w_aux + c * cls_stride, (long long)t.rt * g.Cin, g.Cout, bk, bn);
+      rc = encode_weight_maps(maps, (const bf16*)p->w_aux + c * cls_stride, (long long)t.rt * g.Cin, g.Cout, bk, bn);
       if (rc) return rc;
       tp.stat_row_off = c * tp.tiles_w * tp.tiles_h * tp.tiles_d;
       rc = dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
@@ -708,7 +756,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
       if (g.C2) { rc = encode_view(&maps.a[m][1], parity_view(p->x2, g, g.C2, m >> 1, m & 1), box, bk); if (rc) return rc; }
     }
   }
-  rc = encode_weight_map(&maps.w, p->w_packed, g.Ktot, g.Cout, bk, bn);
+  rc = encode_weight_maps(maps, p->w_packed, g.Ktot, g.Cout, bk, bn);
   if (rc) return rc;
   return dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
 }
@@ -823,7 +871,7 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   if (is_strided(g)) {
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
-    int rc = encode_weight_map(&maps.w, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
+    int rc = encode_weight_maps(maps, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
     if (rc) return rc;
     ActView v;
     v.base = p->dy;
@@ -880,7 +928,7 @@ int conv_dgrad_tc(const ConvGeom& g, const rho_conv_bwd_params* p, cudaStream_t 
   v.stride[0] = (long long)g.Cout * 2; v.stride[1] = v.stride[0] * g.Wo; v.stride[2] = v.stride[1] * g.Ho; v.stride[3] = v.stride[2] * g.Do;
   int rc = encode_view(&maps.a[0][0], v, box, bk);
   if (rc) return rc;
-  rc = encode_weight_map(&maps.w, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
+  rc = encode_weight_maps(maps, wd, (long long)g.taps * g.Cout, g.Cin, bk, bn);
   if (rc) return rc;
   if (!up) return dispatch_tc<bf16>(bn, bk, maps, tp, nullptr, nullptr, (bf16*)p->dx, (bf16*)p->dx2, st);
   rc = dispatch_tc<bf16>(bn, bk, maps, tp, nullptr, nullptr, tmp, (bf16*)nullptr, st);

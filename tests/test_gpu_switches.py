@@ -25,6 +25,7 @@ VARIANTS = [
     {"RHO_FUSE_GN_STATS": "0"},
     {"RHO_ATTN_POLY": "2"},
     {"RHO_ATTN_SPLIT": "1"},
+    {"RHO_CONV_CLUSTER": "1"},          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
 ]
 
 
