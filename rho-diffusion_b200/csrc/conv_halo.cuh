@@ -25,6 +25,7 @@ struct HaloParams {
   int N, D, H, W, Wp;
   int C1, C2, Cin, Cout;
   int kd, pd;                 // depth taps (1 or 3) and padding
+  int k1;                     // 1x1(x1) conv: one tap, no halo rows (a streaming GEMM through the same persistent pipeline)
   int n_blocks;               // Cout / BLOCK_N
   int tiles_per_plane, groups_per_plane;
   long long total_items;
@@ -85,11 +86,12 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     n = (int)(plane / p.D);
     q0 = group * MT * 128;
     mt_here = min(MT, p.tiles_per_plane - group * MT);
-    h_lo = (q0 + p.Wp - 1) / p.Wp - 2;         // floor((q0 - Wp - 1) / Wp) for q0 >= 0
+    h_lo = p.k1 ? q0 / p.Wp : (q0 + p.Wp - 1) / p.Wp - 2;         // 3x3: floor((q0 - Wp - 1) / Wp) for q0 >= 0
   };
 
   if (warp == 0) {
     // ===== TMA producer =====
+    const int ntap = p.k1 ? 1 : 9;
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
           }
           __syncwarp();
           if (++sa == p.SA) { sa = 0; pha ^= 1; }
-          for (int t9 = 0; t9 < 9; ++t9) {
+          for (int t9 = 0; t9 < ntap; ++t9) {
             mbar_wait(&b_empty[sb], phb ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[sb], B_BYTES);
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int ntap = p.k1 ? 1 : 9;
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 0;
     for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
         for (int dd = 0; dd < p.kd; ++dd) {
           mbar_wait(&a_full[sa], pha);
           const uint32_t a_addr = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int shift = (t9 / 3 - 1) * p.Wp + (t9 % 3 - 1);
+          for (int t9 = 0; t9 < ntap; ++t9) {
+            const int shift = p.k1 ? 0 : (t9 / 3 - 1) * p.Wp + (t9 % 3 - 1);
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
             const uint64_t bdesc = umma_desc<ROW_BYTES>(smem_u32(sB + sb * B_BYTES));
@@ -291,7 +294,8 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   HaloPlan pl;
   memset(&pl, 0, sizeof(pl));
   if (halo_mode() == 0 || tc_disabled()) return pl;
-  if (kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return pl;
+  const bool k1 = kd == 1 && kh == 1 && kw == 1;
+  if (!k1 && (kh != 3 || kw != 3 || (kd != 1 && kd != 3))) return pl;
   const int bk = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : ((C1 % 32 == 0 && C2 % 32 == 0) ? 32 : 0);
   if (bk == 0 || (Cout != 32 && Cout != 64 && Cout != 128) || (Cout == 128 && bk != 64)) return pl;
   if (W < 16 || W > 255 || (long long)H * (W + 1) < 256) return pl;
@@ -301,6 +305,7 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   p.N = N; p.D = D; p.H = H; p.W = W; p.Wp = W + 1;
   p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
   p.kd = kd; p.pd = kd / 2;
+  p.k1 = k1 ? 1 : 0;
   p.n_blocks = 1;
   p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
   // static shared memory: statistics scratch (8 warps x BLOCK_N channels x 2 floats), bias, barriers; 1 KB alignment slack, 1 KB reserve
@@ -314,8 +319,8 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
     int R = 0;
     for (int g = 0; g < p.groups_per_plane; ++g) {
       const int q0 = g * mt * 128;
-      const int h_lo = (q0 + p.Wp - 1) / p.Wp - 2;
-      const int last = q0 + mt * 128 - 1 + p.Wp + 1;          // highest flat row any tap of the group touches
+      const int h_lo = k1 ? q0 / p.Wp : (q0 + p.Wp - 1) / p.Wp - 2;
+      const int last = q0 + mt * 128 - 1 + (k1 ? 0 : p.Wp + 1);          // highest flat row any tap of the group touches
       R = std::max(R, last / p.Wp - h_lo + 1);
     }
     if (R > 256) continue;
@@ -375,7 +380,7 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
     int rc = encode_view(&maps.a[s], v, box, pl.bk);
     if (rc) return rc;
   }
-  int rc = encode_weight_map(&maps.w, w, (long long)p.kd * 9 * p.Cin, p.Cout, pl.bk, pl.bn);
+  int rc = encode_weight_map(&maps.w, w, (long long)(p.k1 ? 1 : p.kd * 9) * p.Cin, p.Cout, pl.bk, pl.bn);
   if (rc) return rc;
 #define RHO_HALO(BN, MT, BK) \
   if (pl.bn == BN && pl.mt == MT && pl.bk == BK) return launch_halo<BN, MT, BK>(maps, pl, bias, residual, y, y2, st)

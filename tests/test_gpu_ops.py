@@ -177,6 +177,7 @@ CONV_CASES = [
     (2, 2, 64, 32, 64, (30, 33), 1, 1, 1, False),
     (2, 1, 32, 0, 64, (64, 64), 1, 1, 1, False),
     (3, 1, 64, 32, 32, (2, 24, 24), 1, 1, 1, False),
+    (3, 2, 128, 64, 128, (2, 17, 20), 1, 1, 1, True),          # 1x1x1 on 64-channel blocks through the halo kernel's streaming mode, residual
 ]
 
 
