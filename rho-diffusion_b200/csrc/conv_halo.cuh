@@ -15,6 +15,10 @@
 // The kernel is persistent (one CTA per SM, static round-robin over work items) with double-buffered TMEM accumulators,
 // so the epilogue of item i overlaps the MMAs of item i + 1.  Rows with q % Wp == 0 are the padding column: computed and
 // dropped (1 / Wp waste).
+// Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per scheduler, alternating tiles of an
+// item; a single epilogue warp per scheduler ran at 0.36 IPC and bounded the 32-channel layers).
+// 1x1 convs (k1) run through the same pipeline as a streaming GEMM: one tap, shift 0, slabs without halo rows.  In the
+// per-tap kernel their short K loops leave every tile latency-bound (3.0 TB/s); here they reach 4.9 - 5.2 TB/s.
 #pragma once
 
 namespace rho {
