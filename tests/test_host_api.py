@@ -189,3 +189,23 @@ def test_spherical_harmonic_dataset_matches_reference():
     l, m = g["random_sets"][0]
     assert x.shape == (1, 32, 32, 32) and x.dtype == torch.float32 and len(ds) == 1000
     assert torch.equal(emb, calculate_sha512_embedding({"l": l, "m": m}, l=256))
+
+
+def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the CUDA path) needs no GPU: one bounded config-D eval of the oracle
+    port on the host cores, one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RHO_BENCH_CPU_BUDGET_S="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "UNet denoise evals/s" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
