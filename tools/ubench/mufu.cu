@@ -1,3 +1,4 @@
+// build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -o mufu mufu.cu   (run on the GPU box: gpurun -- tools/ubench/mufu)
 // Throughput of ex2.approx.ftz.f32 vs ex2.approx.ftz.bf16x2 (elements / clk / SM) and of fma.rn.f32x2 vs fma.rn.f32.
 #include <cstdio>
 #include <cuda_bf16.h>

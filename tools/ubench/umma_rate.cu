@@ -1,3 +1,4 @@
+// build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -o umma_rate umma_rate.cu   (run on the GPU box: gpurun -- tools/ubench/umma_rate)
 // Experiment: cycles per tcgen05.mma (cta_group::1, kind::f16, M = 128, K = 16) as a function of N and of the operand row width
 // (128-byte rows / SWIZZLE_128B vs 64-byte rows / SWIZZLE_64B), one CTA per SM, one issuing thread, operands resident in
 // shared memory (contents irrelevant).  Answers: are the N = 32 / N = 64 MMAs of the small-channel convs operand-fetch bound?

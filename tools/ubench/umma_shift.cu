@@ -1,3 +1,4 @@
+// build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -o umma_shift umma_shift.cu   (run on the GPU box: gpurun -- tools/ubench/umma_shift)
 // Experiment: does a K-major SWIZZLE_128B UMMA operand descriptor accept a start address shifted by whole 128-byte rows
 // (not 1024-aligned), and which base_offset value does it need?  D[128x64] = A[shift:shift+128, 0:64] * B[64x64]^T.
 #include <cstdio>
