@@ -354,6 +354,30 @@ def gen_sph_harm(ref):
     print("sph_harm fixture:", first)
 
 
+def gen_deep_galaxy(ref):
+    """Class-level parameter space of the UNMODIFIED reference's DeepGalaxyDataset (rho_diffusion/data/deep_galaxy.py:41-47) and the
+    state-dict manifest of the backbone examples/config_deep_galaxy.json builds with it (UNetv2 kwargs :5-26, MultiEmbeddings over
+    that space with embedding_dim 128 as scripts/inference.py:122-143 passes it).  h5py (absent) is shimmed for the import."""
+    import importlib
+    import json
+    import types
+    if "h5py" not in sys.modules:
+        sys.modules["h5py"] = types.SimpleNamespace(File=object)
+    dg = importlib.import_module("rho_diffusion.data.deep_galaxy")
+    space = OrderedDict((k, [float(v) for v in vals]) for k, vals in dg.DeepGalaxyDataset.parameter_space.param_dict.items())
+    with open("/root/reference/examples/config_deep_galaxy.json") as fh:
+        cfg = json.load(fh)
+    kwargs = dict(cfg["model"]["kwargs"])
+    kwargs.pop("cond_fn")
+    kwargs["cond_fn"] = ref.MultiEmbeddings(parameter_space=dg.DeepGalaxyDataset.parameter_space, embedding_dim=128)
+    model = ref.UNet(**kwargs)
+    manifest = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    torch.save({"parameter_space": space, "manifest": manifest, "inference_parameter_space": cfg["inference"]["parameter_space"]},
+               os.path.join(OUT, "deep_galaxy.pt"))
+    print("deep_galaxy fixture:", {k: len(v) for k, v in space.items()}, len(manifest), "tensors",
+          sum(int(torch.tensor(v).prod()) for v in manifest.values()), "parameters")
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -367,6 +391,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sph_harm":
         gen_sph_harm(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "deep_galaxy":
+        gen_deep_galaxy(ref)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "loss_curve":
         gen_loss_curve(ref)
         return
@@ -376,6 +403,7 @@ def main():
     gen_ddpm(ref)
     gen_gaussian(ref)
     gen_sph_harm(ref)
+    gen_deep_galaxy(ref)
     gen_loss_curve(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

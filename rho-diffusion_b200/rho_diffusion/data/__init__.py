@@ -1,5 +1,6 @@
 from rho_diffusion.data.parameter_space import AbstractParameterSpace, DiscreteParameterSpace, sample_from_discrete_parameter_space
+from rho_diffusion.data.deep_galaxy import DeepGalaxyDataset
 from rho_diffusion.data.synthetic import SphericalHarmonicDataset, compute_spherical_harmonic, make_spherical_grid
 
-__all__ = ["AbstractParameterSpace", "DiscreteParameterSpace", "sample_from_discrete_parameter_space", "SphericalHarmonicDataset",
+__all__ = ["AbstractParameterSpace", "DiscreteParameterSpace", "sample_from_discrete_parameter_space", "SphericalHarmonicDataset", "DeepGalaxyDataset",
            "compute_spherical_harmonic", "make_spherical_grid"]

@@ -24,6 +24,24 @@ from rho_diffusion.config import ExperimentConfig  # noqa: E402
 from rho_diffusion.registry import registry  # noqa: E402
 
 
+def build_pipeline(config, device, n_samples: int, steps: int = 0):
+    """The GaussianDiffusionPipeline of ``config`` as the reference's inference script assembles it (scripts/inference.py:122-143).
+    Returns (pipeline, cond_fn_kwargs or None)."""
+    schedule = registry.get("schedules", config.noise_schedule.name)(device=device, **config.noise_schedule.kwargs)
+    parameter_space = registry.get("datasets", config.dataset.name).parameter_space
+    cond_fn = config.model.kwargs.get("cond_fn")
+    # the shipped spherical-harmonics labels are same-shape sha512 embeddings (added to the time embedding directly,
+    # unet_v2.py:705-712); MultiEmbeddings is only built when the dataset class exposes a discrete parameter space
+    cond_kwargs = {"parameter_space": parameter_space, "embedding_dim": 128} if (cond_fn and parameter_space is not None) else None
+    model = diffusion.GaussianDiffusionPipeline(
+        backbone=config.model.name, backbone_kwargs=config.model.kwargs, schedule=schedule, loss_func=config.training.loss_fn,
+        timesteps=steps or config.noise_schedule.kwargs["num_steps"], cond_fn=cond_fn if cond_kwargs else None,
+        cond_fn_kwargs=cond_kwargs, optimizer=config.optimizer.name, opt_kwargs=config.optimizer.kwargs,
+        sample_every_n_epochs=config.training.sample_every_n_epochs, sampling_batch_size=n_samples,
+        sample_parameter_space=config.inference.parameter_space)
+    return model, cond_kwargs
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("json_config", type=Path)
@@ -41,18 +59,7 @@ def main():
     config = ExperimentConfig.from_json(args.json_config)
     torch.manual_seed(config.inference.seed)
     device = torch.device(args.device)
-    schedule = registry.get("schedules", config.noise_schedule.name)(device=device, **config.noise_schedule.kwargs)
-    parameter_space = registry.get("datasets", config.dataset.name).parameter_space
-    cond_fn = config.model.kwargs.get("cond_fn")
-    # the shipped spherical-harmonics labels are same-shape sha512 embeddings (added to the time embedding directly,
-    # unet_v2.py:705-712); MultiEmbeddings is only built when the dataset class exposes a discrete parameter space
-    cond_kwargs = {"parameter_space": parameter_space, "embedding_dim": 128} if (cond_fn and parameter_space is not None) else None
-    model = diffusion.GaussianDiffusionPipeline(
-        backbone=config.model.name, backbone_kwargs=config.model.kwargs, schedule=schedule, loss_func=config.training.loss_fn,
-        timesteps=args.steps or config.noise_schedule.kwargs["num_steps"], cond_fn=cond_fn if cond_kwargs else None,
-        cond_fn_kwargs=cond_kwargs, optimizer=config.optimizer.name, opt_kwargs=config.optimizer.kwargs,
-        sample_every_n_epochs=config.training.sample_every_n_epochs, sampling_batch_size=args.n_samples,
-        sample_parameter_space=config.inference.parameter_space)
+    model, cond_kwargs = build_pipeline(config, device, args.n_samples, args.steps)
     ckpt = args.model_checkpoint_path or config.inference.checkpoint
     model.backbone.load_state_dict(torch.load(ckpt), strict=True)
     model.eval()

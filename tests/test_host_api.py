@@ -209,3 +209,32 @@ def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_deep_galaxy_config_builds_the_reference_checkpoint_layout():
+    """examples/config_deep_galaxy.json (the reference's file up to the device strings) through scripts/inference.py::build_pipeline on
+    CPU: DeepGalaxyDataset's class-level parameter space equals the reference's (deep_galaxy.py:41-47), and the backbone -- UNetv2 +
+    MultiEmbeddings over that space -- has exactly the reference's state-dict keys and shapes, so its model.pth loads strictly."""
+    import importlib.util
+    from conftest import load_golden
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = load_golden("deep_galaxy.pt")
+    from rho_diffusion.config import ExperimentConfig
+    from rho_diffusion.data import DeepGalaxyDataset
+    space = DeepGalaxyDataset.parameter_space
+    assert list(space.keys()) == list(g["parameter_space"].keys())
+    for k, vals in g["parameter_space"].items():
+        assert [float(v) for v in space[k]] == vals, k
+    with pytest.raises(NotImplementedError):
+        DeepGalaxyDataset(path="missing.h5")
+    spec = importlib.util.spec_from_file_location("rho_inference_script", os.path.join(root, "scripts", "inference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    config = ExperimentConfig.from_json(os.path.join(root, "examples", "config_deep_galaxy.json"))
+    assert {k: [float(v) for v in vals] for k, vals in config.inference.parameter_space.items()} == \
+        {k: [float(v) for v in vals] for k, vals in g["inference_parameter_space"].items()}
+    pipe, cond_kwargs = mod.build_pipeline(config, torch.device("cpu"), n_samples=4, steps=10)
+    assert cond_kwargs is not None and cond_kwargs["embedding_dim"] == 128
+    got = {k: tuple(v.shape) for k, v in pipe.backbone.state_dict().items()}
+    assert got == g["manifest"]
+    assert sum(int(torch.tensor(s).prod()) for s in got.values()) == 15863457
