@@ -461,7 +461,12 @@ static int launch_attn_tc(const CUtensorMap& qmap, const CUtensorMap& kvmap, con
   return RHO_OK;
 }
 
+// attention_tc2.cu: 128-key tiles, P in tensor memory, two query tiles per CTA (head dim 64, long sequences)
+bool attention_fwd_tc2_supported(const rho_attn_params* p);
+int attention_fwd_tc2(const rho_attn_params* p, cudaStream_t st);
+
 int attention_fwd_tc(const rho_attn_params* p, cudaStream_t st) {
+  if (attention_fwd_tc2_supported(p)) return attention_fwd_tc2(p, st);
   auto enc = get_encode();
   if (!enc) return fail(RHO_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
   const int C = p->heads * p->ch;
