@@ -207,6 +207,10 @@ typedef struct rho_attn_params {
   float* lse;                /* [N, heads, T] log-sum-exp of the scaled logits, or NULL (inference) */
 } rho_attn_params;
 int rho_attention_fwd(const rho_attn_params* p, rho_stream_t stream);
+/* Debug hook (tools/attn_trace.py): `buf` = device array of 64*16 int64 (or NULL to switch off).  While set, CTA (0,0,0) of the
+ * head-dim-64 tcgen05 forward writes clock64() stamps of its warp hand-offs, [key tile][slot]: slots 0/1 (2/3) = row owners of
+ * query tile 0 (1) saw S ready / published P; slots 4/5 (6/7) = the MMA issuer saw P of tile 0 (1) / finished issuing for it. */
+void rho_debug_attention_trace(void* buf);
 typedef struct rho_attn_bwd_params {
   rho_attn_params fwd;       /* qkv, out, lse from the forward */
   const void* dout;          /* [N, T, heads*ch] */

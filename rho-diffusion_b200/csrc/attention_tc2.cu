@@ -13,8 +13,11 @@
 //                                                           -> TMEM columns [256 + 64 i, +64)
 // While warp-group 0 exponentiates S_0 the tensor core runs QK_1 / PV_1 and vice versa, so the MUFU (16 ex2 / clk / SM: the
 // bound at head dim 64) never waits for an MMA and the N = 64 PV MMA fetches only 2 KB of V per K step from shared memory.
-// The issuer launches QK_i(j+1) BEFORE PV_i(j) (both only need P_i(j) complete), so the next logits arrive 256 clk earlier;
-// the row owners therefore wait for PV_i(j) (o_done) before their first P store of tile j+1.
+// The issuer launches QK_i(j+1) BEFORE PV_i(j) (both only need P_i(j) complete), so the next logits arrive 256 clk earlier
+// (PV first: 680 vs 759 TFLOP/s); the row owners therefore wait for PV_i(j) (o_done) before their first P store of tile j+1.
+// Measured variants that did not pay (tools/attn_trace.py timelines, profiles/r02_attn_*): S produced / consumed in 64-key halves
+// with their own barriers (N = 64 QK MMAs cost 45 clk each instead of 64 per two: 720 TFLOP/s); two threads per query row
+// (16 softmax warps, one 64-thread barrier.red.or per tile for the redo vote: 802 TFLOP/s).
 // Softmax bookkeeping: p = exp2(s c - m c) against the running max known BEFORE the tile; no per-element max is taken on
 // the common path -- an outgrown max shows up as a row sum > 2^16 (some p > 2^9), in which case the warp takes the exact
 // max, rescales its O rows in TMEM and redoes the tile (P is not aliased onto S, so S is still there).  The stale max
@@ -36,8 +39,12 @@ struct AttnTc2Params {
   int T, heads, C;
   int q_col, k_col, v_col, head_stride;
   float scale_log2, scale;
-  int pv_first;               // tuning hook: issue PV_i(j) before QK_i(j+1)
+  int ld_split;               // tuning hook: start the exponentials after the first 32-column TMEM load
+  long long* trace;           // debug: clock64 stamps of CTA (0,0,0)'s hand-offs, [tile][8] (tools/attn_trace.py), or null
 };
+__device__ __forceinline__ void a2_stamp(const AttnTc2Params& p, int j, int slot) {
+  if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && j < 64 && (threadIdx.x & 31) == 0) p.trace[j * 16 + slot] = clock64();
+}
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (P) is read from tensor memory (lane = row, two bf16 per 32-bit column)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -127,15 +134,17 @@ __device__ __forceinline__ float a2_rowmax(uint32_t ts, int kvalid) {
 // still reads the P buffer) is awaited right before the first P store.
 template <bool FULL, int POLY_MASK>
 __device__ __forceinline__ float a2_exp_pass(uint32_t ts, uint32_t tp, int kvalid, float mb, float scale_log2, uint64_t* wait_bar,
-                                             uint32_t wait_parity) {
+                                             uint32_t wait_parity, int ld_split) {
   const uint64_t scale2 = pack2(scale_log2, scale_log2);
   const uint64_t negmb2 = pack2(-mb, -mb);
   uint64_t ls0 = 0ull, ls1 = 0ull;
   uint32_t a[32], b[32], packed[16];
   tmem_ld32_async(ts, a);
+  if (ld_split) tmem_wait_ld();
   tmem_ld32_async(ts + 32u, b);
-  tmem_wait_ld();
+  if (!ld_split) tmem_wait_ld();
   a2_exp32<FULL, POLY_MASK>(a, 0, kvalid, scale2, negmb2, ls0, ls1, packed);
+  tmem_wait_ld();
   tmem_ld32_async(ts + 64u, a);
   if (wait_bar) {
     mbar_wait(wait_bar, wait_parity);
@@ -244,19 +253,31 @@ __global__ void __launch_bounds__(320, 1)
     tc_fence_after();
     issue_qk(0, 0);
     issue_qk(1, 0);
+    // The issuer's own instruction latency is on the row owners' critical loop (p_ready -> QK -> s_ready): everything that does
+    // not depend on P (waiting for the K / V stages, which the producer fills tiles ahead) happens BEFORE the p_ready wait, and
+    // the MMAs of a hand-off are issued straight-line from one elected region.  Measured dead ends (tools/attn_trace.py): a
+    // rolled K loop (240 clk per MMA of scalar latency), polling the other tile's p_ready between PV groups so that its QK
+    // cuts in line (648 vs 737 TFLOP/s: three elected regions + polls cost more than the queueing they remove).
     for (int j = 0; j < nt; ++j) {
       const int sj = j % A2_ST;
 #pragma unroll 1
       for (int i = 0; i < 2; ++i) {
-        mbar_wait(&p_ready[i], (uint32_t)j & 1);      // P_i(j) is in TMEM and the row owners are done reading S_i(j)
-        if (j + 1 < nt && !p.pv_first) {
-          if (i == 0) mbar_wait(&k_full[(j + 1) % A2_ST], (uint32_t)((j + 1) / A2_ST) & 1);
-          tc_fence_after();
-          issue_qk(i, j + 1);
+        if (i == 0) {
+          if (j + 1 < nt) mbar_wait(&k_full[(j + 1) % A2_ST], (uint32_t)((j + 1) / A2_ST) & 1);
+          mbar_wait(&v_full[sj], (uint32_t)(j / A2_ST) & 1);
         }
-        if (i == 0) mbar_wait(&v_full[sj], (uint32_t)(j / A2_ST) & 1);
+        mbar_wait(&p_ready[i], (uint32_t)j & 1);      // P_i(j) is in TMEM and the row owners are done reading S_i(j)
         tc_fence_after();
+        a2_stamp(p, j, 4 + 2 * i);
         if (elect_one()) {
+          if (j + 1 < nt) {                           // S_i = Q_i K_{j+1}^T first: the row owners wait for it
+            const uint64_t a = at_desc_kmajor<128>(smem_u32(sQ + i * A2_TILE));
+            const uint64_t b = at_desc_kmajor<128>(smem_u32(sK + ((j + 1) % A2_ST) * A2_TILE));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem + (uint32_t)(128 * i), a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_qk, k != 0);
+            umma_commit(&s_ready[i]);
+            if (i == 1) umma_commit(&k_empty[(j + 1) % A2_ST]);
+          }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {               // 16 keys per MMA: 8 TMEM columns of P, two 8-row K atoms (2048 B) of V
             const uint64_t b = at_desc_mnmajor(smem_u32(sV + sj * A2_TILE + k * 16 * 128), A2_TILE);
@@ -267,11 +288,7 @@ __global__ void __launch_bounds__(320, 1)
           if (j == nt - 1) umma_commit(&o_final[i]);
         }
         __syncwarp();
-        if (j + 1 < nt && p.pv_first) {
-          if (i == 0) mbar_wait(&k_full[(j + 1) % A2_ST], (uint32_t)((j + 1) / A2_ST) & 1);
-          tc_fence_after();
-          issue_qk(i, j + 1);
-        }
+        a2_stamp(p, j, 5 + 2 * i);
       }
     }
   } else {
@@ -288,14 +305,15 @@ __global__ void __launch_bounds__(320, 1)
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_ready[i], (uint32_t)j & 1);
       tc_fence_after();
+      if ((warp & 3) == 0) a2_stamp(p, j, 2 * i);
       const int kvalid = p.T - j * A2_BN;           // keys >= kvalid are padding (only in the last tile)
       if (j == 0) m = a2_rowmax(ts, kvalid);
       float lsum;
 #pragma unroll 1
       for (int attempt = 0; attempt < 2; ++attempt) {
         uint64_t* wb = (j > 0 && attempt == 0) ? &o_done[i] : nullptr;
-        if (kvalid >= A2_BN) lsum = a2_exp_pass<true, POLY_MASK>(ts, tp, kvalid, m * p.scale_log2, p.scale_log2, wb, (uint32_t)(j - 1) & 1);
-        else lsum = a2_exp_pass<false, POLY_MASK>(ts, tp, kvalid, m * p.scale_log2, p.scale_log2, wb, (uint32_t)(j - 1) & 1);
+        if (kvalid >= A2_BN) lsum = a2_exp_pass<true, POLY_MASK>(ts, tp, kvalid, m * p.scale_log2, p.scale_log2, wb, (uint32_t)(j - 1) & 1, p.ld_split);
+        else lsum = a2_exp_pass<false, POLY_MASK>(ts, tp, kvalid, m * p.scale_log2, p.scale_log2, wb, (uint32_t)(j - 1) & 1, p.ld_split);
         if (attempt == 1 || j == 0 || !__any_sync(0xffffffffu, !(lsum <= A2_SUM_LIMIT))) break;
         // a row of this warp outgrew the stale max: exact max, rescale this row of O (PV of tile j-1 has completed: o_done was
         // awaited above), redo the tile
@@ -315,6 +333,7 @@ __global__ void __launch_bounds__(320, 1)
       l += lsum;
       tc_fence_before();          // order our tcgen05.ld / st before the MMAs the issuer launches after the barrier
       mbar_arrive(&p_ready[i]);
+      if ((warp & 3) == 0) a2_stamp(p, j, 2 * i + 1);
     }
     // ---- epilogue: O / l -> bf16 -> global
     mbar_wait(&o_final[i], 0);
@@ -346,7 +365,11 @@ __global__ void __launch_bounds__(320, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(512u));
 }
 
+
 // ---- host ---------------------------------------------------------------------------------------------
+static long long* g_attn_trace = nullptr;
+void attention_tc2_set_trace(long long* buf) { g_attn_trace = buf; }
+
 bool attention_fwd_tc2_supported(const rho_attn_params* p) {
   static int on = -1, min_t = 0;
   if (on < 0) {
@@ -392,20 +415,25 @@ int attention_fwd_tc2(const rho_attn_params* p, cudaStream_t st) {
   else { ap.q_col = 0; ap.k_col = C; ap.v_col = 2 * C; ap.head_stride = p->ch; }
   ap.scale = 1.0f / sqrtf((float)p->ch);
   ap.scale_log2 = ap.scale * 1.4426950408889634f;
-  // element pairs (of every 8) whose exponentials run on the FMA pipes instead of the MUFU: RHO_ATTN_POLY = 0 | 1 | 2 | 3 | 4
-  static int poly = -1, pvf = 0;
+  // element pairs (of every 8) whose exponentials run on the FMA pipes instead of the MUFU: RHO_ATTN_POLY = 0 | 1 | 2 | 3 | 4.
+  // Measured on B200 (T = 16384, ch = 64, N = 8): 760 / 845 / 890 / 897 / 848 TFLOP/s -- unlike the first-generation kernel this one
+  // is MUFU-limited, so the default is 3 of every 8 pairs on the FMA pipes.
+  static int poly = -1, cut = 1;
   if (poly < 0) {
-    const char* e = getenv("RHO_ATTN_POLY"); poly = e ? atoi(e) : 0;
-    const char* f = getenv("RHO_ATTN_PVFIRST"); pvf = f ? atoi(f) : 0;
+    const char* e = getenv("RHO_ATTN_POLY"); poly = e ? atoi(e) : 3;
+    const char* f = getenv("RHO_ATTN_LDSPLIT"); cut = f ? atoi(f) : 0;
   }
-  ap.pv_first = pvf;
+  ap.ld_split = cut;
+  ap.trace = g_attn_trace;
   switch (poly) {
+    case 0: return launch_attn_tc2<0x00>(map, ap, p, st);
     case 1: return launch_attn_tc2<0x02>(map, ap, p, st);
     case 2: return launch_attn_tc2<0x22>(map, ap, p, st);
-    case 3: return launch_attn_tc2<0x4A>(map, ap, p, st);
     case 4: return launch_attn_tc2<0xAA>(map, ap, p, st);
-    default: return launch_attn_tc2<0x00>(map, ap, p, st);
+    default: return launch_attn_tc2<0x4A>(map, ap, p, st);
   }
 }
 
 }  // namespace rho
+
+extern "C" void rho_debug_attention_trace(void* buf) { rho::attention_tc2_set_trace(reinterpret_cast<long long*>(buf)); }

@@ -107,6 +107,7 @@ SIGNATURES = {
     "rho_error_string": (C.c_char_p, [C.c_int]),
     "rho_last_error_message": (C.c_char_p, []),
     "rho_launch_count": (c_u64, []),
+    "rho_debug_attention_trace": (None, [c_vp]),
     "rho_nc_to_cl": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp]),
     "rho_cl_to_nc": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp]),
     "rho_add_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_i64, c_vp]),
