@@ -277,6 +277,8 @@ typedef struct rho_p_sample_params {
   float noise_scale;         /* 0.8 (ddpm.py:215) */
   float clamp_lo, clamp_hi;  /* -1, 1 (ddpm.py:218) */
   uint64_t seed;
+  const uint64_t* seed_dev;  /* optional device scalar: when non-NULL it replaces `seed` (one captured graph then serves every
+                              * reverse_process call: the host writes the run's seed into it before replaying) */
 } rho_p_sample_params;
 int rho_p_sample_step(const rho_p_sample_params* p, rho_stream_t stream);
 int rho_advance_timestep(int64_t* t_scalar, int64_t* t_vec, int32_t B, rho_stream_t stream);
@@ -358,10 +360,13 @@ int rho_x0_step(const rho_x0_step_params* p, rho_stream_t stream);
  *                 mode 3: adjoint of mode 0 (parent / window; positions the pooling dropped get 0)
  *                 (D, H, W) are the extents of `src`, (Do, Ho, Wo) those of `dst`.
  *   rho_dropout   nn.Dropout(p) of ResBlock.out_layers (unet_v2.py:239): y = x * [u >= p] / (1 - p) with u from
- *                 Philox4x32-10(counter = i / 4, offset; key = seed); the same call on dy is the backward. */
+ *                 Philox4x32-10(counter = i / 4, offset; key = seed); the same call on dy is the backward.
+ *                 `step_dev` (optional): device int32 step counter (rho_adamw_params.step_dev); its value is folded into the
+ *                 high word of the Philox offset, so a training step replayed from a CUDA graph draws a new mask every step. */
 int rho_resample(const void* src, void* dst, int dtype, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t fd, int32_t fh,
                  int32_t fw, int32_t mode, int32_t Do, int32_t Ho, int32_t Wo, rho_stream_t stream);
-int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, rho_stream_t stream);
+int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                rho_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference (intel/rho-diffusion) on CPU.
 
-Only usable where ``/root/reference`` exists (the build container); used by
-``oracle/make_golden.py`` to generate the committed fixtures under ``tests/golden/`` and by
-the (optional) live cross-check in ``tests/test_oracle_vs_reference.py``.  Nothing in the
-product path, the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this module.
+Sources: ``/root/reference`` where it exists (the build container), else the installed copy under
+``oracle/_ref`` that ``oracle/build_ref.py`` makes (git-ignored; it travels to the GPU box with the
+working tree).  Used by ``oracle/make_golden.py`` to generate the committed fixtures under
+``tests/golden/``, by the live cross-check in ``tests/test_oracle_vs_reference.py`` and by the CPU arm of
+``bench.py`` (``--impl reference`` / ``cpu_baseline``, always in its own process).  Nothing in the product
+path imports this module.
 
 The reference cannot be imported as a package (its ``__init__`` pulls lightning, diffusers,
 matplotlib, h5py, geomloss -- all absent here), so the sub-modules on the hot path are imported
@@ -21,6 +23,8 @@ import torch
 import torch.nn as nn
 
 REF_ROOT = os.environ.get("RHO_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "rho_diffusion")):
+    REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # pip-installed copy (oracle/build_ref.py)
 REF_PKG = os.path.join(REF_ROOT, "rho_diffusion")
 
 _SUBPACKAGES = ("", ".models", ".diffusion", ".data", ".metrics")

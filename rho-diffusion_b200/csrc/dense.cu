@@ -184,7 +184,9 @@ __global__ void embedding_match_kernel(const float* __restrict__ y, int y_stride
   __syncthreads();
   const int k = s_idx;
   for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-    float e = k >= 0 ? table[(long long)k * dim + d] : 0.f;
+    // a label that is not a point of the parameter space has no embedding: the reference fails on it (conditioning.py:132-137);
+    // here the row is poisoned with NaN (loud downstream, no host sync) and idx_out carries -1 for the host-side check
+    float e = k >= 0 ? table[(long long)k * dim + d] : __int_as_float(0x7fc00000);
     float* o = out + (long long)b * dim + d;
     *o = accumulate ? *o + e : e;
   }

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(rho_p_sample_params 
   const float c_eps = beta / sqrtf(1.0f - ab);
   const float c_z = p.noise_scale * sqrtf(beta);
   const bool noisy = t > 1;
+  const uint64_t seed = p.seed_dev ? *p.seed_dev : p.seed;
   const int64_t groups = (p.n + 3) / 4;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
     float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(rho_p_sample_params 
         if (full) load4(p.z + g * 4, z);
         else for (int j = 0; j < 4 && g * 4 + j < p.n; ++j) z[j] = p.z[g * 4 + j];
       } else {
-        philox_normal4((uint64_t)g, (uint64_t)t, p.seed, z);
+        philox_normal4((uint64_t)g, (uint64_t)t, seed, z);
       }
     }
     float x[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};

@@ -66,7 +66,8 @@ __device__ __forceinline__ void philox4(uint64_t ctr, uint64_t offset, uint64_t 
 // y = x * keep / (1 - p), keep_i = [u_i >= p], u_i = 24 random bits of Philox4x32-10(counter = i / 4, offset; key = seed)
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p, float scale,
-                                                      uint64_t seed, uint64_t offset) {
+                                                      uint64_t seed, uint64_t offset, const int32_t* __restrict__ step_dev) {
+  if (step_dev) offset += (uint64_t)(uint32_t)step_dev[0] << 32;      // a new mask per optimizer step under graph replay
   const long long groups = (n + 3) / 4;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];
@@ -106,12 +107,13 @@ int rho_resample(const void* src, void* dst, int dtype, int32_t N, int32_t D, in
   return RHO_OK;
 }
 
-int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, rho_stream_t stream) {
+int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, const int32_t* step_dev,
+                rho_stream_t stream) {
   RHO_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout: bad args");
   const int blocks = (int)std::min<long long>(ceil_div((n + 3) / 4, 256), (long long)sm_count() * 16);
   const float scale = 1.0f / (1.0f - p);
-  if (dtype == RHO_F32) dropout_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, p, scale, seed, offset);
-  else if (dtype == RHO_BF16) dropout_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)y, n, p, scale, seed, offset);
+  if (dtype == RHO_F32) dropout_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, p, scale, seed, offset, step_dev);
+  else if (dtype == RHO_BF16) dropout_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)y, n, p, scale, seed, offset, step_dev);
   else return fail(RHO_ERR_INVALID_ARG, "dropout: bad dtype");
   RHO_CHECK_LAUNCH("dropout");
   return RHO_OK;

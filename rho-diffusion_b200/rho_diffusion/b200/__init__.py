@@ -23,7 +23,7 @@ from rho_diffusion.utils import ddp_setup  # noqa: F401  (re-export: the backend
 
 from . import _lib, ops  # noqa: F401
 
-__all__ = ["optimize", "ddp_setup", "FusedAdamW", "GraphedTrainStep", "set_compute_dtype", "is_available"]
+__all__ = ["optimize", "ddp_setup", "FusedAdamW", "GraphedTrainStep", "set_compute_dtype", "set_dropout_seed", "is_available"]
 
 
 def is_available() -> bool:
@@ -42,19 +42,49 @@ def set_compute_dtype(model: nn.Module, dtype: torch.dtype, engine: int = 0) -> 
     return model
 
 
+def set_dropout_seed(model: nn.Module, seed: int) -> nn.Module:
+    """Keys the dropout masks of every sub-module by ``seed`` (pipeline seed + 7919 * rank) and the module's position, so that
+    layers and ranks draw independent masks (the offset within a module is the call index and the optimizer step)."""
+    for idx, m in enumerate(model.modules()):
+        m._rho_dropout_seed = (int(seed) * 1000003 + idx) & 0x7FFFFFFFFFFFFFFF
+    return model
+
+
+def partition_buckets(offsets, total: int, n_buckets: int):
+    """Cuts the flat buffer ``[0, total)`` into at most ``n_buckets`` contiguous ranges of ~equal size at parameter boundaries
+    (``offsets``: start of every parameter, ascending).  Returns ``(ranges, bucket_of)``: ``[(lo, hi), ...]`` covering
+    ``[0, total)`` without gaps and the bucket index of every parameter."""
+    n = len(offsets)
+    n_b = max(1, min(int(n_buckets), n))
+    target = total / n_b
+    ranges, bucket_of, lo, b = [], [], 0, 0
+    for i in range(n):
+        end = offsets[i + 1] if i + 1 < n else total
+        bucket_of.append(b)
+        if (end >= target * (b + 1) and b < n_b - 1) or i == n - 1:
+            ranges.append((lo, end))
+            lo, b = end, b + 1
+    return ranges, bucket_of
+
+
 class FusedAdamW:
     """torch.optim.AdamW semantics over flat fp32 buffers, fused with the EMA update, one kernel per step.
 
-    * parameters are re-pointed at slices of one contiguous buffer (values preserved; ``state_dict()`` of the
-      model is unaffected), gradients accumulate into slices of a second one;
-    * with a process group, ``step()`` first sums the flat gradient buffer across ranks with ONE NCCL all-reduce
-      and folds the 1/world mean into the update (the intended DDP semantics of scripts/training_ddp.py:171-176,
-      which the reference loses by calling ``model.module.training_step``, SURVEY quick facts);
+    * parameters are re-pointed at slices of one contiguous buffer (values preserved; ``state_dict()`` of the model is
+      unaffected); ``p.grad`` of every parameter IS a slice of a second flat buffer, and the backward kernels write the
+      parameter gradients straight into it (:class:`ops.GradSink`): no per-parameter accumulate launches, no gather copies;
+    * with a process group the flat gradient buffer is split into ``buckets`` contiguous buckets (aligned to parameter
+      boundaries, ~equal bytes).  The backward produces gradients from the END of the buffer to its start; as soon as the
+      last gradient of a bucket has been enqueued, that bucket's NCCL all-reduce (SUM) is launched asynchronously, so the
+      exchange overlaps the rest of the backward -- the bucketed, overlapped reduction the reference asks
+      ``DistributedDataParallel`` for (scripts/training_ddp.py:171-176) and then loses by calling ``model.module.training_step``
+      (SURVEY quick facts).  ``step()`` waits for the buckets and folds the 1/world mean into the update.  All of it is
+      stream-ordered, so the whole step including the collectives is capturable in one CUDA graph (GraphedTrainStep);
     * ``ema_decay > 0`` keeps a flat shadow copy with the warm-up schedule of rho_diffusion/ema.py:33.
     """
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, ema_decay: float = 0.0,
-                 process_group=None, align: int = 64):
+                 process_group=None, align: int = 64, buckets: int = 8):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FusedAdamW: no trainable parameters")
@@ -80,9 +110,15 @@ class FusedAdamW:
                 view.copy_(p.detach())
                 p.data = view
         self.flat_shadow = self.flat_p.clone() if self.ema_decay > 0 else None
-        self._bind_grads()
         self.step_id = 0
         self.step_dev = None          # set by enable_device_step(): the step counter lives on the device (graph replay)
+        # ---- buckets: contiguous [lo, hi) ranges of the flat buffers, cut at parameter boundaries
+        self.bucket_ranges, self._bucket_of = partition_buckets(offsets, total, buckets)
+        self._bucket_size = [0] * len(self.bucket_ranges)
+        for bi in self._bucket_of:
+            self._bucket_size[bi] += 1
+        self._bind_grads()
+        self.zero_grad()
         ops.bump_weights_epoch()
 
     @classmethod
@@ -96,28 +132,51 @@ class FusedAdamW:
             raise NotImplementedError("amsgrad / maximize are not supported by the fused kernel")
         return cls(g["params"], lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], **kw)
 
+    # -- gradients ---------------------------------------------------------------------------------------------------------
     def _bind_grads(self):
         self._views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        self._sinks = []
+        for p, v, b in zip(self.params, self._views, self._bucket_of):
+            p.grad = v                                   # p.grad IS the flat slice (tests / users read gradients there)
+            p._rho_sink = ops.GradSink(v, self, b)
+            self._sinks.append(p._rho_sink)
+
+    def _world(self) -> int:
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group)
+        return 1
 
     def zero_grad(self, set_to_none: bool = True):
-        """Gradients are dropped (``p.grad = None``): the first backward then hands its weight-gradient tensor to
-        ``p.grad`` without a kernel, instead of one accumulate launch per parameter tensor (329 for the 64^3 UNet);
-        :meth:`step` gathers them into the flat buffer with a handful of multi-tensor copies."""
-        for p in self.params:
-            p.grad = None
+        """The first backward kernel that produces a parameter's gradient OVERWRITES its slice, so only the slices that no
+        kernel wrote in the previous step are zeroed (unused parameters; normally none) -- a gradient that reaches such a
+        parameter through plain autograd accumulation (``p.grad += g``) then adds onto zero.  The rest is per-step bookkeeping
+        (which sinks were written, which buckets are complete / in flight)."""
+        stale = [s.view for s in self._sinks if not s.touched]
+        if stale and len(stale) < len(self._sinks):
+            torch._foreach_zero_(stale)
+        elif stale:
+            self.flat_g.zero_()
+        for s in self._sinks:
+            s.touched = False
+        self._pending = list(self._bucket_size)
+        self._works = []
+        self._reduced = [False] * len(self.bucket_ranges)
 
-    def _gather_grads(self):
-        dst, src, missing = [], [], []
-        for p, v in zip(self.params, self._views):
-            if p.grad is None:
-                missing.append(v)
-            elif p.grad.data_ptr() != v.data_ptr():
-                dst.append(v)
-                src.append(p.grad if p.grad.dtype == torch.float32 else p.grad.float())
-        if src:
-            torch._foreach_copy_(dst, src)
-        if missing:
-            torch._foreach_zero_(missing)
+    def _reduce_bucket(self, b: int):
+        lo, hi = self.bucket_ranges[b]
+        self._reduced[b] = True
+        self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.process_group, async_op=True))
+
+    def _grad_ready(self, b: int):
+        """Called by a GradSink right after the kernel that wrote its gradient was enqueued."""
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self._world() > 1:
+            self._reduce_bucket(b)
+
+    def collective_description(self) -> str:
+        mb = [(hi - lo) * 4 / 1e6 for lo, hi in self.bucket_ranges]
+        return (f"NCCL all-reduce(SUM) of the flat fp32 gradient buffer in {len(mb)} buckets ({min(mb):.0f}-{max(mb):.0f} MB), each launched "
+                "async as soon as its last gradient is enqueued (overlaps the backward); 1/world folded into the AdamW kernel")
 
     def shadow_state_dict(self, model: nn.Module) -> dict:
         """EMA weights keyed like ``model.state_dict()`` (for saving the averaged checkpoint)."""
@@ -136,7 +195,23 @@ class FusedAdamW:
         if self.step_dev is None:
             self.step_dev = torch.zeros(16, dtype=torch.int32, device=self.flat_p.device)
             self.step_dev[0] = self.step_id
+        ops.dropout_step_dev = self.step_dev      # dropout masks are keyed by the device step count from now on
         return self
+
+    def _snapshot(self):
+        return (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(),
+                None if self.flat_shadow is None else self.flat_shadow.clone(), self.step_id,
+                None if self.step_dev is None else self.step_dev.clone())
+
+    def _restore(self, snap):
+        p, m, v, sh, step_id, step_dev = snap
+        self.flat_p.copy_(p); self.flat_m.copy_(m); self.flat_v.copy_(v)
+        if sh is not None:
+            self.flat_shadow.copy_(sh)
+        self.step_id = step_id
+        if step_dev is not None:
+            self.step_dev.copy_(step_dev)
+        ops.bump_weights_epoch()
 
     @property
     def steps_taken(self) -> int:
@@ -145,12 +220,15 @@ class FusedAdamW:
     @torch.no_grad()
     def step(self):
         g = self.param_groups[0]
-        self._gather_grads()
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            world = dist.get_world_size(self.process_group)
-            if world > 1:
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.process_group)
+        # slices no kernel wrote this step were zeroed by zero_grad (or hold a gradient accumulated by plain autograd)
+        world = self._world()
+        if world > 1:
+            for b in range(len(self.bucket_ranges)):
+                if not self._reduced[b]:
+                    self._reduce_bucket(b)
+            for w in self._works:
+                w.wait()                                  # the compute stream waits for the NCCL stream (no host sync)
+            self._works = []
         self.step_id += 1
         d_t = self.ema_decay * (1.0 - math.exp(-self.step_id / 2000.0)) if self.flat_shadow is not None else 0.0
         ops.adamw_ema_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_shadow, self.step_id, g["lr"], g["betas"],
@@ -170,7 +248,9 @@ class GraphedTrainStep:
             loss = step(data, labels)          # a 0-d device tensor, valid until the next call
 
     Semantics are those of ``optimizer.zero_grad(); loss = model.training_step([data, labels]); loss.backward();
-    optimizer.step()`` (tests/test_gpu_model.py::test_graphed_train_step_matches_eager)."""
+    optimizer.step()`` (tests/test_gpu_model.py::test_graphed_train_step_matches_eager).  In a multi-process job the bucketed
+    NCCL all-reduces launched from inside the backward are part of the captured graph (fork / join onto NCCL's stream), so
+    every rank replays the same step, collectives included."""
 
     def __init__(self, pipeline, optimizer: "FusedAdamW", data: torch.Tensor, labels: torch.Tensor = None, warmup: int = 2):
         self.pipeline, self.optimizer = pipeline, optimizer
@@ -182,17 +262,33 @@ class GraphedTrainStep:
         self._t_pin = torch.zeros((data.shape[0],), dtype=torch.int64).pin_memory()
         optimizer.enable_device_step()
         self._draw()
+        # the warm-up runs REAL steps (allocator pools, packed-weight caches, kernel attributes): weights, moments, EMA shadow and
+        # the step counters are put back afterwards, so the first replay is optimizer step 1 on the caller's parameters
+        snap = optimizer._snapshot()
+        noise_calls = getattr(pipeline, "_noise_calls", None)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):           # allocator pools, packed-weight caches, kernel attributes
+            for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
-        self.steps = warmup                   # optimizer steps already taken by the warm-up
+        optimizer._restore(snap)
+        del snap
+        if noise_calls is not None:
+            pipeline._noise_calls = noise_calls
+        self.steps = 0
+
+    def close(self):
+        """Releases the captured graph.  A graph that holds NCCL collectives must be released BEFORE the process group is
+        destroyed (destroying the communicator with such a graph alive hangs)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
 
     def _batch(self):
         return [self.data, self.labels] if self.labels is not None else self.data
@@ -238,6 +334,7 @@ def optimize(model: nn.Module, optimizer=None, dtype: torch.dtype = torch.bfloat
     if any(p.device.type != "cuda" for p in inner.parameters()):
         raise _lib.RhoB200Error("optimize(): move the model to a CUDA device first (there is no CPU path)")
     set_compute_dtype(inner, dtype, engine)
+    set_dropout_seed(inner, int(getattr(inner, "seed", 0)) + 7919 * int(getattr(inner, "global_rank", 0)))
     if optimizer is None:
         return inner
     fused = optimizer if isinstance(optimizer, FusedAdamW) else FusedAdamW.from_torch(optimizer, ema_decay=ema_decay)

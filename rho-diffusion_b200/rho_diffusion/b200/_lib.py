@@ -79,6 +79,7 @@ class PSampleParams(C.Structure):
     _fields_ = [
         ("x", c_vp), ("eps", c_vp), ("z", c_vp), ("t", c_vp), ("alpha", c_vp), ("beta", c_vp), ("alpha_bar", c_vp),
         ("T", c_i32), ("n", c_i64), ("noise_scale", c_f32), ("clamp_lo", c_f32), ("clamp_hi", c_f32), ("seed", c_u64),
+        ("seed_dev", c_vp),
     ]
 
 
@@ -150,7 +151,7 @@ SIGNATURES = {
     "rho_abs_quantile": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp, c_vp, c_sz, c_vp]),
     "rho_x0_step": (C.c_int, [P(X0StepParams), c_vp]),
     "rho_resample": (C.c_int, [c_vp, c_vp, C.c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "rho_dropout": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_f32, c_u64, c_u64, c_vp]),
+    "rho_dropout": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_f32, c_u64, c_u64, c_vp, c_vp]),
 }
 
 _lib = None

@@ -150,6 +150,35 @@ def bump_weights_epoch():
     _weights_epoch += 1
 
 
+class GradSink:
+    """Destination of one parameter's gradient inside the fused optimizer's flat fp32 gradient buffer.
+
+    The backward kernels (conv wgrad, GroupNorm / Linear / embedding backward) write the parameter gradient STRAIGHT into
+    ``view`` -- a slice of the flat buffer shaped like the parameter -- and the autograd Function returns ``None`` for it, so
+    there is neither a per-parameter accumulate launch nor a gather copy.  First touch per step overwrites (no zero pass);
+    a parameter that receives a second contribution before ``zero_grad`` falls back to autograd's accumulation, which adds
+    into the same view (``p.grad`` IS the view).  ``done`` notifies the optimizer, which launches the all-reduce of a
+    bucket as soon as the last gradient of that bucket has been enqueued (overlap with the rest of the backward)."""
+    __slots__ = ("view", "owner", "bucket", "touched")
+
+    def __init__(self, view, owner, bucket):
+        self.view, self.owner, self.bucket, self.touched = view, owner, bucket, False
+
+    def done(self):
+        self.touched = True
+        self.owner._grad_ready(self.bucket)
+
+
+def grad_sink(param, needed: bool = True):
+    """The untouched sink of ``param`` (a fused-optimizer parameter), or None (plain autograd path)."""
+    if not needed or param is None:
+        return None
+    sink = getattr(param, "_rho_sink", None)
+    if sink is None or sink.touched:
+        return None
+    return sink
+
+
 def packed_weight(owner, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """[Cout, Cin, *k] fp32 (state-dict layout) -> [Cout, taps, Cin] in ``dtype``.
 
@@ -268,7 +297,8 @@ def _conv_forward(x, x2, wp, bias, residual, spec: ConvSpec, Cout, engine=L.CONV
     return y
 
 
-def conv_backward(x, x2, wp, dy, spec: ConvSpec, Cout, need_dx, need_dw, need_db, w_shape, engine=L.CONV_AUTO):
+def conv_backward(x, x2, wp, dy, spec: ConvSpec, Cout, need_dx, need_dw, need_db, w_shape, engine=L.CONV_AUTO, dw_out=None, db_out=None):
+    """``dw_out`` / ``db_out``: optional fp32 destinations (flat-gradient slices) the weight-gradient kernels write directly."""
     dy = dy.contiguous()
     bp = L.ConvBwdParams()
     bp.fwd = _conv_params(x, x2, wp, None, None, None, spec, Cout, engine, False)
@@ -284,9 +314,9 @@ def conv_backward(x, x2, wp, dy, spec: ConvSpec, Cout, need_dx, need_dw, need_db
         L.check(L.lib().rho_conv_dgrad(C.byref(bp), stream()), "conv_dgrad")
     if need_dw or need_db:
         if need_dw:
-            dw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+            dw = dw_out if dw_out is not None else torch.empty(w_shape, dtype=torch.float32, device=x.device)
         if need_db:
-            db = torch.empty((Cout,), dtype=torch.float32, device=x.device)
+            db = db_out if db_out is not None else torch.empty((Cout,), dtype=torch.float32, device=x.device)
         bp.dw, bp.dbias = ptr(dw), ptr(db)
         L.check(L.lib().rho_conv_wgrad(C.byref(bp), stream()), "conv_wgrad")
     return dx, dx2, dw, db
@@ -304,6 +334,7 @@ class ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, x2, wp)
         ctx.spec, ctx.engine, ctx.has_bias, ctx.has_res = spec, engine, bias is not None, residual is not None
         ctx.w_shape = tuple(weight.shape)
+        ctx.params = (weight, bias)          # the Parameters themselves: their gradient sinks are looked up in backward
         return y
 
     @staticmethod
@@ -312,8 +343,14 @@ class ConvFn(torch.autograd.Function):
         if dy.dtype != x.dtype:  # y_f32 head: gradient arrives in fp32
             dy = cast(dy, x.dtype)
         need_dx = ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1])
-        dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, ctx.w_shape[0], need_dx, ctx.needs_input_grad[2],
-                                        ctx.has_bias and ctx.needs_input_grad[4], ctx.w_shape, ctx.engine)
+        need_dw, need_db = ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[4]
+        sw, sb = grad_sink(ctx.params[0], need_dw), grad_sink(ctx.params[1], need_db)
+        dx, dx2, dw, db = conv_backward(x, x2, wp, dy, ctx.spec, ctx.w_shape[0], need_dx, need_dw, need_db, ctx.w_shape, ctx.engine,
+                                        dw_out=sw.view if sw else None, db_out=sb.view if sb else None)
+        if sw:
+            sw.done(); dw = None
+        if sb:
+            sb.done(); db = None
         dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
         return dx, dx2, dw, None, db, dres, None, None, None, None, None
 
@@ -448,6 +485,7 @@ class GnActFn(torch.autograd.Function):
         y, stats = gn_forward(x, x2, g32, b32, film, pre_add, act, out_dtype, groups, eps)
         ctx.save_for_backward(x, x2, g32, b32, film, pre_add, stats)
         ctx.act, ctx.groups, ctx.eps = act, groups, eps
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -460,8 +498,9 @@ class GnActFn(torch.autograd.Function):
         bp.fwd.out_dtype = dt(dy)
         dx = torch.empty_like(x)
         dx2 = torch.empty_like(x2) if x2 is not None else None
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(beta)
+        sg, sbt = grad_sink(ctx.params[0], ctx.needs_input_grad[2]), grad_sink(ctx.params[1], ctx.needs_input_grad[3])
+        dgamma = sg.view if sg else torch.empty_like(gamma)
+        dbeta = sbt.view if sbt else torch.empty_like(beta)
         dfilm = torch.empty_like(film) if film is not None else None
         dpre = torch.empty((x.shape[0], Ct), dtype=torch.float32, device=x.device) if pre_add is not None else None
         bp.dy, bp.dx, bp.dx2, bp.dgamma, bp.dbeta = ptr(dy), ptr(dx), ptr(dx2), ptr(dgamma), ptr(dbeta)
@@ -473,6 +512,10 @@ class GnActFn(torch.autograd.Function):
         ws = workspace(L.lib().rho_gn_bwd_workspace_bytes(C.byref(bp)), x.device)
         bp.workspace, bp.workspace_bytes = ws.data_ptr(), ws.numel()
         L.check(L.lib().rho_gn_bwd(C.byref(bp), stream()), "gn_bwd")
+        if sg:
+            sg.done(); dgamma = None
+        if sbt:
+            sbt.done(); dbeta = None
         return dx, dx2, dgamma, dbeta, dfilm, dpre, None, None, None, None
 
 
@@ -562,6 +605,7 @@ class LinearFn(torch.autograd.Function):
         L.check(L.lib().rho_linear_fwd(C.byref(p), stream()), "linear_fwd")
         ctx.save_for_backward(x, w)
         ctx.act_in, ctx.has_bias, ctx.has_add = act_in, bias is not None, add is not None
+        ctx.params = (weight, bias)
         return y
 
     @staticmethod
@@ -570,10 +614,16 @@ class LinearFn(torch.autograd.Function):
         dy = dy.float().contiguous()
         p = _linear_params(x, w, None, None, None, ctx.act_in)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-        db = torch.empty((w.shape[0],), dtype=torch.float32, device=x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        sw, sb = grad_sink(ctx.params[0], ctx.needs_input_grad[1]), grad_sink(ctx.params[1], need_db)
+        dw = (sw.view if sw else torch.empty_like(w)) if ctx.needs_input_grad[1] else None
+        db = (sb.view if sb else torch.empty((w.shape[0],), dtype=torch.float32, device=x.device)) if need_db else None
         L.check(L.lib().rho_linear_bwd(C.byref(p), dy.data_ptr(), dy.stride(0), ptr(dx), dx.stride(0) if dx is not None else 0,
                                        ptr(dw), ptr(db), stream()), "linear_bwd")
+        if sw:
+            sw.done(); dw = None
+        if sb:
+            sb.done(); db = None
         dadd = dy if (ctx.has_add and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dadd, None
 
@@ -583,7 +633,9 @@ def linear(x, weight, bias=None, add=None, act_in=L.ACT_NONE):
 
 
 class EmbeddingMatchFn(torch.autograd.Function):
-    """sum_i table_i[index of y[:, i] in values_i] (MultiEmbeddings.forward, models/conditioning.py:115-139)."""
+    """sum_i table_i[index of y[:, i] in values_i] (MultiEmbeddings.forward, models/conditioning.py:115-139).  Rows with a value
+    that matches no point of the space come out as NaN; ``last_indices`` ([n_keys, B] int32, -1 = no match) lets the caller check."""
+    last_indices = None
 
     @staticmethod
     def forward(ctx, y, values_list, *tables):
@@ -600,7 +652,9 @@ class EmbeddingMatchFn(torch.autograd.Function):
             L.check(L.lib().rho_embedding_match(y.data_ptr() + 4 * i, y.stride(0), B, vals.data_ptr(), vals.numel(), tab32.data_ptr(), dim,
                                                 out.data_ptr(), int(i > 0), idxs[i].data_ptr(), stream()), "embedding_match")
         ctx.save_for_backward(idxs)
+        EmbeddingMatchFn.last_indices = idxs
         ctx.shapes = [tuple(t.shape) for t in tables]
+        ctx.params = tables
         return out
 
     @staticmethod
@@ -612,10 +666,13 @@ class EmbeddingMatchFn(torch.autograd.Function):
             if not ctx.needs_input_grad[2 + i]:
                 grads.append(None)
                 continue
-            g = torch.zeros(shp, dtype=torch.float32, device=dout.device)
+            sink = grad_sink(ctx.params[i])
+            g = sink.view.zero_() if sink else torch.zeros(shp, dtype=torch.float32, device=dout.device)
             L.check(L.lib().rho_embedding_match_bwd(idxs[i].data_ptr(), dout.shape[0], dout.data_ptr(), shp[1], g.data_ptr(), shp[0],
                                                     stream()), "embedding_match_bwd")
-            grads.append(g)
+            if sink:
+                sink.done()
+            grads.append(None if sink else g)
         return (None, None, *grads)
 
 
@@ -640,9 +697,11 @@ def q_sample(x0, noise, t, alpha_bar):
     return out
 
 
-def p_sample_step(x, eps, z, t_scalar, alpha, beta, alpha_bar, noise_scale=0.8, clamp=(-1.0, 1.0), seed=0):
-    """In-place ancestral update of ``x`` (fp32); ``t_scalar`` is a 1-element int64 device tensor."""
+def p_sample_step(x, eps, z, t_scalar, alpha, beta, alpha_bar, noise_scale=0.8, clamp=(-1.0, 1.0), seed=0, seed_dev=None):
+    """In-place ancestral update of ``x`` (fp32); ``t_scalar`` is a 1-element int64 device tensor.  ``seed_dev``: optional
+    1-element int64 device tensor that replaces ``seed`` (a captured graph then serves every run)."""
     p = L.PSampleParams()
+    p.seed_dev = ptr(seed_dev)
     p.x, p.eps, p.z, p.t = x.data_ptr(), eps.data_ptr(), ptr(z), t_scalar.data_ptr()
     p.alpha, p.beta, p.alpha_bar, p.T = alpha.data_ptr(), beta.data_ptr(), alpha_bar.data_ptr(), alpha_bar.numel()
     p.n, p.noise_scale, p.clamp_lo, p.clamp_hi, p.seed = x.numel(), noise_scale, clamp[0], clamp[1], seed
@@ -804,10 +863,23 @@ def upsample_nearest(x, factors):
 
 
 _dropout_calls = 0
+dropout_step_dev: Optional[torch.Tensor] = None      # device step counter (FusedAdamW.enable_device_step) folded into the mask offset
+
+
+def weights_signature(module) -> tuple:
+    """Changes whenever parameter memory of ``module`` may have been rewritten: optimizer steps of the fused optimizer (epoch),
+    in-place updates under autograd / ``load_state_dict`` / EMA swaps (version counters), re-pointed storage (addresses)."""
+    ver = ptrs = 0
+    for q in module.parameters():
+        ver += q._version
+        ptrs ^= q.data_ptr()
+    return (_weights_epoch, ver, ptrs)
 
 
 class DropoutFn(torch.autograd.Function):
-    """nn.Dropout(p) in training mode; the mask is a pure function of (seed, call index, element index)."""
+    """nn.Dropout(p) in training mode; the mask is a pure function of (seed, call index within the step, optimizer step,
+    element index).  The call index restarts with every optimizer step (``begin_step``), the step count is read ON THE DEVICE
+    when the fused optimizer keeps it there, so a training step replayed from a CUDA graph draws a fresh mask every step."""
 
     @staticmethod
     def forward(ctx, x, p, seed):
@@ -815,15 +887,17 @@ class DropoutFn(torch.autograd.Function):
         _dropout_calls += 1
         x = x.contiguous()
         y = torch.empty_like(x)
-        ctx.p, ctx.seed, ctx.offset = float(p), int(seed), _dropout_calls
-        L.check(L.lib().rho_dropout(x.data_ptr(), y.data_ptr(), dt(x), x.numel(), ctx.p, ctx.seed, ctx.offset, stream()), "dropout")
+        ctx.p, ctx.seed, ctx.offset, ctx.step_dev = float(p), int(seed), _dropout_calls, dropout_step_dev
+        L.check(L.lib().rho_dropout(x.data_ptr(), y.data_ptr(), dt(x), x.numel(), ctx.p, ctx.seed, ctx.offset, ptr(ctx.step_dev), stream()),
+                "dropout")
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        L.check(L.lib().rho_dropout(dy.data_ptr(), dx.data_ptr(), dt(dy), dy.numel(), ctx.p, ctx.seed, ctx.offset, stream()), "dropout_bwd")
+        L.check(L.lib().rho_dropout(dy.data_ptr(), dx.data_ptr(), dt(dy), dy.numel(), ctx.p, ctx.seed, ctx.offset, ptr(ctx.step_dev), stream()),
+                "dropout_bwd")
         return dx, None, None
 
 

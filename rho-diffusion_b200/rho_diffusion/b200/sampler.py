@@ -29,22 +29,24 @@ class AncestralSampler:
         self.T = int(alpha_bar.numel())
         self.noise_scale, self.clamp = noise_scale, clamp
         self.use_graph = bool(use_cuda_graph)
-        self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
-        self.tt = torch.zeros((self.shape[0],), dtype=torch.int64, device=device)
-        self.t_scalar = torch.zeros((1,), dtype=torch.int64, device=device)
-        self.cond = cond_example.clone() if cond_example is not None else None
-        self.z = torch.zeros(self.shape, dtype=torch.float32, device=device) if external_noise else None
-        self.seed_holder = 0
+        with torch.inference_mode(False):      # state buffers outlive the (inference-mode) call that builds the sampler
+            self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
+            self.tt = torch.zeros((self.shape[0],), dtype=torch.int64, device=device)
+            self.t_scalar = torch.zeros((1,), dtype=torch.int64, device=device)
+            self.cond = torch.empty_like(cond_example).copy_(cond_example) if cond_example is not None else None
+            self.z = torch.zeros(self.shape, dtype=torch.float32, device=device) if external_noise else None
+            self.seed_dev = torch.zeros((1,), dtype=torch.int64, device=device)   # Philox key of the run, read by the step kernel
         self.graph = None
-        self._graph_seed = None
+        self._graph_sig = None
 
-    def _step(self, seed):
+    def _step(self, seed=0):
         eps = self.backbone(self.x, self.tt, self.cond) if self.cond is not None else self.backbone(self.x, self.tt)
         ops.p_sample_step(self.x, eps, self.z, self.t_scalar, self.alpha, self.beta, self.alpha_bar, self.noise_scale, self.clamp,
-                          seed)
+                          seed, seed_dev=self.seed_dev)
         ops.advance_timestep(self.t_scalar, self.tt)
 
-    def _capture(self, seed):
+    def _capture(self, seed=0):
+        self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
         # warm-up on a side stream (packs weights, sets kernel attributes, sizes the workspace), then capture
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
@@ -58,12 +60,15 @@ class AncestralSampler:
         self.tt.fill_(1)
         with torch.cuda.graph(g):
             self._step(seed)
-        self.graph, self._graph_seed = g, seed
+        # the eager warm-up above packed the conv weights; the graph reads those snapshots, so it is only valid for this
+        # state of the parameters (optimizer steps, load_state_dict and EMA swaps change the signature -> re-capture)
+        self.graph, self._graph_sig = g, ops.weights_signature(self.backbone)
 
     def run(self, x_init, cond=None, seed=0, noises=None, t_checkpoints=None, num_steps=None, progress=False):
         T = self.T if num_steps is None else int(num_steps)
-        if self.use_graph and (self.graph is None or (self.z is None and self._graph_seed != seed)):
+        if self.use_graph and (self.graph is None or self._graph_sig != ops.weights_signature(self.backbone)):
             self._capture(seed)
+        self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
         self.x.copy_(x_init.reshape(self.shape).to(torch.float32))
         if self.cond is not None:
             self.cond.copy_(cond)
@@ -112,6 +117,7 @@ class X0Sampler:
         self.thresh = torch.ones((self.shape[0],), dtype=torch.float32, device=device)
         self.cond = cond_example.clone() if cond_example is not None else None
         self.graph = None
+        self._graph_sig = None
 
     def _step(self):
         out = self.backbone(self.x, self.tt, self.cond) if self.cond is not None else self.backbone(self.x, self.tt)
@@ -133,12 +139,12 @@ class X0Sampler:
         self.tt.fill_(1)
         with torch.cuda.graph(g):
             self._step()
-        self.graph = g
+        self.graph, self._graph_sig = g, ops.weights_signature(self.backbone)
 
     def run(self, x_init, cond=None, t_checkpoints=None, num_steps=None):
         T = self.T if num_steps is None else int(num_steps)
-        if self.use_graph and self.graph is None:
-            self._capture()
+        if self.use_graph and (self.graph is None or self._graph_sig != ops.weights_signature(self.backbone)):
+            self._capture()      # stale packed-weight snapshots after training / load_state_dict / EMA swap
         self.x.copy_(x_init.reshape(self.shape).to(torch.float32))
         if self.cond is not None:
             self.cond.copy_(cond)

@@ -44,7 +44,7 @@ class AbstractDiffusionPipeline(nn.Module):
         self.metrics = nn.ModuleDict()   # the reference's PSNR metric is only logged; see DDPM(log_psnr=...)
         self.hparams = types.SimpleNamespace(model_kwargs=backbone_kwargs, opt_kwargs=dict(opt_kwargs or {}))
         self.timesteps = timesteps
-        self.global_rank = 0
+        self._global_rank = None          # None: follow torch.distributed (see the property below)
         self.current_epoch = 0
         self._python_logger = getLogger(self.__class__.__name__)
 
@@ -55,6 +55,22 @@ class AbstractDiffusionPipeline(nn.Module):
     @property
     def device(self):
         return next(self.parameters()).device
+
+    @property
+    def global_rank(self) -> int:
+        """Lightning's ``global_rank``.  Without a Trainer it follows the process group (0 when none is initialised), so that
+        every rank of a torchrun job keys its Philox noise differently (``noise``: seed + 7919 * rank) and the ranks of a
+        batch-sharded ``generate`` do not produce duplicate samples; assigning to it pins a value."""
+        if self._global_rank is not None:
+            return self._global_rank
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank()
+        return 0
+
+    @global_rank.setter
+    def global_rank(self, value) -> None:
+        self._global_rank = None if value is None else int(value)
 
     # -- optimizer ---------------------------------------------------------------------------------------
     def configure_optimizers(self, mpi_world_size: int = 1) -> dict:
@@ -86,8 +102,17 @@ class AbstractDiffusionPipeline(nn.Module):
         self._schedule = value
 
     def random_timesteps(self, num_steps: int) -> Tensor:
-        """``randint(0, T)`` drawn from the **CPU** generator, like abstract_diffusion.py:163-169."""
+        """``randint(0, T)`` drawn from the **CPU** generator, like abstract_diffusion.py:163-169.  Under torchrun the
+        training script reseeds that generator with ``seed + rank`` AFTER the model is built (identical weight init, different
+        timesteps per rank): ``reseed_per_rank``."""
         return torch.randint(low=0, high=self.timesteps, size=(num_steps,))
+
+    def reseed_per_rank(self, seed: int) -> int:
+        """Call once after construction in a multi-process job: the CPU generator behind ``random_timesteps`` (and the
+        data-loader shuffles) continues from ``seed + rank``.  Returns the rank used."""
+        rank = self.global_rank
+        torch.manual_seed(int(seed) + rank)
+        return rank
 
     def reshape_timesteps(self, data: Tensor, t: Tensor) -> Tensor:
         return t.view((-1, *((1,) * (data.ndim - 1))))

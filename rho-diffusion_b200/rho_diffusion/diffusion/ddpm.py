@@ -180,8 +180,13 @@ class DDPM(AbstractDiffusionPipeline):
             shape = [self.sampling_batch_size, self.backbone_kwargs["out_channels"]] + data_shape
             self.data_dtype = torch.float32
         device = self.device
-        cond = sample_from_discrete_parameter_space(parameter_space, shape[0], random=random, device=device) \
-            if parameter_space is not None else None
+        if isinstance(parameter_space, Tensor):
+            # extension: explicit condition rows (e.g. same-shape label embeddings, one per sample) instead of a discrete space
+            assert parameter_space.shape[0] >= shape[0], "generate(): fewer condition rows than sampling_batch_size"
+            cond = parameter_space[: shape[0]].to(device)
+        else:
+            cond = sample_from_discrete_parameter_space(parameter_space, shape[0], random=random, device=device) \
+                if parameter_space is not None else None
         if shard and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             from rho_diffusion.b200.sampler import shard_range
             lo, hi = shard_range(shape[0], dist.get_world_size(), dist.get_rank())

@@ -1,6 +1,8 @@
 """Parameter-space conditioning (reference ``rho_diffusion/models/conditioning.py:31-139``)."""
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import Union
 
@@ -40,6 +42,7 @@ class MultiEmbeddings(nn.Module):
             for key, n in sizes.items():
                 self.embedding_layers[key] = nn.Embedding(num_embeddings=n, embedding_dim=embedding_dim)
         self._value_tables = {}
+        self._labels_checked = False
 
     def _values(self, device):
         tabs = self._value_tables.get(device)
@@ -56,4 +59,17 @@ class MultiEmbeddings(nn.Module):
         from rho_diffusion.b200 import ops
 
         tables = [layer.weight for layer in self.embedding_layers.values()]
-        return ops.EmbeddingMatchFn.apply(y, self._values(y.device), *tables)
+        out = ops.EmbeddingMatchFn.apply(y, self._values(y.device), *tables)
+        # A label outside the parameter space makes the reference fail (conditioning.py:132-137).  The kernel poisons such rows
+        # with NaN; the first eager call (and every call under RHO_STRICT_LABELS=1) also checks the matched indices on the host
+        # and raises -- one device sync, skipped while a CUDA graph is being captured.
+        strict = os.environ.get("RHO_STRICT_LABELS", "") == "1"
+        if (strict or not self._labels_checked) and not torch.cuda.is_current_stream_capturing():
+            self._labels_checked = True
+            idxs = ops.EmbeddingMatchFn.last_indices
+            if idxs is not None and bool((idxs < 0).any()):
+                bad = (idxs < 0).nonzero()[0].tolist()
+                key = list(self.embedding_layers.keys())[bad[0]]
+                raise ValueError(f"MultiEmbeddings: label value of sample {bad[1]} for key {key!r} is not a point of the parameter space "
+                                 f"{list(self.parameter_space[key])}")
+        return out

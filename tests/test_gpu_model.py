@@ -305,18 +305,17 @@ def test_graphed_train_step_matches_eager():
             return float(loss.detach())
 
         if graphed:
-            step = GraphedTrainStep(ddpm, fused, xd, yd, warmup=2)        # two warm-up steps on one internally drawn (t, noise)
-        else:
-            t_w, noise_w = ddpm.random_timesteps(x0.shape[0]), ddpm.noise(xd)   # the same draws, taken eagerly
-            for _ in range(2):
-                eager_step(t_w, noise_w)
+            before = fused.flat_p.clone()
+            step = GraphedTrainStep(ddpm, fused, xd, yd, warmup=2)        # the warm-up steps are undone: weights, moments, EMA, counters
+            assert torch.equal(before, fused.flat_p) and fused.steps_taken == 0 and float(fused.flat_m.abs().max()) == 0.0
+            assert torch.equal(fused.flat_shadow, fused.flat_p)
         for t, noise in draws:
             losses.append(float(step(xd, yd, t=t.to(DEV), noise=noise.to(DEV))) if graphed else eager_step(t, noise.to(DEV)))
         return losses, fused
 
     eager, fe = run(False)
     graph, fg = run(True)
-    assert fg.steps_taken == 8 and fe.steps_taken == 8
+    assert fg.steps_taken == 6 and fe.steps_taken == 6
     graph2, _ = run(True)
     assert graph == graph2                                   # replay is bit-reproducible
     print("eager ", eager)
@@ -325,3 +324,83 @@ def test_graphed_train_step_matches_eager():
         assert a == pytest.approx(b, rel=1e-5)
     assert torch.allclose(fe.flat_p, fg.flat_p, rtol=0, atol=1e-6)
     assert torch.allclose(fe.flat_shadow, fg.flat_shadow, rtol=0, atol=1e-6)
+
+
+def test_sampler_graph_is_recaptured_when_the_weights_change():
+    """ The captured sampling graph reads packed-weight snapshots: after load_state_dict / training / an EMA swap a
+    later reverse_process must not replay stale conv weights next to live Linear / GroupNorm parameters."""
+    from oracle.synth import synth_state_dict
+    ddpm, g, x0, y = make_ddpm()
+    ddpm.eval()
+    gen = torch.Generator().manual_seed(3)
+    x_init = torch.randn(x0.shape, generator=gen).to(DEV)
+    noises = {t: torch.randn(x0.shape, generator=gen) for t in range(g["T"])}
+    run = lambda graph: ddpm.reverse_process(torch.zeros(x0.shape, device=DEV), conditions=y.to(DEV), x_init=x_init, noises=noises,  # noqa: E731
+                                            num_steps=6, use_cuda_graph=graph)["denoised"].clone()
+    a_graph = run(True)
+    manifest = {k: tuple(v.shape) for k, v in ddpm.backbone.state_dict().items()}
+    ddpm.backbone.load_state_dict(synth_state_dict(manifest, seed=4242))          # new weights, same module objects
+    b_graph = run(True)                                                            # same cached sampler -> must re-capture
+    ddpm._samplers = {}
+    b_eager = run(False)
+    assert (a_graph - b_graph).abs().max() > 1e-3
+    assert torch.allclose(b_graph, b_eager, rtol=0, atol=2e-5)
+
+
+def test_sampler_graph_serves_every_seed():
+    """ The Philox key of the run lives in device memory: one captured graph is replayed for every reverse_process call
+    (no re-capture per call), different calls draw different noise, the same seed reproduces the trajectory."""
+    ddpm, g, x0, y = make_ddpm()
+    ddpm.eval()
+    shape = x0.shape
+    r1 = ddpm.reverse_process(torch.zeros(shape, device=DEV), conditions=y.to(DEV), num_steps=5)["denoised"].clone()
+    sampler = next(iter(ddpm._samplers.values()))
+    graph = sampler.graph
+    r2 = ddpm.reverse_process(torch.zeros(shape, device=DEV), conditions=y.to(DEV), num_steps=5)["denoised"].clone()
+    assert next(iter(ddpm._samplers.values())).graph is graph                     # not re-captured
+    assert (r1 - r2).abs().max() > 1e-3
+    x_init = torch.randn(shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    s1 = sampler.run(x_init, y.to(DEV), seed=99, num_steps=5)["denoised"].clone()
+    s2 = sampler.run(x_init, y.to(DEV), seed=99, num_steps=5)["denoised"].clone()
+    s3 = sampler.run(x_init, y.to(DEV), seed=100, num_steps=5)["denoised"].clone()
+    assert torch.equal(s1, s2) and (s1 - s3).abs().max() > 1e-3
+
+
+def test_dropout_mask_follows_the_device_step_counter():
+    """ Under graph replay the host-side call counter is frozen; the mask must still change every optimizer step: the
+    device step counter is folded into the Philox offset (same counter value -> same mask, forward and backward agree)."""
+    from rho_diffusion.b200 import ops
+    x = torch.ones(1 << 14, device=DEV)
+    step = torch.zeros(16, dtype=torch.int32, device=DEV)
+    old = ops.dropout_step_dev
+    try:
+        ops.dropout_step_dev = step
+        g = torch.cuda.CUDAGraph()
+        xin = x.clone().requires_grad_(True)
+        ops.dropout(xin, 0.5, seed=7)                           # warm-up outside the capture
+        with torch.cuda.graph(g):
+            y = ops.dropout(xin, 0.5, seed=7)
+            (gx,) = torch.autograd.grad(y, xin, torch.ones_like(y))
+        g.replay(); y0, g0 = y.clone(), gx.clone()
+        step[0] = 1
+        g.replay(); y1 = y.clone()
+        step[0] = 0
+        g.replay(); y2 = y.clone()
+        assert torch.equal(y0, y2) and not torch.equal(y0, y1)
+        assert torch.equal(g0, y0)                              # backward of ones through the same mask
+        assert 0.4 < float((y1 == 0).float().mean()) < 0.6
+    finally:
+        ops.dropout_step_dev = old
+
+
+def test_unmatched_label_raises_like_the_reference():
+    from collections import OrderedDict
+    from rho_diffusion.models.conditioning import MultiEmbeddings
+    me = MultiEmbeddings(parameter_space=OrderedDict([("a", [0.25, 0.5]), ("b", [1, 2, 3])]), embedding_dim=16).to(DEV)
+    ok = me(torch.tensor([[0.5, 3.0], [0.25, 1.0]], device=DEV))
+    assert torch.isfinite(ok).all()
+    me2 = MultiEmbeddings(parameter_space=OrderedDict([("a", [0.25, 0.5]), ("b", [1, 2, 3])]), embedding_dim=16).to(DEV)
+    with pytest.raises(ValueError, match="not a point of the parameter space"):
+        me2(torch.tensor([[0.5, 3.0], [0.25, 7.0]], device=DEV))
+    out = me2(torch.tensor([[0.5, 3.0], [0.25, 7.0]], device=DEV))      # later calls do not sync: the bad row is NaN-poisoned
+    assert torch.isfinite(out[0]).all() and torch.isnan(out[1]).all()

@@ -7,6 +7,7 @@ all-reduce + identical fused AdamW), those weights equal a single-process run on
 import os
 import socket
 import sys
+import time
 
 import pytest
 import torch
@@ -82,7 +83,25 @@ def _worker(rank, world, port, out):
     noises = {t: torch.randn((4, *spec["x_shape"][1:]), generator=g) for t in range(50)}
     res = ddpm.reverse_process(torch.zeros((hi - lo, *spec["x_shape"][1:]), device=device), conditions=y[lo:hi].to(device),
                                x_init=x_init[lo:hi].to(device), noises={t: z[lo:hi] for t, z in noises.items()}, num_steps=8)
-    out[rank] = (flat, res["denoised"].cpu(), lo, hi)
+    #  nothing injected: the ranks must NOT draw the same Philox noise / x_T -- global_rank follows the process group
+    ddpm.train()
+    assert ddpm.global_rank == r
+    own_noise = ddpm.noise(torch.zeros(2, 8, device=device)).cpu()
+    own_sample = ddpm.reverse_process(torch.zeros((1, *spec["x_shape"][1:]), device=device), conditions=y[:1].to(device), num_steps=3)["denoised"].cpu()
+    # the whole data-parallel step (bucketed all-reduces included) replayed from ONE CUDA graph: identical to the eager loop
+    from rho_diffusion.b200 import GraphedTrainStep
+    ddpm2, _ = _build(device)
+    opt2 = ddpm2.configure_optimizers(1)["optimizer"]
+    ddpm2, fused2 = optimize(ddpm2, optimizer=opt2, dtype=torch.float32)
+    ddpm2.train()
+    xs, ys = x[lo:hi].to(device), y[lo:hi].to(device)
+    graphed = GraphedTrainStep(ddpm2, fused2, xs, ys)
+    for t, noise in steps:
+        graphed(xs, ys, t=t[lo:hi].to(device), noise=noise[lo:hi].to(device))
+    torch.cuda.synchronize()
+    flat_graph = fused2.flat_p.detach().cpu().clone()
+    graphed.close()
+    out[rank] = (flat, res["denoised"].cpu(), lo, hi, flat_graph, own_noise, own_sample)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -93,10 +112,19 @@ def test_two_gpu_data_parallel_training_and_sharded_sampling():
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-    flat0, den0, lo0, hi0 = out[0]
-    flat1, den1, lo1, hi1 = out[1]
+    ctx = mp.spawn(_worker, args=(world, port, out), nprocs=world, join=False)
+    deadline = time.time() + 300            # a collective that never completes must fail the test, not hang the box
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for proc in ctx.processes:
+                proc.kill()
+            pytest.fail("two-GPU workers did not finish within 300 s")
+    flat0, den0, lo0, hi0, fg0, noise0, samp0 = out[0]
+    flat1, den1, lo1, hi1, fg1, noise1, samp1 = out[1]
     assert torch.equal(flat0, flat1)                                  # replicas stay bit-identical
+    assert torch.equal(fg0, fg1)                                      # ... also when the step is replayed from a CUDA graph
+    assert torch.equal(fg0, flat0)                                    # graph replay == eager loop (same kernels, same collectives)
+    assert not torch.equal(noise0, noise1) and (samp0 - samp1).abs().max() > 1e-3      # per-rank Philox keys
     # single process, whole batch, same (t, noise): the data-parallel result to fp32 rounding
     for p in (ROOT, PKG):
         if p not in sys.path:

@@ -32,6 +32,21 @@ def _worker(rank, world, port, out):
     dist.all_reduce(flat_g, op=dist.ReduceOp.SUM)
     flat_g *= 1.0 / w
     lo, hi = shard_range(101, w, r)
+    # bucketed, asynchronously launched all-reduces over slices of one flat buffer (what FusedAdamW does from inside the backward,
+    # last bucket first) give exactly the whole-buffer all-reduce
+    from rho_diffusion.b200 import partition_buckets
+    g0 = torch.Generator().manual_seed(100 + rank)
+    sizes = [7, 64, 1, 300, 50, 128, 9, 441]
+    offsets = [sum(sizes[:i]) for i in range(len(sizes))]
+    total = sum(sizes)
+    whole = torch.randn(total, generator=g0)
+    bucketed = whole.clone()
+    dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+    ranges, _ = partition_buckets(offsets, total, 3)
+    works = [dist.all_reduce(bucketed[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in reversed(ranges)]
+    for wk in works:
+        wk.wait()
+    assert torch.equal(whole, bucketed)
     out[rank] = (float(flat_g[0]), float(flat_g[-1]), lo, hi)
     dist.barrier()
     dist.destroy_process_group()
@@ -54,3 +69,20 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_partition_buckets_covers_the_flat_buffer_at_parameter_boundaries():
+    from rho_diffusion.b200 import partition_buckets
+    import random
+    rng = random.Random(5)
+    for n_params in (1, 2, 5, 40, 329):
+        for n_b in (1, 3, 8, 64):
+            sizes = [64 * rng.randint(1, 500) for _ in range(n_params)]
+            offsets = [sum(sizes[:i]) for i in range(n_params)]
+            total = sum(sizes)
+            ranges, bucket_of = partition_buckets(offsets, total, n_b)
+            assert ranges[0][0] == 0 and ranges[-1][1] == total and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            assert len(ranges) <= min(n_b, n_params) and len(bucket_of) == n_params and bucket_of == sorted(bucket_of)
+            assert set(bucket_of) == set(range(len(ranges)))
+            for off, b in zip(offsets, bucket_of):
+                assert ranges[b][0] <= off < ranges[b][1]          # cut at parameter boundaries: a parameter lives in ONE bucket
