@@ -368,6 +368,21 @@ int rho_resample(const void* src, void* dst, int dtype, int32_t N, int32_t D, in
 int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, const int32_t* step_dev,
                 rho_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * synthetic density-field generators on the device (keeps the input pipeline off the host):
+ *   rho_sph_harm_density  out[n, i, j, k] (fp32, [N, G, G, G]) = the normalised density of compute_spherical_harmonic
+ *                         (rho_diffusion/data/synthetic.py:84-124) for (l[n], m[n]) on the grid linspace(lo, hi, G)^3 with the
+ *                         reference's meshgrid(indexing="xy") / swapped-angle / complex min-max conventions; double precision
+ *                         inside.  workspace: rho_sph_harm_workspace_bytes(N, G).
+ *   rho_gaussian_blobs    out[n] (fp32, [N, D, H, W], D = 1 / H = 1 for lower n) = 2 min(sum_k exp(-|x - c_k|^2 / 2 w_n^2), 1) - 1
+ *                         with n_blobs[n] (<= 8) centres from Philox4x32-10(counter = (first_index + n, k), key = seed), each
+ *                         coordinate 0.2 + 0.6 u, x at cell centres of the unit box (the last axis is coordinate 0). */
+size_t rho_sph_harm_workspace_bytes(int32_t N, int32_t G);
+int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi, void* workspace,
+                         size_t workspace_bytes, rho_stream_t stream);
+int rho_gaussian_blobs(float* out, int32_t N, int32_t D, int32_t H, int32_t W, const int32_t* n_blobs, const float* width, uint64_t seed,
+                       uint64_t first_index, rho_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

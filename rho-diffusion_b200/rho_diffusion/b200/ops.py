@@ -903,3 +903,30 @@ class DropoutFn(torch.autograd.Function):
 
 def dropout(x, p: float, seed: int = 0):
     return DropoutFn.apply(x, p, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic density fields generated on the device (rho_diffusion/data/synthetic.py)
+# ------------------------------------------------------------------------------------------------
+def sph_harm_density(l: torch.Tensor, m: torch.Tensor, grid_el: int, lo: float = -2.0, hi: float = 2.0) -> torch.Tensor:
+    """(B,) int32 device tensors of degrees / orders -> (B, 1, G, G, G) fp32 normalised |Y_l^|m| r| volumes (synthetic.py:84-124)."""
+    _need_cuda(l, m)
+    l, m = l.to(torch.int32).contiguous(), m.to(torch.int32).contiguous()
+    B = l.numel()
+    out = torch.empty((B, 1, grid_el, grid_el, grid_el), dtype=torch.float32, device=l.device)
+    ws = workspace(L.lib().rho_sph_harm_workspace_bytes(B, grid_el), l.device)
+    L.check(L.lib().rho_sph_harm_density(out.data_ptr(), B, grid_el, l.data_ptr(), m.data_ptr(), float(lo), float(hi), ws.data_ptr(),
+                                         ws.numel(), stream()), "sph_harm_density")
+    return out
+
+
+def gaussian_blobs(n_blobs: torch.Tensor, width: torch.Tensor, data_shape, seed: int, first_index: int) -> torch.Tensor:
+    """(B,) int32 blob counts and (B,) fp32 widths -> (B, 1, *data_shape) fp32 fields in [-1, 1] (see rho_gaussian_blobs)."""
+    _need_cuda(n_blobs, width)
+    n_blobs, width = n_blobs.to(torch.int32).contiguous(), width.to(torch.float32).contiguous()
+    B = n_blobs.numel()
+    D, H, W = _pad3(data_shape)
+    out = torch.empty((B, 1, *[int(s) for s in data_shape]), dtype=torch.float32, device=n_blobs.device)
+    L.check(L.lib().rho_gaussian_blobs(out.data_ptr(), B, D, H, W, n_blobs.data_ptr(), width.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                       int(first_index), stream()), "gaussian_blobs")
+    return out

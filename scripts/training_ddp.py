@@ -47,6 +47,7 @@ def main():
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--num-workers", type=int, default=8)
     parser.add_argument("--save", default="model.pth", help="checkpoint file written by rank 0 at the end")
+    parser.add_argument("--host-data", action="store_true", help="always go through a host DataLoader, even for datasets that can generate on the device")
     parser.add_argument("--sample-during-training", action="store_true",
                         help="run generate() every training.sample_every_n_epochs epochs (ddpm.py:301-310; commented out in the reference script)")
     parser.add_argument("--cuda-graph", action="store_true",
@@ -66,7 +67,10 @@ def main():
     dset_class = registry.get("datasets", config.dataset.name)
     dset = dset_class(**config.dataset.kwargs)
     sampler = None
-    if world > 1:
+    if hasattr(dset, "device_loader") and device.type == "cuda" and not args.host_data:
+        # synthetic datasets generate their batches ON THE DEVICE (one kernel launch per batch): no worker processes, no H2D copies
+        loader = sampler = dset.device_loader(config.training.batch_size, device, rank=rank, world=world)
+    elif world > 1:
         sampler = torch.utils.data.distributed.DistributedSampler(dataset=dset, num_replicas=world, rank=rank, seed=config.training.seed)
         loader = DataLoader(dset, batch_size=config.training.batch_size, sampler=sampler, num_workers=args.num_workers, pin_memory=True,
                             drop_last=args.cuda_graph)

@@ -115,11 +115,15 @@ def test_config_d_sampling_steps_stay_bounded_and_deterministic(config_d_oracle)
     assert torch.isfinite(outs[0]).all() and outs[0].min() >= -1 and outs[0].max() <= 1
 
 
-def test_config_a_shipped_config_eval_matches_oracle():
-    """examples/config_spherical_harmonics.json (model kwargs restated; the reference JSON is not read at test time)."""
+@pytest.mark.parametrize("new_order", [True, False])
+def test_config_a_shipped_config_eval_matches_oracle(new_order):
+    """examples/config_spherical_harmonics.json (model kwargs restated; the reference JSON is not read at test time).  The JSON says
+    ``"use_new_attention_order": false``; under the reference's pinned pydantic v1 the bool is coerced to the truthy string "False", so
+    the shipped config actually selects the NEW order (QKVAttention) -- the quirk ``rho_diffusion.config`` reproduces
+    (test_config_schema_and_pydantic_v1_bool_quirk).  Both orders are checked at full size."""
     kwargs = dict(dims=3, in_channels=1, out_channels=1, model_channels=64, num_res_blocks=2, data_shape=[32, 32, 32],
                   attention_resolutions=[16, 8], use_scale_shift_norm=True, num_heads=4, num_classes=20, activation="SiLU",
-                  use_new_attention_order=False)
+                  use_new_attention_order=new_order)
     model, sd = build_unet(kwargs, torch.bfloat16)
     x = synth_input("cfgA.x", (2, 1, 32, 32, 32))
     y = synth_input("cfgA.y", (2, 256), kind="rand")

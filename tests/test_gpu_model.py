@@ -201,6 +201,12 @@ def test_reverse_process_shared_noise_matches_reference(graph):
     err = float((den - rv["denoised"]).abs().max())
     print("trajectory max abs err", err, "graph" if graph else "eager")
     assert err < 1e-3   # 50 chained fp32 evals + clamps
+    # final density-field moments (north star): mean / variance / third central moment per sample against the reference's trajectory
+    ref = rv["denoised"]
+    for k in range(den.shape[0]):
+        a, b = den[k].double().flatten(), ref[k].double().flatten()
+        for mom_a, mom_b in ((a.mean(), b.mean()), (a.var(), b.var()), (((a - a.mean()) ** 3).mean(), ((b - b.mean()) ** 3).mean())):
+            assert abs(float(mom_a) - float(mom_b)) < 1e-4
     assert res["buffer"].shape[1] == 3
     assert den.min() >= -1 and den.max() <= 1
 

@@ -56,3 +56,23 @@ def test_inference_script_on_the_deep_galaxy_config(tmp_path):
     x = torch.load(gen)
     assert x.shape == (4, 1, 128, 128) and torch.isfinite(x).all(), out[-1500:]
     assert float(x.abs().max()) <= 1.0 + 1e-6           # dynamic thresholding keeps samples in [-1, 1]
+
+
+def test_training_script_builds_cond_fn_and_saves_the_ema_checkpoint(tmp_path):
+    """examples/config_gaussian_blobs.json: `model.kwargs.cond_fn = "MultiEmbeddings"` (the mechanism of the DeepGalaxy config) over the
+    dataset class's parameter space, batches generated on the device, EMA on: the script trains, writes model.pth and model_ema.pth in the
+    reference layout (embedding tables included), and the inference script samples from the result."""
+    cfg = os.path.join(ROOT, "examples", "config_gaussian_blobs.json")
+    ckpt = str(tmp_path / "blobs.pth")
+    out = run(["scripts/training_ddp.py", cfg, "-d", "cuda", "-e", "1", "--max-steps", "6", "--save", ckpt])
+    losses = [float(line.split("loss: ")[1].split(",")[0]) for line in out.splitlines() if "loss: " in line]
+    assert losses and all(0.0 < v < 5.0 for v in losses), out[-1500:]
+    sd, ema = torch.load(ckpt), torch.load(str(tmp_path / "blobs_ema.pth"))
+    assert sd.keys() == ema.keys() and "cond_fn.embedding_layers.n.weight" in sd and sd["cond_fn.embedding_layers.w.weight"].shape == (3, 128)
+    assert any(not torch.equal(sd[k], ema[k]) for k in sd)          # the shadow lags the weights
+    gen = str(tmp_path / "gen.pt")
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "5", "--steps", "5", "--out", gen])
+    x = torch.load(gen)
+    assert x.shape == (5, 1, 64, 64) and torch.isfinite(x).all(), out[-1500:]
+    # the same script on the host data path (DataLoader workers, pinned copies)
+    run(["scripts/training_ddp.py", cfg, "-d", "cuda", "-e", "1", "--max-steps", "2", "--num-workers", "2", "--host-data", "--save", ""])
