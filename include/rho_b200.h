@@ -373,12 +373,15 @@ int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t 
  *   rho_sph_harm_density  out[n, i, j, k] (fp32, [N, G, G, G]) = the normalised density of compute_spherical_harmonic
  *                         (rho_diffusion/data/synthetic.py:84-124) for (l[n], m[n]) on the grid linspace(lo, hi, G)^3 with the
  *                         reference's meshgrid(indexing="xy") / swapped-angle / complex min-max conventions; double precision
- *                         inside.  workspace: rho_sph_harm_workspace_bytes(N, G).
+ *                         inside.  The lexicographic complex extremes are decided by rounding noise at symmetric grid points, so
+ *                         callers pass the host restatement's extremes per sample (`minmax`); NULL = the kernel's own.
+ *                         workspace: rho_sph_harm_workspace_bytes(N, G).
  *   rho_gaussian_blobs    out[n] (fp32, [N, D, H, W], D = 1 / H = 1 for lower n) = 2 min(sum_k exp(-|x - c_k|^2 / 2 w_n^2), 1) - 1
  *                         with n_blobs[n] (<= 8) centres from Philox4x32-10(counter = (first_index + n, k), key = seed), each
  *                         coordinate 0.2 + 0.6 u, x at cell centres of the unit box (the last axis is coordinate 0). */
 size_t rho_sph_harm_workspace_bytes(int32_t N, int32_t G);
-int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi, void* workspace,
+int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi,
+                         const double* minmax /* optional [N][4]: re, im of the complex min and max to normalise with */, void* workspace,
                          size_t workspace_bytes, rho_stream_t stream);
 int rho_gaussian_blobs(float* out, int32_t N, int32_t D, int32_t H, int32_t W, const int32_t* n_blobs, const float* width, uint64_t seed,
                        uint64_t first_index, rho_stream_t stream);

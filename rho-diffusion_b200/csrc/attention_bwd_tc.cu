@@ -521,20 +521,34 @@ static int launch_attn_bwd_tc(const rho_attn_bwd_params* p, const AttnBwdTcParam
   return RHO_OK;
 }
 
+// attention_bwd_tc2.cu: 64-column tiles, P / dS in tensor memory, two row-owner groups on alternate tiles (head dim 64)
+bool attention_bwd_tc2_supported(const rho_attn_bwd_params* p);
+size_t attention_bwd_tc2_workspace(const rho_attn_bwd_params* p);
+int attention_bwd_tc2(const rho_attn_bwd_params* p, cudaStream_t st);
+
 size_t attention_bwd_tc_workspace(const rho_attn_bwd_params* p) {
+  if (attention_bwd_tc2_supported(p)) return attention_bwd_tc2_workspace(p);
   const rho_attn_params& f = p->fwd;
   return (size_t)f.N * f.heads * ((f.T + 31) / 32) * 64 * sizeof(float);
 }
 
+// per-row statistics for `tiles` 32-row tiles per (sample, head) (rows >= T are zero)
+int attn_bwd_stats(const rho_attn_bwd_params* p, float* ld, int tiles, cudaStream_t st) {
+  const rho_attn_params& f = p->fwd;
+  const long long total = (long long)f.N * f.heads * tiles * 32;
+  attn_bwd_stats_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const bf16*)f.out, (const bf16*)p->dout, f.lse, ld, f.T, f.heads, f.ch,
+                                                                       tiles, total);
+  RHO_CHECK_LAUNCH("attention_bwd_stats");
+  return RHO_OK;
+}
+
 int attention_bwd_tc(const rho_attn_bwd_params* p, cudaStream_t st) {
+  if (attention_bwd_tc2_supported(p)) return attention_bwd_tc2(p, st);
   const rho_attn_params& f = p->fwd;
   float* ld = (float*)p->workspace;
   {
-    const int tiles = (f.T + 31) / 32;
-    const long long total = (long long)f.N * f.heads * tiles * 32;
-    attn_bwd_stats_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const bf16*)f.out, (const bf16*)p->dout, f.lse, ld, f.T, f.heads,
-                                                                         f.ch, tiles, total);
-    RHO_CHECK_LAUNCH("attention_bwd_stats");
+    int rc = attn_bwd_stats(p, ld, (f.T + 31) / 32, st);
+    if (rc) return rc;
   }
   AttnBwdTcParams ap;
   ap.T = f.T; ap.heads = f.heads; ap.C = f.heads * f.ch;

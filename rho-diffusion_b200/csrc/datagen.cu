@@ -7,7 +7,12 @@
 //                         theta = atan(sqrt(x^2 + y^2) / z) is passed to scipy's sph_harm as the AZIMUTH and
 //                         phi = atan(y / x) as the POLAR angle; solution = Y_l^|m|(polar, azimuth) * r is min-max normalised
 //                         as a COMPLEX array (numpy's min / max order complex numbers lexicographically) and the density is
-//                         |solution|.  Double precision throughout, like numpy; output fp32.
+//                         |solution|.  Double precision throughout, like numpy; output fp32.  The lexicographic extremes are
+//                         ILL-CONDITIONED: symmetric grid points have real parts that agree to the last bits, so which of them
+//                         (with opposite imaginary parts) wins depends on rounding noise of the special-function library.  The
+//                         caller therefore normally passes the extremes of the host restatement (`minmax`, cached per (l, |m|)),
+//                         which makes the device field equal the reference's to ~1e-15; with `minmax = NULL` the kernel uses its
+//                         own lexicographic extremes (equal to the reference's only where no such near-tie exists).
 //   rho_gaussian_blobs    n-D (n = 1, 2, 3) Gaussian-blob density fields: rho(x) = sum_k exp(-|x - c_k|^2 / (2 w^2)) with K
 //                         centres c_k uniform in [0.2, 0.8]^n drawn from Philox4x32-10 (key = seed, counter = (sample index, k)),
 //                         x in [0, 1]^n at cell centres; output = 2 min(rho, 1) - 1 in [-1, 1].  Labels are (K, w).
@@ -129,10 +134,13 @@ __global__ void __launch_bounds__(256) sph_harm_solution_kernel(Cplx* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) sph_harm_normalize_kernel(const Cplx* __restrict__ sol, const Cplx* __restrict__ partial, int G, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) sph_harm_normalize_kernel(const Cplx* __restrict__ sol, const Cplx* __restrict__ partial, int G, float* __restrict__ out,
+                                                                 const double* __restrict__ minmax) {
   const int n = blockIdx.y;
   __shared__ Cplx s_mn, s_mx;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && minmax) {
+    s_mn.re = minmax[4 * n]; s_mn.im = minmax[4 * n + 1]; s_mx.re = minmax[4 * n + 2]; s_mx.im = minmax[4 * n + 3];
+  } else if (threadIdx.x == 0) {
     Cplx mn = partial[(long long)n * gridDim.x * 2], mx = partial[(long long)n * gridDim.x * 2 + 1];
     for (int b = 1; b < (int)gridDim.x; ++b) {
       const Cplx a = partial[((long long)n * gridDim.x + b) * 2], c = partial[((long long)n * gridDim.x + b) * 2 + 1];
@@ -177,8 +185,8 @@ size_t rho_sph_harm_workspace_bytes(int32_t N, int32_t G) {
   return (size_t)N * G * G * G * sizeof(Cplx) + (size_t)N * sph_blocks(G) * 2 * sizeof(Cplx);
 }
 
-int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi, void* workspace,
-                         size_t workspace_bytes, rho_stream_t stream) {
+int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi, const double* minmax,
+                         void* workspace, size_t workspace_bytes, rho_stream_t stream) {
   RHO_REQUIRE(out && l && m && N > 0 && N <= 65535 && G > 1, "sph_harm_density: bad args");
   if (!workspace || workspace_bytes < rho_sph_harm_workspace_bytes(N, G)) return fail(RHO_ERR_WORKSPACE, "sph_harm_density: workspace too small");
   Cplx* sol = (Cplx*)workspace;
@@ -186,7 +194,7 @@ int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, con
   const dim3 grid(sph_blocks(G), (unsigned)N);
   sph_harm_solution_kernel<<<grid, 256, 0, as_stream(stream)>>>(sol, partial, G, l, m, lo, hi);
   RHO_CHECK_LAUNCH("sph_harm_solution");
-  sph_harm_normalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(sol, partial, G, out);
+  sph_harm_normalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(sol, partial, G, out, minmax);
   RHO_CHECK_LAUNCH("sph_harm_normalize");
   return RHO_OK;
 }

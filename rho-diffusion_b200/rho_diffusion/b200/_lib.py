@@ -153,7 +153,7 @@ SIGNATURES = {
     "rho_resample": (C.c_int, [c_vp, c_vp, C.c_int, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "rho_dropout": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_f32, c_u64, c_u64, c_vp, c_vp]),
     "rho_sph_harm_workspace_bytes": (c_sz, [c_i32, c_i32]),
-    "rho_sph_harm_density": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, C.c_double, C.c_double, c_vp, c_sz, c_vp]),
+    "rho_sph_harm_density": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, C.c_double, C.c_double, c_vp, c_vp, c_sz, c_vp]),
     "rho_gaussian_blobs": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_u64, c_u64, c_vp]),
 }
 

@@ -908,15 +908,18 @@ def dropout(x, p: float, seed: int = 0):
 # ------------------------------------------------------------------------------------------------
 # synthetic density fields generated on the device (rho_diffusion/data/synthetic.py)
 # ------------------------------------------------------------------------------------------------
-def sph_harm_density(l: torch.Tensor, m: torch.Tensor, grid_el: int, lo: float = -2.0, hi: float = 2.0) -> torch.Tensor:
-    """(B,) int32 device tensors of degrees / orders -> (B, 1, G, G, G) fp32 normalised |Y_l^|m| r| volumes (synthetic.py:84-124)."""
-    _need_cuda(l, m)
+def sph_harm_density(l: torch.Tensor, m: torch.Tensor, grid_el: int, lo: float = -2.0, hi: float = 2.0, minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,) int32 device tensors of degrees / orders -> (B, 1, G, G, G) fp32 normalised |Y_l^|m| r| volumes (synthetic.py:84-124).
+    ``minmax``: optional (B, 4) float64 device tensor with (re, im) of the complex minimum and maximum to normalise with."""
+    _need_cuda(l, m, minmax)
+    if minmax is not None:
+        assert minmax.dtype == torch.float64 and minmax.shape == (l.numel(), 4) and minmax.is_contiguous()
     l, m = l.to(torch.int32).contiguous(), m.to(torch.int32).contiguous()
     B = l.numel()
     out = torch.empty((B, 1, grid_el, grid_el, grid_el), dtype=torch.float32, device=l.device)
     ws = workspace(L.lib().rho_sph_harm_workspace_bytes(B, grid_el), l.device)
-    L.check(L.lib().rho_sph_harm_density(out.data_ptr(), B, grid_el, l.data_ptr(), m.data_ptr(), float(lo), float(hi), ws.data_ptr(),
-                                         ws.numel(), stream()), "sph_harm_density")
+    L.check(L.lib().rho_sph_harm_density(out.data_ptr(), B, grid_el, l.data_ptr(), m.data_ptr(), float(lo), float(hi), ptr(minmax),
+                                         ws.data_ptr(), ws.numel(), stream()), "sph_harm_density")
     return out
 
 

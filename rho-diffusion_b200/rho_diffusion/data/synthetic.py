@@ -152,7 +152,23 @@ class SphericalHarmonicDataset(torch.utils.data.Dataset):
             embs.append(emb)
         lt = torch.tensor([v[0] for v in lm], dtype=torch.int32).to(device, non_blocking=True)
         mt = torch.tensor([v[1] for v in lm], dtype=torch.int32).to(device, non_blocking=True)
-        return ops.sph_harm_density(lt, mt, G, lo, hi), torch.stack(embs).to(device, non_blocking=True)
+        mm = torch.tensor([self._extremes(l, m) for l, m in lm], dtype=torch.float64).to(device, non_blocking=True)  # noqa: E741
+        return ops.sph_harm_density(lt, mt, G, lo, hi, minmax=mm), torch.stack(embs).to(device, non_blocking=True)
+
+    def _extremes(self, l: int, m: int):  # noqa: E741
+        """(re, im) of the complex min and max the reference normalises with, from the host restatement (cached per (l, |m|)):
+        numpy orders complex numbers lexicographically and symmetric grid points tie in the real part up to rounding noise of the
+        special-function library, so these two numbers cannot be reproduced by an independent implementation -- everything else
+        of the field is generated on the device."""
+        cache = self.__dict__.setdefault("_mm_cache", {})
+        key = (l, abs(m))
+        if key not in cache:
+            g = self.grid_kwargs
+            xyz, theta, phi = make_spherical_grid(g["x"], g["y"], g["z"])
+            sol = _sph_harm(abs(m), l, theta, phi) * np.sqrt((xyz ** 2).sum(axis=0))
+            mn, mx = sol.min(), sol.max()
+            cache[key] = (float(np.real(mn)), float(np.imag(mn)), float(np.real(mx)), float(np.imag(mx)))
+        return cache[key]
 
     def device_loader(self, batch_size: int, device, rank: int = 0, world: int = 1) -> DeviceLoader:
         if world > 1:

@@ -28,6 +28,8 @@ VARIANTS = [
     {"RHO_ATTN_V2": "0"},               # first-generation attention forward (64-key tiles, P through shared memory) for every shape
     {"RHO_ATTN_V2_MIN_T": "1"},         # second-generation forward (P in TMEM, two query tiles per CTA) forced for every head-dim-64 shape
     {"RHO_ATTN_V2_MIN_T": "1", "RHO_ATTN_POLY": "0"},   # ... with every exponential on the MUFU
+    {"RHO_ATTN_BWD_V2": "0"},           # first-generation attention backward (32-column tiles, P / dS through shared memory)
+    {"RHO_ATTN_BWD_V2_MIN_T": "1"},     # second-generation backward (64-column tiles, P / dS in TMEM) forced for every head-dim-64 shape
     {"RHO_CONV_CLUSTER": "1"},          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
 ]
 
