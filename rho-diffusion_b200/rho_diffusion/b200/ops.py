@@ -409,6 +409,38 @@ def cast(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None
     return y
 
 
+class ForkFn(torch.autograd.Function):
+    """Identity with ``n`` outputs for a tensor that feeds ``n`` consumers (ResBlock input -> GroupNorm + skip, the UNet's long
+    skips, the time embedding -> every ResBlock).  Autograd would sum the consumers' gradients with ATen's ``add``; here the sum is
+    one ``rho_add_cast`` launch per extra consumer, so the training step runs no kernel that is not ours."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g for g in grads if g is not None]
+        if not gs:
+            return None, None
+        acc = gs[0]
+        for g in gs[1:]:
+            acc = cast(acc, acc.dtype, add=g if g.dtype == acc.dtype else cast(g, acc.dtype))
+        return acc, None
+
+
+def fork(x: Optional[torch.Tensor], n: int = 2):
+    """``n`` aliases of ``x`` whose gradients are summed by our own kernel (see ForkFn); plain aliases outside training."""
+    if x is None:
+        return (None,) * n
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return (x,) * n
+    outs = ForkFn.apply(x, n)
+    for o in outs:
+        carry_stats(o, x)
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 # GroupNorm32 (+FiLM / embedding add) + activation
 # ------------------------------------------------------------------------------------------------

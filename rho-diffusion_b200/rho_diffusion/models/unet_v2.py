@@ -147,7 +147,8 @@ class ResBlock(TimestepBlock):
         ops = _ops()
         x, x2 = h if isinstance(h, tuple) else (h, None)
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
-        a = gn1.forward_cl(x, x2, act=self._act, ctx=ctx)
+        (xg, x), (x2g, x2) = ops.fork(x), ops.fork(x2)          # both feed the main path AND the skip: gradients summed by our kernel
+        a = gn1.forward_cl(xg, x2g, act=self._act, ctx=ctx)
         if self.updown:
             # unet_v2.py:263-268: resample the activated features AND the skip input, then convolve
             assert x2 is None
@@ -202,7 +203,8 @@ class AttentionBlock(nn.Module):
     def forward_cl(self, h, ctx: ExecCtx):
         shape = h.shape
         xf = _ops().carry_stats(h.reshape(shape[0], -1, shape[-1]), h)            # (N, T, C) view
-        a = self.norm.forward_cl(xf, ctx=ctx)
+        xn, xf = _ops().fork(xf)                           # GroupNorm input and residual
+        a = self.norm.forward_cl(xn, ctx=ctx)
         qkv = self.qkv.forward_cl(a, ctx=ctx)              # (N, T, 3C)
         o = self.attention.forward_cl(qkv)
         out = self.proj_out.forward_cl(o, residual=xf, ctx=ctx)
@@ -358,14 +360,17 @@ class UNet(nn.Module):
         ops = _ops()
         ctx = ExecCtx(dtype=self._rho_dtype, engine=getattr(self, "_rho_engine", 0))
         emb = self._embedding(timesteps, y)
+        n_blocks = len(self.input_blocks) + 1 + len(self.output_blocks)
+        embs = list(ops.fork(emb, n_blocks))               # one alias per consumer block (gradients summed by our add kernel)
         h = ops.to_channels_last(x, ctx.dtype)
         hs = []
         for module in self.input_blocks:
-            h = module.forward_cl(h, emb, ctx)
-            hs.append(h)
-        h = self.middle_block.forward_cl(h, emb, ctx)
+            h = module.forward_cl(h, embs.pop(), ctx)
+            h, skip = ops.fork(h)                          # next block + long skip
+            hs.append(skip)
+        h = self.middle_block.forward_cl(h, embs.pop(), ctx)
         for module in self.output_blocks:
-            h = module.forward_cl((h, hs.pop()), emb, ctx)
+            h = module.forward_cl((h, hs.pop()), embs.pop(), ctx)
         a = self.out[0].forward_cl(h, act=self._act, ctx=ctx)
         o = self.out[2].forward_cl(a, y_f32=True, ctx=ctx)   # eps-hat leaves the network in fp32
         return ops.to_channels_first(o, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)

@@ -111,7 +111,7 @@ def main():
         save_model_checkpoint(model.backbone, args.save)                   # reference state_dict layout (utils.py:166-167)
         if config.training.ema_decay > 0:
             root, ext = os.path.splitext(args.save)
-            torch.save(optimizer.shadow_state_dict(model.backbone), root + "_ema" + ext)
+            torch.save({k: v.cpu() for k, v in optimizer.shadow_state_dict(model.backbone).items()}, root + "_ema" + ext)
         print("saved", args.save, "" if epoch is None else f"(epoch {epoch + 1})", flush=True)
 
     steps, t0, graphed = 0, time.time(), None

@@ -7,9 +7,9 @@ import bench
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda", 0)
-ddpm, _ = bench.build_model(dev, torch.bfloat16)
+ddpm, _ = bench.build_model(bench.CONFIGS['D'], dev, torch.bfloat16)
 ddpm.eval()
-x, y = bench.make_inputs(B, 0)
+x, y = bench.make_inputs(bench.CONFIGS['D'], B, 0)
 x, y = x.to(dev), y.to(dev)
 tt = torch.full((B,), 500, dtype=torch.int64, device=dev)
 with torch.inference_mode():

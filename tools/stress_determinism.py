@@ -10,9 +10,9 @@ from rho_diffusion.b200 import optimize
 dev = torch.device("cuda", 0)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 for B in (2, 8):
-    ddpm, _ = bench.build_model(dev, torch.bfloat16)
+    ddpm, _ = bench.build_model(bench.CONFIGS['D'], dev, torch.bfloat16)
     ddpm.eval()
-    x, y = bench.make_inputs(B, 0)
+    x, y = bench.make_inputs(bench.CONFIGS['D'], B, 0)
     x, y = x.to(dev), y.to(dev)
     tt = torch.full((B,), 437, dtype=torch.int64, device=dev)
     with torch.inference_mode():
@@ -23,11 +23,11 @@ for B in (2, 8):
 
 
 def train_run():
-    ddpm, _ = bench.build_model(dev, torch.bfloat16)
+    ddpm, _ = bench.build_model(bench.CONFIGS['D'], dev, torch.bfloat16)
     opt = ddpm.configure_optimizers(1)["optimizer"]
     ddpm, fused = optimize(ddpm, optimizer=opt, dtype=torch.bfloat16)
     ddpm.train()
-    x, y = bench.make_inputs(2, 100)
+    x, y = bench.make_inputs(bench.CONFIGS['D'], 2, 100)
     x, y = x.to(dev), y.to(dev)
     g = torch.Generator().manual_seed(1)
     losses = []
