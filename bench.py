@@ -457,26 +457,38 @@ def run_b200(args):
             ddim = max_over_ranks(h0.elapsed_time(h1))
             del xs
 
-    # ---- exact fp32 engine (the reference's own arithmetic, TF32 off): evals/s at a small batch
+    # ---- fp32 engines (the reference's own arithmetic, TF32 off): evals/s at a small batch of the exact CUDA-core engine and of the
+    #      split-bf16 tensor-core engine (six bf16 products per fp32 product, fp32 accumulation flushed every 32 MMAs)
     fp32 = None
     if args.fp32_steps > 0 and dtype == torch.bfloat16:
         from rho_diffusion.b200 import set_compute_dtype
         Bf = min(B, args.fp32_batch)
+        res, outs = {}, {}
         with torch.inference_mode():
             set_compute_dtype(ddpm, torch.float32)
             xf, yf, tf = x_dev[:Bf].contiguous(), cond_dev[:Bf].contiguous(), torch.full((Bf,), 500, dtype=torch.int64, device=device)
-            ddpm.backbone(xf, tf, yf)
-            barrier()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(args.fp32_steps):
-                ddpm.backbone(xf, tf, yf)
-            p1.record()
-            barrier()
-            ms_fp32 = max_over_ranks(p0.elapsed_time(p1))
+            for name, split in (("cuda_core", False), ("split_bf16_tcgen05", True)):
+                ops.set_fp32_split(split)
+                outs[name] = ddpm.backbone(xf, tf, yf).double()
+                barrier()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(args.fp32_steps):
+                    ddpm.backbone(xf, tf, yf)
+                p1.record()
+                barrier()
+                res[name] = max_over_ranks(p0.elapsed_time(p1))
+            ops.set_fp32_split(False)
             set_compute_dtype(ddpm, dtype)
-        fp32 = {"metric": "UNet denoise evals/s, exact fp32 engine (TF32 off)", "value": world * Bf * args.fp32_steps / (ms_fp32 * 1e-3),
-                "unit": "evals/s", "batch_per_gpu": Bf, "steps": args.fp32_steps, "ms_per_eval_batch": ms_fp32 / args.fp32_steps}
+        diff = outs["split_bf16_tcgen05"] - outs["cuda_core"]
+        fp32 = {"metric": "UNet denoise evals/s, exact fp32 engine (TF32 off, CUDA cores)", "unit": "evals/s", "batch_per_gpu": Bf, "steps": args.fp32_steps,
+                "value": world * Bf * args.fp32_steps / (res["cuda_core"] * 1e-3), "ms_per_eval_batch": res["cuda_core"] / args.fp32_steps,
+                "split_bf16": {"metric": "same eval on the split-bf16 tensor-core engine (RHO_FP32_SPLIT=1)",
+                               "value": world * Bf * args.fp32_steps / (res["split_bf16_tcgen05"] * 1e-3),
+                               "ms_per_eval_batch": res["split_bf16_tcgen05"] / args.fp32_steps,
+                               "speedup": res["cuda_core"] / res["split_bf16_tcgen05"],
+                               "rel_l2_vs_cuda_core": float(diff.norm() / outs["cuda_core"].norm())}}
+        del outs
 
     # ---- training leg (samples/s): q_sample -> UNet fwd/bwd -> fused AdamW; N > 1: bucketed NCCL all-reduce overlapped with backward
     train = None

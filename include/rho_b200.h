@@ -65,6 +65,13 @@ int rho_nc_to_cl(const void* src, int src_dtype, void* dst, int dst_dtype, int64
 int rho_cl_to_nc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t N, int64_t C, int64_t S, rho_stream_t stream);
 /* dst = a (+ b) elementwise with dtype conversion; b may be NULL */
 int rho_add_cast(const void* a, int a_dtype, const void* b, int b_dtype, void* dst, int dst_dtype, int64_t n, rho_stream_t stream);
+/* Split-bf16 engine ("fp32-accurate on the tensor cores", the exact path the reference's TF32-off arithmetic asks for,
+ * scripts/training_ddp.py:42-43): rho_split3_concat writes x = x1 + x2 + x3 (three bf16 terms, 24 mantissa bits) as the six
+ * channel blocks [x1 | x1 | x2 | x1 | x2 | x3] of a channels-last bf16 tensor [rows, 6 (C1 + C2)] (x2 = optional second source
+ * of a channel concat); rho_split3_weight expands fp32 weights [Cout, Cin, taps] to [Cout, 6 Cin, taps] with the bf16-exact terms
+ * [w1 | w2 | w1 | w3 | w2 | w1].  rho_conv_fwd on those operands with y_f32 = 1 accumulates the six products in fp32 (TMEM). */
+int rho_split3_concat(const float* x, int32_t C1, const float* x2, int32_t C2, void* out, int64_t rows, rho_stream_t stream);
+int rho_split3_weight(const float* w, float* out, int32_t Cout, int32_t Cin, int32_t taps, rho_stream_t stream);
 /* x *= (*scale_dev if scale_dev else 1) * scale_host, in place (upstream-gradient scaling without a host sync) */
 int rho_scale(void* x, int dtype, int64_t n, const float* scale_dev, float scale_host, rho_stream_t stream);
 

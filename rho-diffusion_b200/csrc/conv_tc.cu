@@ -477,6 +477,179 @@ static int dispatch_tc(int bn, int bk, const TcMaps& maps_in, const TcParams& p_
   return fail(RHO_ERR_UNSUPPORTED, "conv_tc: no kernel for BLOCK_N=%d BLOCK_K=%d", bn, bk);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// fp32-output variant for the split-bf16 engine (six bf16 products per fp32 product, rho_b200.h: rho_split3_concat).
+// The tensor core's fp32 accumulation TRUNCATES: measured on the plain kernel above, the error of a split-bf16 conv grows
+// linearly with the contraction length (5e-6 at K = 864 ... 1.5e-4 at K = 27648, tools/fp32_split_error.py) -- each of the K / 16
+// accumulating MMAs loses up to one ulp of the running sum, always toward zero.  Here a chain is at most TCF_FLUSH K blocks
+// (TCF_FLUSH * BLOCK_K / 16 MMAs) long: the issuer alternates between TWO TMEM accumulators, and the epilogue warps add each
+// finished partial sum into fp32 REGISTERS (round-to-nearest FADD) while the tensor core fills the other buffer.
+constexpr int TCF_FLUSH = 8;
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_tc_f32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p,
+                                                          const float* __restrict__ bias, float* __restrict__ y) {
+  constexpr int ROW_BYTES = BLOCK_K * 2;
+  constexpr int A_BYTES = TC_BM * ROW_BYTES;
+  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], part_ready[2], part_drained[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = (int)blockIdx.x % p.n_blocks;
+  int mt = (int)blockIdx.x / p.n_blocks;
+  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th = mt % p.tiles_h; mt /= p.tiles_h;
+  const int td = mt % p.tiles_d; mt /= p.tiles_d;
+  const int tn = mt;
+  const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = tn * p.bn;
+  const int kb_per_tap = (p.C1 + p.C2) / BLOCK_K;
+  const int num_kb = p.ntaps * kb_per_tap;
+  const int num_parts = (num_kb + TCF_FLUSH - 1) / TCF_FLUSH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&part_ready[b], 1); mbar_init(&part_drained[b], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32u : (uint32_t)(2 * BLOCK_N);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const TcTap tap = p.taps[t];
+      for (int kb = 0; kb < kb_per_tap; ++kb) {
+        const int c = kb * BLOCK_K;
+        const int src = c >= p.C1 ? 1 : 0;
+        const int cc = src ? c - p.C1 : c;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_5d(sa, &maps.a[tap.map][src], &full_bar[stage], cc, w0 + tap.dw, h0 + tap.dh, d0 + tap.dd, n0 + tap.dn);
+          tma_load_2d(sa + A_BYTES, &maps.w, &full_bar[stage], tap.kofs + c, nb * BLOCK_N);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc<BLOCK_N>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int part = 0; part < num_parts; ++part) {
+      const int b = part & 1;
+      if (part >= 2) {                              // the epilogue warps have drained this buffer's previous partial sum
+        mbar_wait(&part_drained[b], (uint32_t)((part >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      const int kb_end = min(num_kb, (part + 1) * TCF_FLUSH);
+      for (int kb = part * TCF_FLUSH; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = umma_desc<ROW_BYTES>(sa);
+        const uint64_t bdesc = umma_desc<ROW_BYTES>(sa + A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16(tmem_base + (uint32_t)(b * BLOCK_N), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                     (kb != part * TCF_FLUSH) || k != 0);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&part_ready[b]);
+      __syncwarp();
+    }
+  } else {
+    const int et = threadIdx.x - 64;   // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) sbias[i] = bias ? bias[nb * BLOCK_N + i] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int lane_base = 32 * (warp & 3);
+    const int r = lane_base + lane;
+    const int iw = r & (p.bw - 1), ih = (r >> p.lbw) & (p.bh - 1), id = (r >> (p.lbw + p.lbh)) & (p.bd - 1),
+              in = r >> (p.lbw + p.lbh + p.lbd);
+    const int gw = w0 + iw, gh = h0 + ih, gd = d0 + id, gn = n0 + in;
+    const bool valid = gw < p.Gw && gh < p.Gh && gd < p.Gd && gn < p.N;
+    const long long pos = (((long long)gn * p.Do + (gd * p.os_d + p.oo_d)) * p.Ho + (gh * p.os_h + p.oo_h)) * p.Wo + (gw * p.os_w + p.oo_w);
+    float acc[BLOCK_N];
+#pragma unroll
+    for (int c = 0; c < BLOCK_N; ++c) acc[c] = sbias[c];
+    for (int part = 0; part < num_parts; ++part) {
+      const int b = part & 1;
+      mbar_wait(&part_ready[b], (uint32_t)(part >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(b * BLOCK_N + c0), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[c0 + e] += __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+      mbar_arrive(&part_drained[b]);
+    }
+    if (valid) {
+      float* dst = y + pos * p.Cout + nb * BLOCK_N;
+#pragma unroll
+      for (int c = 0; c < BLOCK_N; c += 4) {
+        const float o[4] = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
+        store4(dst + c, o);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+template <int BLOCK_N, int BLOCK_K>
+static int launch_tc_f32(const TcMaps& maps, const TcParams& p, const float* bias, float* y, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (TC_BM + BLOCK_N) * BLOCK_K * 2;
+  constexpr int STAGES = (160 * 1024 / STAGE_BYTES) > 8 ? 8 : (160 * 1024 / STAGE_BYTES);       // one CTA per SM
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+  auto kern = conv_tc_f32_kernel<BLOCK_N, BLOCK_K, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_tc_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_blocks;
+  if (tiles > 2147483647LL) return fail(RHO_ERR_UNSUPPORTED, "conv_tc_f32: grid too large");
+  kern<<<(unsigned)tiles, 192, SMEM, st>>>(maps, p, bias, y);
+  RHO_CHECK_LAUNCH("conv_fwd_tcgen05_f32");
+  return RHO_OK;
+}
+
+static int dispatch_tc_f32(int bn, int bk, const TcMaps& maps, const TcParams& p_in, const float* bias, float* y, cudaStream_t st) {
+  TcParams p = p_in;
+  p.tma_store = 0;
+  p.stat_part = nullptr;
+#define RHO_TCF(BN, BK) \
+  if (bn == BN && bk == BK) return launch_tc_f32<BN, BK>(maps, p, bias, y, st)
+  RHO_TCF(128, 64); RHO_TCF(64, 64); RHO_TCF(32, 64);
+  RHO_TCF(128, 32); RHO_TCF(64, 32); RHO_TCF(32, 32);
+#undef RHO_TCF
+  return fail(RHO_ERR_UNSUPPORTED, "conv_tc_f32: no kernel for BLOCK_N=%d BLOCK_K=%d", bn, bk);
+}
+
 static bool tc_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -572,7 +745,10 @@ __global__ void pack_aux_kernel(AuxTable t, const float* __restrict__ w, bf16* _
 
 static bool tc_common_ok(const ConvGeom& g, const rho_conv_params* p) {
   if (tc_disabled()) return false;
-  if (p->act_dtype != RHO_BF16 || p->w_dtype != RHO_BF16 || p->y_f32) return false;
+  if (p->act_dtype != RHO_BF16 || p->w_dtype != RHO_BF16) return false;
+  // fp32 output (the split-bf16 "exact on tensor cores" engine and nothing else): per-tap kernel, per-thread fp32 stores, no
+  // residual (bf16-only in the epilogue), no fused upsample
+  if (p->y_f32 && (p->residual != nullptr || !(g.ud == 1 && g.uh == 1 && g.uw == 1))) return false;
   if (pick_block_k(g.C1, g.C2) < 32 || pick_block_n(g.Cout) == 0) return false;
   if (g.taps > TC_MAX_TAPS) return false;
   if (g.N > 32767 || g.D > 32767 || g.H > 32767 || g.W > 32767) return false;
@@ -673,6 +849,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
     if (is_upsampled(g)) { probe.Gd = g.D; probe.Gh = g.H; probe.Gw = g.W; } else { probe.Gd = g.Do; probe.Gh = g.Ho; probe.Gw = g.Wo; }
     pick_tile(probe);
     bn = pick_block_n_for_grid(g.Cout, (long long)probe.tiles_w * probe.tiles_h * probe.tiles_d * probe.tiles_n);
+    if (p->y_f32 && bn > 128) bn = 128;          // the fp32-output kernel keeps BLOCK_N partial sums per thread in registers
   }
   tp.n_blocks = g.Cout / bn;
   TcMaps maps;
@@ -710,7 +887,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
     return RHO_OK;
   }
 
-  if (is_plain(g)) {
+  if (is_plain(g) && !p->y_f32) {
     const HaloPlan hp = halo_plan(g.N, g.D, g.H, g.W, g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw);
     if (hp.ok) return conv_halo_run(hp, p->x, p->x2, p->w_packed, p->bias, (const bf16*)p->residual, (bf16*)p->y, nullptr, 0, stat_part, st);
   }
@@ -758,6 +935,7 @@ int conv_fwd_tc(const ConvGeom& g, const rho_conv_params* p, cudaStream_t st) {
   }
   rc = encode_weight_maps(maps, p->w_packed, g.Ktot, g.Cout, bk, bn);
   if (rc) return rc;
+  if (p->y_f32) return dispatch_tc_f32(bn, bk, maps, tp, p->bias, (float*)p->y, st);
   return dispatch_tc<bf16>(bn, bk, maps, tp, p->bias, (const bf16*)p->residual, (bf16*)p->y, (bf16*)nullptr, st);
 }
 

@@ -80,6 +80,51 @@ __global__ void __launch_bounds__(256) add_cast8_kernel(const TA* __restrict__ a
   }
 }
 
+// fp32 -> three bf16 terms x = x1 + x2 + x3 (x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2): 24 mantissa bits), written
+// as SIX channel blocks [x1 | x1 | x2 | x1 | x2 | x3] of a channels-last tensor [rows, 6 C].  Contracted with the weight blocks
+// [w1 | w2 | w1 | w3 | w2 | w1] it gives x1 w1 + x1 w2 + x2 w1 + x1 w3 + x2 w2 + x3 w1 = x w up to 2^-24-relative terms: an
+// fp32-accurate convolution on the bf16 tensor cores with fp32 accumulation (the "split-bf16" engine, rho_b200.h).
+// x2 (optional): second source of a channel concat (C = C1 + C2).
+__global__ void __launch_bounds__(256) split3_concat_kernel(const float* __restrict__ x, int C1, const float* __restrict__ x2, int C2,
+                                                            bf16* __restrict__ out, long long rows) {
+  const int C = C1 + C2, cv = C >> 2;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cv;
+    const int c = (int)(i % cv) * 4;
+    float v[4];
+    if (c < C1) load4(x + row * C1 + c, v); else load4(x2 + row * C2 + (c - C1), v);
+    float t1[4], t2[4], t3[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      t1[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+      const float r1 = v[e] - t1[e];
+      t2[e] = __bfloat162float(__float2bfloat16_rn(r1));
+      t3[e] = __bfloat162float(__float2bfloat16_rn(r1 - t2[e]));
+    }
+    bf16* o = out + row * 6 * C + c;
+    store4(o, t1); store4(o + C, t1); store4(o + 2 * C, t2); store4(o + 3 * C, t1); store4(o + 4 * C, t2); store4(o + 5 * C, t3);
+  }
+}
+
+// weights [Cout, Cin, taps] fp32 -> [Cout, 6 Cin, taps] fp32 holding the bf16-exact terms in the block order [w1 | w2 | w1 | w3 | w2 | w1]
+__global__ void __launch_bounds__(256) split3_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const long long co = i / ((long long)taps * Cin);
+    const float v = w[i];
+    const float w1 = __bfloat162float(__float2bfloat16_rn(v));
+    const float r1 = v - w1;
+    const float w2 = __bfloat162float(__float2bfloat16_rn(r1));
+    const float w3 = __bfloat162float(__float2bfloat16_rn(r1 - w2));
+    float* o = out + (co * 6 * Cin + ci) * taps + t;
+    const long long blk = (long long)Cin * taps;
+    o[0] = w1; o[blk] = w2; o[2 * blk] = w1; o[3 * blk] = w3; o[4 * blk] = w2; o[5 * blk] = w1;
+  }
+}
+
 template <typename T>
 __global__ void scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ s_dev, float s_host) {
   const float s = (s_dev ? *s_dev : 1.0f) * s_host;
@@ -156,6 +201,24 @@ int rho_scale(void* x, int dtype, int64_t n, const float* scale_dev, float scale
   else if (dtype == RHO_BF16) scale_kernel<bf16><<<blocks, 256, 0, as_stream(stream)>>>((bf16*)x, n, scale_dev, scale_host);
   else return fail(RHO_ERR_INVALID_ARG, "scale: bad dtype");
   RHO_CHECK_LAUNCH("scale");
+  return RHO_OK;
+}
+
+int rho_split3_concat(const float* x, int32_t C1, const float* x2, int32_t C2, void* out, int64_t rows, rho_stream_t stream) {
+  RHO_REQUIRE(x && out && rows > 0 && C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "split3_concat: bad args");
+  const long long total = rows * ((C1 + C2) >> 2);
+  const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 16);
+  split3_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, C1, x2, C2, (bf16*)out, rows);
+  RHO_CHECK_LAUNCH("split3_concat");
+  return RHO_OK;
+}
+
+int rho_split3_weight(const float* w, float* out, int32_t Cout, int32_t Cin, int32_t taps, rho_stream_t stream) {
+  RHO_REQUIRE(w && out && Cout > 0 && Cin > 0 && taps > 0, "split3_weight: bad args");
+  const long long total = (long long)Cout * Cin * taps;
+  const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 16);
+  split3_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, out, Cout, Cin, taps);
+  RHO_CHECK_LAUNCH("split3_weight");
   return RHO_OK;
 }
 

@@ -113,6 +113,8 @@ SIGNATURES = {
     "rho_cl_to_nc": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp]),
     "rho_add_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_i64, c_vp]),
     "rho_scale": (C.c_int, [c_vp, C.c_int, c_i64, c_vp, c_f32, c_vp]),
+    "rho_split3_concat": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "rho_split3_weight": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "rho_conv_pack_weight": (C.c_int, [c_vp, c_vp, C.c_int, c_i32, c_i32, c_i32, c_vp]),
     "rho_conv_aux_weight_bytes": (c_sz, [P(ConvParams)]),
     "rho_conv_pack_weight_aux": (C.c_int, [P(ConvParams), c_vp, c_vp, c_vp]),

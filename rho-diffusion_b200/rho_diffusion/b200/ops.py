@@ -379,8 +379,81 @@ def aux_weight(owner, weight, spec: ConvSpec, x, x2, wp, dtype):
     return out
 
 
+# ---- split-bf16 engine: fp32-accurate convolutions on the bf16 tensor cores (inference) ----------------------------------
+_fp32_split = None
+
+
+def fp32_split_enabled() -> bool:
+    """``RHO_FP32_SPLIT`` = 0 | 1 (default 0; also ``ops.set_fp32_split``): under ``torch.no_grad`` the fp32 path runs its
+    convolutions as six bf16 tensor-core products (x = x1 + x2 + x3, w = w1 + w2 + w3, all terms above 2^-24 kept) accumulated in
+    fp32 with a register flush every 32 MMAs instead of the CUDA-core FFMA engine: 2.5x faster on config D and CLOSER to the fp64
+    result (5-7e-7 relative per conv at any contraction length vs 5e-7 ... 3e-6), but not bit-compatible with it -- a 50-step
+    shared-noise trajectory drifts 1.4e-3 from the reference's instead of < 1e-3 -- so the exact path keeps the CUDA-core engine
+    by default.  Training (autograd) always uses the CUDA-core engine, whose backward shares its operands."""
+    global _fp32_split
+    if _fp32_split is None:
+        import os
+        _fp32_split = os.environ.get("RHO_FP32_SPLIT", "0") == "1" and os.environ.get("RHO_DISABLE_TCGEN05", "0") != "1"
+    return _fp32_split
+
+
+def set_fp32_split(on: bool) -> None:
+    global _fp32_split
+    _fp32_split = bool(on)
+
+
+def split_packed_weight(owner, weight: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, *k] fp32 -> packed bf16 [Cout, taps, 6 Cin] of the bf16-exact terms [w1 | w2 | w1 | w3 | w2 | w1] (cached like
+    :func:`packed_weight`)."""
+    cache = owner.__dict__.setdefault("_rho_packed", {})
+    ver = (weight._version, _weights_epoch, weight.data_ptr(), tuple(weight.shape))
+    hit = cache.get("split6")
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (Cout * Cin)
+    with torch.inference_mode(False):
+        out = hit[1] if (hit is not None and hit[1].shape == (Cout, taps, 6 * Cin)) else \
+            torch.empty((Cout, taps, 6 * Cin), dtype=torch.bfloat16, device=w.device)
+        w6 = torch.empty((Cout, 6 * Cin, taps), dtype=torch.float32, device=w.device)
+    L.check(L.lib().rho_split3_weight(w.data_ptr(), w6.data_ptr(), Cout, Cin, taps, stream()), "split3_weight")
+    L.check(L.lib().rho_conv_pack_weight(w6.data_ptr(), out.data_ptr(), BF16, Cout, 6 * Cin, taps, stream()), "conv_pack_weight")
+    cache["split6"] = (ver, out)
+    return out
+
+
+def _conv_fp32_split(owner, x, x2, weight, bias, residual, spec):
+    """fp32 conv_nd through the tcgen05 engine (see fp32_split_enabled); returns None when the shape has to stay on the CUDA cores."""
+    Ct = x.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+    Cout = weight.shape[0]
+    if Ct % 32 or Cout % 32 or x.shape[-1] % 4 or (x2 is not None and x2.shape[-1] % 4):
+        return None
+    if max(spec.up) > 1:                               # the fused-upsample pack pre-sums taps (not bf16-exact): upsample explicitly
+        x = upsample_nearest(x, spec.up)
+        x2 = upsample_nearest(x2, spec.up) if x2 is not None else None
+        spec = ConvSpec(spec.dims, spec.kernel, spec.stride, (1,) * spec.dims)
+    rows = x.numel() // x.shape[-1]
+    xc = torch.empty((*x.shape[:-1], 6 * Ct), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().rho_split3_concat(x.data_ptr(), x.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0, xc.data_ptr(), rows, stream()),
+            "split3_concat")
+    wp6 = split_packed_weight(owner, weight)
+    b = bias.detach().float() if bias is not None else None
+    p = _conv_params(xc, None, wp6, b, None, None, spec, Cout, L.CONV_TCGEN05, True)
+    if int(L.lib().rho_conv_engine_for(C.byref(p))) != L.CONV_TCGEN05:
+        return None
+    y = conv_forward(xc, None, wp6, b, None, spec, Cout, L.CONV_TCGEN05, y_f32=True)
+    return cast(y, torch.float32, add=residual) if residual is not None else y
+
+
 def conv(owner, x, x2, weight, bias, residual, spec, dtype, engine=L.CONV_AUTO, y_f32=False):
     """conv_nd through the autograd tape; ``owner`` is the module that holds ``weight`` (packed-weight cache)."""
+    if dtype == torch.float32 and engine == L.CONV_AUTO and not torch.is_grad_enabled() and fp32_split_enabled():
+        y = _conv_fp32_split(owner, x, x2, weight, bias, residual, spec)
+        if y is not None:
+            return y
     wp = packed_weight(owner, weight, dtype)
     aux = aux_weight(owner, weight, spec, x, x2, wp, dtype) if engine != L.CONV_SIMT else None
     stats = [] if (dtype == torch.bfloat16 and engine != L.CONV_SIMT and not y_f32) else None

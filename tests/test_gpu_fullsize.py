@@ -70,17 +70,22 @@ def test_config_d_full_size_bf16_eval_matches_oracle(config_d_oracle):
     assert got.shape == ref.shape and err < 2e-2
 
 
-def test_config_d_full_size_fp32_eval_matches_oracle(config_d_oracle):
-    from rho_diffusion.b200 import set_compute_dtype
+@pytest.mark.parametrize("engine", ["cuda_core", "split_bf16"])
+def test_config_d_full_size_fp32_eval_matches_oracle(config_d_oracle, engine):
+    """fp32 contract (<= 1e-5 relative) at full size on both fp32 engines: the exact CUDA-core FFMA engine (default) and the
+    split-bf16 tensor-core engine (six bf16 products per fp32 product, flushed fp32 accumulation; RHO_FP32_SPLIT=1)."""
+    from rho_diffusion.b200 import ops, set_compute_dtype
     model, sd, x, y, t, ref = config_d_oracle
     set_compute_dtype(model, torch.float32)
+    ops.set_fp32_split(engine == "split_bf16")
     try:
         with torch.inference_mode():
             got = model(x[:1].to(DEV), t[:1].to(DEV), y[:1].to(DEV))
     finally:
+        ops.set_fp32_split(False)
         set_compute_dtype(model, torch.bfloat16)
     err = rel_l2(got, ref)
-    print("config D (64^3) fp32 vs fp32 oracle: rel L2", err)
+    print(f"config D (64^3) fp32 ({engine}) vs fp32 oracle: rel L2", err)
     assert err < 1e-5
 
 

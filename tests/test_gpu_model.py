@@ -211,6 +211,28 @@ def test_reverse_process_shared_noise_matches_reference(graph):
     assert den.min() >= -1 and den.max() <= 1
 
 
+def test_reverse_process_on_the_split_bf16_engine_stays_near_the_reference_trajectory():
+    """The split-bf16 fp32 engine is as close to exact arithmetic as the CUDA-core engine but rounds differently from both it and the
+    reference's CPU kernels; 50 chained evals + clamps amplify that to ~1.4e-3 max-abs on this fixture (CUDA-core engine: < 1e-3),
+    with the final density-field moments still equal to 1e-4."""
+    from rho_diffusion.b200 import ops
+    ddpm, g, _, y = make_ddpm()
+    ddpm.eval()
+    rv, T = g["reverse"], g["T"]
+    noises = {T - 1 - i: z for i, z in enumerate(rv["z"])}
+    ops.set_fp32_split(True)
+    try:
+        res = ddpm.reverse_process(torch.zeros(rv["x_init"].shape, device=DEV), conditions=y.to(DEV), x_init=rv["x_init"].to(DEV),
+                                   noises=noises, use_cuda_graph=False)
+    finally:
+        ops.set_fp32_split(False)
+    den, ref = res["denoised"].cpu(), rv["denoised"]
+    assert float((den - ref).abs().max()) < 4e-3
+    for k in range(den.shape[0]):
+        a, b = den[k].double().flatten(), ref[k].double().flatten()
+        assert abs(float(a.mean() - b.mean())) < 1e-4 and abs(float(a.var() - b.var())) < 1e-4
+
+
 def test_reverse_process_graph_in_kernel_noise_is_deterministic_and_bounded():
     ddpm, g, _, y = make_ddpm(torch.bfloat16)
     ddpm.eval()

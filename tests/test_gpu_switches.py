@@ -30,7 +30,8 @@ VARIANTS = [
     {"RHO_ATTN_V2_MIN_T": "1", "RHO_ATTN_POLY": "0"},   # ... with every exponential on the MUFU
     {"RHO_ATTN_BWD_V2": "0"},           # first-generation attention backward (32-column tiles, P / dS through shared memory)
     {"RHO_ATTN_BWD_V2_MIN_T": "1"},     # second-generation backward (64-column tiles, P / dS in TMEM) forced for every head-dim-64 shape
-    {"RHO_CONV_CLUSTER": "1"},          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
+    {"RHO_CONV_CLUSTER": "1"},
+    {"RHO_FP32_SPLIT": "1"},            # fp32 inference convs as six bf16 tensor-core products with flushed fp32 accumulation          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
 ]
 
 
@@ -48,6 +49,8 @@ def test_switched_paths_keep_parity(env):
         select = select.replace("test_conv_epilogue_groupnorm_statistics", "(test_conv_epilogue_groupnorm_statistics and not case9)")
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_ops.py"), os.path.join(ROOT, "tests", "test_gpu_model.py"),
            "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", select + " or test_unet_forward_bf16_within_tolerance"]
+    if "RHO_FP32_SPLIT" in env:            # the fp32 goldens (<= 1e-5 against the unmodified reference) and the per-block taps on the split engine
+        cmd[-1] = "test_unet_forward_fp32_matches_reference or test_per_block_taps_fp32 or test_split_bf16"
     r = subprocess.run(cmd, env=e, cwd=ROOT, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-2000:]
     assert r.returncode == 0, tail
