@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --c
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active \
   --clock-control none --profile-from-start off --csv --page raw --log-file gpurun_out/r02_ncu_eval_b8_per_launch.csv python tools/one_eval.py 8 > gpurun_out/ncu_eval.log 2>&1; echo "ncu eval rc=$?"
 python tools/ncu_traffic.py gpurun_out/r02_ncu_eval_b8_per_launch.csv gpurun_out/r02_ncu_traffic_b8.json | head -16
-for k in conv_tc_kernel conv_halo_kernel attn_tc2_kernel; do
+for k in conv_tc_kernel conv_halo_kernel attn_tc2_kernel gn_apply8_kernel; do
   skip=8; [ $k = attn_tc2_kernel ] && skip=1
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -s $skip -c 2 -o gpurun_out/r02_ncu_full_$k -f python tools/one_eval.py 8 > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu $k rc=$?"
   ncu -i gpurun_out/r02_ncu_full_$k.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_${k}_raw.csv 2>/dev/null
