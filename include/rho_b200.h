@@ -385,13 +385,60 @@ int rho_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t 
  *                         workspace: rho_sph_harm_workspace_bytes(N, G).
  *   rho_gaussian_blobs    out[n] (fp32, [N, D, H, W], D = 1 / H = 1 for lower n) = 2 min(sum_k exp(-|x - c_k|^2 / 2 w_n^2), 1) - 1
  *                         with n_blobs[n] (<= 8) centres from Philox4x32-10(counter = (first_index + n, k), key = seed), each
- *                         coordinate 0.2 + 0.6 u, x at cell centres of the unit box (the last axis is coordinate 0). */
+ *                         coordinate 0.2 + 0.6 u, x at cell centres of the unit box (the last axis is coordinate 0).
+ *   rho_lineprofile       out[b, f] (fp32, [B, G]) = the rotational spectrum of SpectroscopyDataset.simulate_lineprofile
+ *                         (rho_diffusion/data/spectroscopy.py:142-189) divided by its maximum (:120-121): sum over the transitions
+ *                         k in [offsets[b], offsets[b + 1]) whose centre lies inside [grid[0], grid[G - 1]] of
+ *                         intensities[k] exp(-(grid[f] - centers[k])^2 / (2 widths[b]^2)), with numpy's promotion (fp32 difference and
+ *                         square, fp64 division, exp and sum).  workspace: rho_lineprofile_workspace_bytes(B, G). */
+size_t rho_lineprofile_workspace_bytes(int32_t B, int32_t G);
+int rho_lineprofile(float* out, int32_t B, int32_t G, const float* grid, const float* centers, const float* intensities, const int32_t* offsets,
+                    const double* widths, void* workspace, size_t workspace_bytes, rho_stream_t stream);
 size_t rho_sph_harm_workspace_bytes(int32_t N, int32_t G);
 int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, const int32_t* m, double lo, double hi,
                          const double* minmax /* optional [N][4]: re, im of the complex min and max to normalise with */, void* workspace,
                          size_t workspace_bytes, rho_stream_t stream);
 int rho_gaussian_blobs(float* out, int32_t N, int32_t D, int32_t H, int32_t W, const int32_t* n_blobs, const float* width, uint64_t seed,
                        uint64_t first_index, rho_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * the two remaining registered backbones: v1 UNet (rho_diffusion/models/unet.py:30-269) and the diffusion
+ * VisionTransformer (rho_diffusion/models/vit.py:31-372).  Their contractions run on rho_conv_* / rho_attention_*; these are the
+ * element-wise / row-wise pieces around them:
+ *   rho_activation[_bwd]  y = act(x) / dx = dy act'(x): `self.activation(self.conv1(x))` (unet.py:122-123), Linear -> activation
+ *                         (vit.py:155-161, 166-170, 311-315); 16-byte aligned pointers.
+ *   rho_convt_weight      dst[b][a][taps-1-t] = src[a][b][t] (fp32): nn.ConvTranspose{2,3}d(k, stride 1, padding k//2) of the v1 up
+ *                         path (unet.py:69-75, 94-100) IS conv_nd with the [Cin, Cout, *k] weight transposed and flipped; the map is
+ *                         its own adjoint with A and B swapped (weight gradient); taps = 1 is a plain transpose.
+ *   rho_patchify          inverse = 0: x [N, C, D, H, W] -> tokens [N, T, C pd ph pw], tokens in row-major order of the patch grid,
+ *                         features in the order of weight.view(E, -1): the kernel = stride = patch conv of PatchEmbedding
+ *                         (vit.py:72-77, 119-126) becomes a Linear over tokens; inverse = 1: tokens -> field (+ bias[c]): the
+ *                         kernel = stride ConvTranspose `output_conv` (vit.py:297-303, 358-371) after its Linear.  Each direction
+ *                         is the other's adjoint (without the bias).
+ *   rho_bias_expand       dst[c reps + r] = src[c]; inverse: dst[c] = sum_r src[c reps + r] (that ConvTranspose's bias as a Linear bias)
+ *   rho_add_bcast         y[o][i] = x[o][i] + add[i] (positional embedding added to every sample, vit.py:349-352); inner % 4 == 0
+ *   rho_colsum            out[g][c] = sum_{r < rows} src[(g rows + r) ld + c], fixed order (gradients of the broadcast operands)
+ *   rho_layernorm_*       nn.LayerNorm(C) over tokens [rows, C] (vit.py:140-141), optionally of x + pre_add[row / rows_per_sample]
+ *                         (the diffusion-time embedding added before norm_1, vit.py:179-181); stats [rows, 2] = (mean, rstd);
+ *                         backward: dx, dgamma / dbeta (deterministic two-stage sums over a workspace), dpre_add [samples, C]. */
+typedef struct {
+  int64_t rows; int32_t C; int32_t rows_per_sample;
+  int32_t in_dtype, out_dtype; float eps; int32_t _pad;
+  const void* x; const float* pre_add /* optional [rows / rows_per_sample, C] */; const float* gamma; const float* beta;
+  void* y; float* stats;
+} rho_layernorm_params;
+int rho_activation(const void* x, void* y, int dtype, int64_t n, int act, rho_stream_t stream);
+int rho_activation_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, int act, rho_stream_t stream);
+int rho_convt_weight(const float* src, float* dst, int32_t A, int32_t B, int32_t taps, rho_stream_t stream);
+int rho_patchify(const void* src, int src_dtype, void* dst, int dst_dtype, const float* bias, int32_t N, int32_t C, int32_t D, int32_t H,
+                 int32_t W, int32_t pd, int32_t ph, int32_t pw, int32_t inverse, rho_stream_t stream);
+int rho_bias_expand(const float* src, float* dst, int32_t C, int32_t reps, int32_t inverse, rho_stream_t stream);
+int rho_add_bcast(const void* x, int dtype, const float* add, void* y, int64_t outer, int64_t inner, rho_stream_t stream);
+int rho_colsum(const void* src, int dtype, int64_t ld, int32_t groups, int32_t rows, int64_t cols, float* out, rho_stream_t stream);
+int rho_layernorm_fwd(const rho_layernorm_params* p, rho_stream_t stream);
+size_t rho_layernorm_bwd_workspace_bytes(const rho_layernorm_params* p);
+int rho_layernorm_bwd(const rho_layernorm_params* p, const void* dy, void* dx, float* dgamma, float* dbeta, float* dpre_add, void* workspace,
+                      size_t workspace_bytes, rho_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -80,3 +80,38 @@ def loss_curve_inputs(step: int, shape, T: int, n_data: int = 8):
 import torch as _torch  # noqa: E402
 
 _RANDINT, _RANDN = _torch.randint, _torch.randn
+
+
+# ---- the two remaining registered backbones ---------------------------------------------------------------------
+# v1 UNet (models/unet.py): stride-1 blocks, ConvTranspose up path, GroupNorm(8); VisionTransformer (models/vit.py): patch
+# embedding, LayerNorm, nn.MultiheadAttention, MLP, kernel = stride ConvTranspose.  "model" is the registry name.
+BACKBONE_CASES = {
+    # 2-D, ReLU (the constructor default), residual branches (ConvTranspose on the up path)
+    "unet1_2d": dict(model="UNet", kwargs=dict(block_type="UNetBlock2d", input_channels=3, down_channels=[32, 64, 128],
+                                               up_channels=[128, 64, 32], time_embedding_dim=32, activation="ReLU", residual=True),
+                     x_shape=(2, 3, 16, 24), t=[3, 700]),
+    # 2-D, GELU, no residual branch, wider time embedding, 64-multiple channels (tensor-core shapes in bf16)
+    "unet1_2d_gelu": dict(model="UNet", kwargs=dict(block_type="UNetBlock2d", input_channels=1, down_channels=[64, 128],
+                                                    up_channels=[128, 64], time_embedding_dim=64, activation="GELU", residual=False),
+                          x_shape=(2, 1, 32, 32), t=[0, 999]),
+    # 3-D blocks: N == down_channels[k] == depth would be needed for the reference's `time_pe[..., None, None]` add to broadcast
+    # (unet.py:130-132); the generator records whether the reference runs at all
+    "unet1_3d": dict(model="UNet", kwargs=dict(block_type="UNetBlock3d", input_channels=1, down_channels=[32, 64],
+                                               up_channels=[64, 32], time_embedding_dim=32, activation="SiLU", residual=True),
+                     x_shape=(2, 1, 4, 8, 8), t=[5, 250]),
+    # ViT 2-D: 4x4 patches of 3-channel 16x16 images, 4 heads of 16
+    "vit_2d": dict(model="VisionTransformer", kwargs=dict(patch_size=4, input_shapes=[16, 16], num_channels=3, embedding_dim=64, hidden_dim=128,
+                                                          activation="GELU", transformer_depth=2, pos_embedding_dim=32, time_embedding_dim=32,
+                                                          dropout=0.0, num_heads=4),
+                   x_shape=(2, 3, 16, 16), t=[3, 700]),
+    # ViT 3-D: 2x2x2 patches, one head of 64 (the tcgen05 attention shape in bf16), SiLU
+    "vit_3d": dict(model="VisionTransformer", kwargs=dict(patch_size=2, input_shapes=[4, 8, 8], num_channels=1, embedding_dim=64, hidden_dim=64,
+                                                          activation="SiLU", transformer_depth=1, pos_embedding_dim=64, time_embedding_dim=64,
+                                                          dropout=0.0, num_heads=1),
+                   x_shape=(2, 1, 4, 8, 8), t=[11, 420]),
+    # ViT 1-D: patches of 8 over a series of 128, 2 heads of 32
+    "vit_1d": dict(model="VisionTransformer", kwargs=dict(patch_size=8, input_shapes=[128], num_channels=2, embedding_dim=64, hidden_dim=96,
+                                                          activation="GELU", transformer_depth=2, pos_embedding_dim=32, time_embedding_dim=48,
+                                                          dropout=0.0, num_heads=2),
+                   x_shape=(3, 2, 128), t=[1, 500, 999]),
+}

@@ -378,6 +378,41 @@ def gen_deep_galaxy(ref):
           sum(int(torch.tensor(v).prod()) for v in manifest.values()), "parameters")
 
 
+def gen_backbones(ref):
+    """v1 UNet and VisionTransformer: output of the unmodified reference modules on synthetic weights and inputs,
+    and the gradient of mse(out, target) w.r.t. every parameter (norms of all, full tensors of the small ones)."""
+    import importlib
+    from oracle.cases import BACKBONE_CASES
+    importlib.import_module("rho_diffusion.models.unet")
+    importlib.import_module("rho_diffusion.models.vit")
+    out = {}
+    for case, spec in BACKBONE_CASES.items():
+        cls = ref.registry.get("models", spec["model"])
+        torch.manual_seed(0)
+        model = cls(**spec["kwargs"])
+        manifest = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        model.load_state_dict(synth_state_dict(manifest, seed=777), strict=True)
+        x = synth_input(case + ".x", spec["x_shape"])
+        target = synth_input(case + ".target", spec["x_shape"])
+        t = torch.tensor(spec["t"], dtype=torch.long)
+        entry = {"manifest": manifest}
+        try:
+            model.train()          # dropout = 0 in every case: train == eval arithmetic
+            y = model(x, t)
+            loss = torch.nn.functional.mse_loss(y, target)
+            loss.backward()
+            entry.update(out=y.detach().clone(), loss=float(loss),
+                         grad_norms={k: float(p.grad.norm()) for k, p in model.named_parameters() if p.grad is not None},
+                         grads={k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None and p.numel() <= 4096})
+            print(f"backbone {case}: out {tuple(y.shape)} |y| {float(y.abs().mean()):.4f} loss {float(loss):.5f} "
+                  f"{len(entry['grad_norms'])} parameter gradients")
+        except RuntimeError as exc:
+            entry["reference_error"] = str(exc).splitlines()[0]
+            print(f"backbone {case}: the reference raises: {entry['reference_error']}")
+        out[case] = entry
+    torch.save(out, os.path.join(OUT, "backbones.pt"))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -394,6 +429,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "deep_galaxy":
         gen_deep_galaxy(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "backbones":
+        gen_backbones(ref)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "loss_curve":
         gen_loss_curve(ref)
         return
@@ -404,6 +442,7 @@ def main():
     gen_gaussian(ref)
     gen_sph_harm(ref)
     gen_deep_galaxy(ref)
+    gen_backbones(ref)
     gen_loss_curve(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -534,3 +534,77 @@ def philox_normal(n: int, offset: int, seed: int) -> np.ndarray:
         out[:, 2 * h] = r * np.cos(2 * np.pi * u[:, 2 * h + 1])
         out[:, 2 * h + 1] = r * np.sin(2 * np.pi * u[:, 2 * h + 1])
     return out.reshape(-1)[:n].astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# the remaining registered backbones: v1 UNet (models/unet.py) and VisionTransformer (models/vit.py)
+# --------------------------------------------------------------------------------------------
+def _conv_t(x, w, b, padding):
+    return {4: F.conv_transpose2d, 5: F.conv_transpose3d}[x.dim()](x, w, b, stride=1, padding=padding)
+
+
+def unet1_forward(sd: dict, kwargs: dict, data: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """models/unet.py:152-269 (`UNet.forward`) with its blocks (:117-136), functional over a state dict.
+
+    One deliberate difference: the time embedding is added per (sample, channel) for every data dimensionality -- the reference's
+    `time_pe[(...,) + (None,) * 2]` (:130-132) only lines up for 2-D data and raises for `UNetBlock3d`.  On 2-D data this function is
+    pinned to the unmodified reference (tests/golden/backbones.pt)."""
+    act = _ACTS[kwargs.get("activation", "ReLU")]
+    pad = kwargs.get("padding", 1)
+    residual = kwargs.get("residual", True)
+    n_down, n_up = len(kwargs["down_channels"]) - 1, len(kwargs["up_channels"]) - 1
+    pe = F.linear(timestep_embedding(t, kwargs.get("time_embedding_dim", 32)), sd["time_mlp.1.weight"], sd["time_mlp.1.bias"])
+
+    def block(p, x, is_up):
+        tp = F.linear(pe, sd[p + "time_embedding_readout.weight"], sd[p + "time_embedding_readout.bias"])
+        h = act(_conv(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=pad))
+        if is_up:
+            h = act(_conv_t(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], pad))
+        else:
+            h = act(_conv(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=pad))
+        if residual:
+            rw, rb = sd[p + "residual_conv.weight"], sd[p + "residual_conv.bias"]
+            h = h + (_conv_t(x, rw, rb, pad) if is_up else _conv(x, rw, rb, padding=pad))
+        h = h + tp.reshape(*tp.shape, *([1] * (x.dim() - 2)))
+        return act(F.group_norm(h, 8, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5))
+
+    x = _conv(data, sd["input_conv.weight"], sd["input_conv.bias"], padding=1)
+    skips = []
+    for i in range(n_down):
+        x = block(f"downsample.{i}.", x, False)
+        skips.append(x)
+    for i in range(n_up):
+        x = block(f"upsample.{i}.", torch.cat((x, skips.pop()), dim=1), True)
+    return _conv(x, sd["output_conv.weight"], sd["output_conv.bias"])
+
+
+def vit_forward(sd: dict, kwargs: dict, data: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """models/vit.py:321-372 (`VisionTransformer.forward`) with `PatchEmbedding.forward` (:119-126) and `AttentionBlock.forward`
+    (:176-189), functional over a state dict; dropout = 0 (eval arithmetic)."""
+    act = _ACTS[kwargs["activation"]]
+    p, E, heads = kwargs["patch_size"], kwargs["embedding_dim"], kwargs.get("num_heads", 16)
+    nd = len(kwargs["input_shapes"])
+    h = _conv(data, sd["patch_embedder.conv_shaper.weight"], sd["patch_embedder.conv_shaper.bias"], stride=p)
+    grid = tuple(h.shape[2:])
+    h = h.flatten(2).transpose(1, 2)                                   # n (h w d) l
+    T = h.shape[1]
+    pos = act(F.linear(timestep_embedding(torch.arange(T), kwargs.get("pos_embedding_dim", 128)), sd["pos_embedding.1.weight"],
+                       sd["pos_embedding.1.bias"]))
+    h = h + pos
+    ch = E // heads
+    for i in range(kwargs.get("transformer_depth", 8)):
+        b = f"transformer_blocks.{i}."
+        te = act(F.linear(timestep_embedding(t, kwargs.get("time_embedding_dim", 128)), sd[b + "time_transform.1.weight"]))
+        nrm = F.layer_norm(h + te[:, None, :], (E,), sd[b + "norm_1.weight"], sd[b + "norm_1.bias"], 1e-5)
+        qkv = F.linear(nrm, sd[b + "attention_layer.in_proj_weight"], sd[b + "attention_layer.in_proj_bias"])
+        q, k, v = (z.reshape(z.shape[0], T, heads, ch).transpose(1, 2) for z in qkv.chunk(3, dim=-1))
+        w = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(ch), dim=-1)
+        o = (w @ v).transpose(1, 2).reshape(-1, T, E)
+        ar = nrm + F.linear(o, sd[b + "attention_layer.out_proj.weight"], sd[b + "attention_layer.out_proj.bias"])
+        n2 = F.layer_norm(ar, (E,), sd[b + "norm_2.weight"], sd[b + "norm_2.bias"], 1e-5)
+        m = act(F.linear(n2, sd[b + "linear_block.0.weight"], sd[b + "linear_block.0.bias"]))
+        h = ar + F.linear(m, sd[b + "linear_block.3.weight"], sd[b + "linear_block.3.bias"])
+    h = F.linear(h, sd["output_projection.weight"])
+    h = h.transpose(1, 2).reshape(h.shape[0], -1, *grid)              # b (j k l) c -> b c j k l
+    conv_t = {1: F.conv_transpose1d, 2: F.conv_transpose2d, 3: F.conv_transpose3d}[nd]
+    return conv_t(h, sd["output_conv.weight"], sd["output_conv.bias"], stride=p)

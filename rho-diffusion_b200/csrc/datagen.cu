@@ -68,6 +68,51 @@ __global__ void __launch_bounds__(256) gaussian_blobs_kernel(float* __restrict__
   }
 }
 
+// ---- rotational-spectrum line profiles (rho_diffusion/data/spectroscopy.py:142-189) --------------------------------------
+// profile[f] = sum_k I_k exp(-(nu_f - c_k)^2 / (2 w^2)) over the transitions whose centre lies inside the grid, with numpy's
+// promotion rules (fp32 difference and square, fp64 division / exp / sum), then divided by its maximum (spectroscopy.py:120-121).
+// Ragged batch: sample b owns transitions [offsets[b], offsets[b + 1]).
+__global__ void __launch_bounds__(256) lineprofile_kernel(double* __restrict__ prof, double* __restrict__ partial_max, int G,
+                                                          const float* __restrict__ grid, const float* __restrict__ centers,
+                                                          const float* __restrict__ intens, const int32_t* __restrict__ offsets,
+                                                          const double* __restrict__ widths) {
+  const int b = blockIdx.y;
+  const int k0 = offsets[b], k1 = offsets[b + 1];
+  const float lo = grid[0], hi = grid[G - 1];
+  const double w = widths[b];
+  const double denom = 2.0 * (w * w);
+  double mx = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < G; f += gridDim.x * blockDim.x) {
+    const float nu = grid[f];
+    double acc = 0.0;
+    for (int k = k0; k < k1; ++k) {
+      const float c = centers[k];
+      if (c > hi || c < lo) continue;
+      const float d = nu - c;
+      acc += (double)intens[k] * exp(-((double)(d * d)) / denom);
+    }
+    prof[(size_t)b * G + f] = acc;
+    mx = fmax(mx, acc);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial_max[(size_t)b * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) lineprofile_normalize_kernel(const double* __restrict__ prof, const double* __restrict__ partial_max, int G,
+                                                                    float* __restrict__ out) {
+  const int b = blockIdx.y;
+  double mx = 0.0;
+  for (unsigned i = 0; i < gridDim.x; ++i) mx = fmax(mx, partial_max[(size_t)b * gridDim.x + i]);
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < G; f += gridDim.x * blockDim.x)
+    out[(size_t)b * G + f] = (float)(prof[(size_t)b * G + f] / mx);
+}
+
 // ---- spherical harmonics -------------------------------------------------------------------------------------
 struct Cplx {
   double re, im;
@@ -196,6 +241,24 @@ int rho_sph_harm_density(float* out, int32_t N, int32_t G, const int32_t* l, con
   RHO_CHECK_LAUNCH("sph_harm_solution");
   sph_harm_normalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(sol, partial, G, out, minmax);
   RHO_CHECK_LAUNCH("sph_harm_normalize");
+  return RHO_OK;
+}
+
+static unsigned lp_blocks(int G) { return (unsigned)std::min<long long>(ceil_div((long long)G, 256), 256); }
+
+size_t rho_lineprofile_workspace_bytes(int32_t B, int32_t G) { return ((size_t)B * G + (size_t)B * lp_blocks(G)) * sizeof(double); }
+
+int rho_lineprofile(float* out, int32_t B, int32_t G, const float* grid, const float* centers, const float* intensities, const int32_t* offsets,
+                    const double* widths, void* workspace, size_t workspace_bytes, rho_stream_t stream) {
+  RHO_REQUIRE(out && grid && centers && intensities && offsets && widths && B > 0 && B <= 65535 && G > 1, "lineprofile: bad args");
+  if (!workspace || workspace_bytes < rho_lineprofile_workspace_bytes(B, G)) return fail(RHO_ERR_WORKSPACE, "lineprofile: workspace too small");
+  double* prof = (double*)workspace;
+  double* partial = prof + (size_t)B * G;
+  const dim3 gridDim3(lp_blocks(G), (unsigned)B);
+  lineprofile_kernel<<<gridDim3, 256, 0, as_stream(stream)>>>(prof, partial, G, grid, centers, intensities, offsets, widths);
+  RHO_CHECK_LAUNCH("lineprofile");
+  lineprofile_normalize_kernel<<<gridDim3, 256, 0, as_stream(stream)>>>(prof, partial, G, out);
+  RHO_CHECK_LAUNCH("lineprofile_normalize");
   return RHO_OK;
 }
 

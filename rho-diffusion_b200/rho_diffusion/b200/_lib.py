@@ -101,6 +101,14 @@ class X0StepParams(C.Structure):
     ]
 
 
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ("rows", c_i64), ("C", c_i32), ("rows_per_sample", c_i32),
+        ("in_dtype", c_i32), ("out_dtype", c_i32), ("eps", c_f32), ("_pad", c_i32),
+        ("x", c_vp), ("pre_add", c_vp), ("gamma", c_vp), ("beta", c_vp), ("y", c_vp), ("stats", c_vp),
+    ]
+
+
 P = C.POINTER
 # name -> (restype, argtypes); every symbol declared in include/rho_b200.h
 SIGNATURES = {
@@ -157,6 +165,18 @@ SIGNATURES = {
     "rho_sph_harm_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "rho_sph_harm_density": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, C.c_double, C.c_double, c_vp, c_vp, c_sz, c_vp]),
     "rho_gaussian_blobs": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_u64, c_u64, c_vp]),
+    "rho_lineprofile_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "rho_lineprofile": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "rho_activation": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp]),
+    "rho_activation_bwd": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_i64, C.c_int, c_vp]),
+    "rho_convt_weight": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "rho_patchify": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "rho_bias_expand": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "rho_add_bcast": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "rho_colsum": (C.c_int, [c_vp, C.c_int, c_i64, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    "rho_layernorm_fwd": (C.c_int, [P(LayerNormParams), c_vp]),
+    "rho_layernorm_bwd_workspace_bytes": (c_sz, [P(LayerNormParams)]),
+    "rho_layernorm_bwd": (C.c_int, [P(LayerNormParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

@@ -186,7 +186,8 @@ def packed_weight(owner, weight: torch.Tensor, dtype: torch.dtype) -> torch.Tens
     address and the optimizer epoch -- never in a global table, where a recycled device address of a different
     model could alias a stale entry."""
     cache = owner.__dict__.setdefault("_rho_packed", {})
-    ver = (weight._version, _weights_epoch, weight.data_ptr(), tuple(weight.shape))
+    # (an inference tensor -- a weight computed by a kernel under inference_mode -- tracks no version; such weights are never cached)
+    ver = (-1 if weight.is_inference() else weight._version, _weights_epoch, weight.data_ptr(), tuple(weight.shape))
     hit = cache.get(dtype)
     if hit is not None and hit[0] == ver:
         return hit[1]
@@ -1038,3 +1039,237 @@ def gaussian_blobs(n_blobs: torch.Tensor, width: torch.Tensor, data_shape, seed:
     L.check(L.lib().rho_gaussian_blobs(out.data_ptr(), B, D, H, W, n_blobs.data_ptr(), width.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                        int(first_index), stream()), "gaussian_blobs")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining registered backbones: v1 UNet (models/unet.py) and VisionTransformer (models/vit.py)
+# ------------------------------------------------------------------------------------------------
+class ActivationFn(torch.autograd.Function):
+    """Stand-alone registry activation (unet.py:122-123 ``activation(conv(x))``; vit.py:155-161 Linear -> activation)."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.check(L.lib().rho_activation(x.data_ptr(), y.data_ptr(), dt(x), x.numel(), act, stream()), "activation")
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = cast(dy, x.dtype)
+        dx = torch.empty_like(x)
+        L.check(L.lib().rho_activation_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dt(x), x.numel(), ctx.act, stream()), "activation_bwd")
+        return dx, None
+
+
+def activation(x, act: int):
+    return x if act == L.ACT_NONE else ActivationFn.apply(x, act)
+
+
+class ConvTWeightFn(torch.autograd.Function):
+    """[A, B, *k] fp32 -> [B, A, *k] flipped along every kernel axis: the conv_nd weight of a stride-1 ConvTranspose
+    (unet.py:69-75); with k = () a plain transpose.  Backward is the same map with A and B swapped."""
+
+    @staticmethod
+    def forward(ctx, w):
+        _need_cuda(w)
+        w = w.detach().float().contiguous()
+        A, B = w.shape[0], w.shape[1]
+        taps = w.numel() // (A * B)
+        out = torch.empty((B, A, *w.shape[2:]), dtype=torch.float32, device=w.device)
+        L.check(L.lib().rho_convt_weight(w.data_ptr(), out.data_ptr(), A, B, taps, stream()), "convt_weight")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.float().contiguous()
+        B, A = g.shape[0], g.shape[1]
+        taps = g.numel() // (A * B)
+        out = torch.empty((A, B, *g.shape[2:]), dtype=torch.float32, device=g.device)
+        L.check(L.lib().rho_convt_weight(g.data_ptr(), out.data_ptr(), B, A, taps, stream()), "convt_weight_bwd")
+        return out
+
+
+class _NoCache:
+    """Throw-away owner for weights that are recomputed every call (no packed-weight cache)."""
+
+
+def conv_uncached(x, x2, weight, bias, residual, spec, dtype, engine=L.CONV_AUTO, y_f32=False):
+    """:func:`conv` for a weight that is itself the output of a kernel (transposed / flipped ConvTranspose weights): the packed copy
+    is rebuilt every call, because a recycled device address would alias a stale cache entry."""
+    return conv(_NoCache(), x, x2, weight, bias, residual, spec, dtype, engine, y_f32)
+
+
+def linear_tokens(owner, x, weight, bias=None, residual=None, dtype=None, engine=L.CONV_AUTO, y_f32=False, cached=True):
+    """nn.Linear over channels-last tokens [..., I] -> [..., O] on the conv_nd engines (a 1x1 conv; tcgen05 in bf16), bias and
+    an optional residual fused in the epilogue.  ``weight`` is the [O, I] Linear weight."""
+    spec = ConvSpec.make(1, 1)
+    lead = x.shape[:-1]
+    x3 = x.reshape(x.shape[0], -1, x.shape[-1])
+    r3 = residual.reshape(residual.shape[0], -1, residual.shape[-1]) if residual is not None else None
+    dtype = dtype or x.dtype
+    y = conv(owner if cached else _NoCache(), x3, None, weight, bias, r3, spec, dtype, engine, y_f32)
+    return y.reshape(*lead, weight.shape[0])
+
+
+class PatchifyFn(torch.autograd.Function):
+    """(N, C, *spatial) field <-> (N, T, C prod(patch)) tokens (rho_patchify); the inverse direction adds a per-channel bias."""
+
+    @staticmethod
+    def forward(ctx, src, patch, inverse, field_shape, out_dtype, bias):
+        _need_cuda(src, bias)
+        src = src.contiguous()
+        N, Cc, *sp = field_shape
+        D, H, W = _pad3(sp)
+        pd, ph, pw = _pad3(patch)
+        T = (D // pd) * (H // ph) * (W // pw)
+        F = Cc * pd * ph * pw
+        b = bias.detach().float().contiguous() if bias is not None else None
+        if inverse:
+            assert tuple(src.shape) == (N, T, F), (tuple(src.shape), (N, T, F))
+            dst = torch.empty(tuple(field_shape), dtype=out_dtype, device=src.device)
+        else:
+            assert tuple(src.shape) == tuple(field_shape)
+            dst = torch.empty((N, T, F), dtype=out_dtype, device=src.device)
+        L.check(L.lib().rho_patchify(src.data_ptr(), dt(src), dst.data_ptr(), dt(dst), ptr(b), N, Cc, D, H, W, pd, ph, pw, int(inverse),
+                                     stream()), "patchify")
+        ctx.args = (tuple(patch), bool(inverse), tuple(field_shape), src.dtype, bias is not None)
+        return dst
+
+    @staticmethod
+    def backward(ctx, g):
+        patch, inverse, field_shape, in_dtype, has_bias = ctx.args
+        g = g.contiguous()
+        dsrc = PatchifyFn.apply(g, patch, not inverse, field_shape, in_dtype, None) if ctx.needs_input_grad[0] else None
+        dbias = None
+        if has_bias and ctx.needs_input_grad[5]:
+            N, Cc, *sp = field_shape
+            S = 1
+            for s in sp:
+                S *= s
+            # dbias[c] = sum over samples and positions of g[n, c, :]: row sums of [N C, S], then the sum over n
+            rows = torch.empty((N * Cc,), dtype=torch.float32, device=g.device)
+            L.check(L.lib().rho_bias_expand(cast(g, torch.float32).data_ptr(), rows.data_ptr(), N * Cc, S, 1, stream()), "bias_rowsum")
+            dbias = torch.empty((Cc,), dtype=torch.float32, device=g.device)
+            L.check(L.lib().rho_colsum(rows.data_ptr(), F32, Cc, 1, N, Cc, dbias.data_ptr(), stream()), "colsum")
+        return dsrc, None, None, None, None, dbias
+
+
+def patchify(x, patch, out_dtype):
+    return PatchifyFn.apply(x, tuple(patch), False, tuple(x.shape), out_dtype, None)
+
+
+def unpatchify(tokens, patch, field_shape, out_dtype, bias=None):
+    return PatchifyFn.apply(tokens, tuple(patch), True, tuple(field_shape), out_dtype, bias)
+
+
+class AddBcastFn(torch.autograd.Function):
+    """x [N, ...] + add [...] broadcast over the leading dim (positional embedding, vit.py:349-352)."""
+
+    @staticmethod
+    def forward(ctx, x, add):
+        _need_cuda(x, add)
+        x = x.contiguous()
+        a = add.float().contiguous()
+        inner = a.numel()
+        assert x.numel() % inner == 0 and tuple(x.shape[1:]) == tuple(a.shape)
+        y = torch.empty_like(x)
+        L.check(L.lib().rho_add_bcast(x.data_ptr(), dt(x), a.data_ptr(), y.data_ptr(), x.numel() // inner, inner, stream()), "add_bcast")
+        ctx.add_shape = tuple(a.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dadd = None
+        if ctx.needs_input_grad[1]:
+            inner = 1
+            for s in ctx.add_shape:
+                inner *= s
+            dadd = torch.empty(ctx.add_shape, dtype=torch.float32, device=g.device)
+            L.check(L.lib().rho_colsum(g.data_ptr(), dt(g), inner, 1, g.numel() // inner, inner, dadd.data_ptr(), stream()), "colsum")
+        return g, dadd
+
+
+def add_bcast(x, add):
+    return AddBcastFn.apply(x, add)
+
+
+def _ln_params(x, pre_add, gamma, beta, y, stats, eps) -> L.LayerNormParams:
+    p = L.LayerNormParams()
+    Cc = x.shape[-1]
+    p.rows, p.C = x.numel() // Cc, Cc
+    p.rows_per_sample = (x.numel() // Cc) // x.shape[0]
+    p.in_dtype, p.out_dtype, p.eps = dt(x), (dt(y) if y is not None else dt(x)), eps
+    p.x, p.pre_add, p.gamma, p.beta, p.y, p.stats = ptr(x), ptr(pre_add), ptr(gamma), ptr(beta), ptr(y), ptr(stats)
+    return p
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(C)(x + pre_add[:, None, :]) over channels-last tokens [N, T, C] (vit.py:179-186)."""
+
+    @staticmethod
+    def forward(ctx, x, pre_add, gamma, beta, eps):
+        _need_cuda(x, pre_add, gamma, beta)
+        x = x.contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        pa = pre_add.float().contiguous() if pre_add is not None else None
+        y = torch.empty_like(x)
+        stats = torch.empty((x.numel() // x.shape[-1], 2), dtype=torch.float32, device=x.device)
+        L.check(L.lib().rho_layernorm_fwd(C.byref(_ln_params(x, pa, g32, b32, y, stats, eps)), stream()), "layernorm_fwd")
+        ctx.save_for_backward(x, pa, g32, stats)
+        ctx.eps = eps
+        ctx.params = (gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pa, g32, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = cast(dy, x.dtype)
+        p = _ln_params(x, pa, g32, None, None, stats, ctx.eps)
+        dx = torch.empty_like(x)
+        need_p = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        sg, sb = grad_sink(ctx.params[0], need_p), grad_sink(ctx.params[1], need_p)
+        dgamma = (sg.view if sg else torch.empty_like(g32)) if need_p else None
+        dbeta = (sb.view if sb else torch.empty_like(g32)) if need_p else None
+        dpre = torch.empty_like(pa) if (pa is not None and ctx.needs_input_grad[1]) else None
+        ws = workspace(L.lib().rho_layernorm_bwd_workspace_bytes(C.byref(p)), x.device)
+        L.check(L.lib().rho_layernorm_bwd(C.byref(p), dy.data_ptr(), dx.data_ptr(), ptr(dgamma), ptr(dbeta), ptr(dpre), ws.data_ptr(), ws.numel(),
+                                          stream()), "layernorm_bwd")
+        if sg:
+            sg.done(); dgamma = None
+        if sb:
+            sb.done(); dbeta = None
+        return dx, dpre, dgamma, dbeta, None
+
+
+def layernorm(x, gamma, beta, eps=1e-5, pre_add=None):
+    return LayerNormFn.apply(x, pre_add, gamma, beta, eps)
+
+
+class BiasExpandFn(torch.autograd.Function):
+    """bias [C] -> [C reps] (each entry repeated): the bias of a kernel = stride ConvTranspose seen by its Linear (vit.py:297-303)."""
+
+    @staticmethod
+    def forward(ctx, b, reps):
+        _need_cuda(b)
+        b = b.detach().float().contiguous()
+        out = torch.empty((b.numel() * reps,), dtype=torch.float32, device=b.device)
+        L.check(L.lib().rho_bias_expand(b.data_ptr(), out.data_ptr(), b.numel(), reps, 0, stream()), "bias_expand")
+        ctx.reps = reps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.float().contiguous()
+        out = torch.empty((g.numel() // ctx.reps,), dtype=torch.float32, device=g.device)
+        L.check(L.lib().rho_bias_expand(g.data_ptr(), out.data_ptr(), out.numel(), ctx.reps, 1, stream()), "bias_expand_bwd")
+        return out, None

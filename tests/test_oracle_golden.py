@@ -156,3 +156,22 @@ def test_gaussian_pipeline_restatement():
     rv = g["reverse"]
     out = O.g_reverse_process(tab, den, rv["x_init"], cond=y)
     assert (out - rv["denoised"]).abs().max() < 5e-5
+
+
+def test_backbone_oracles_are_pinned_to_the_reference():
+    """v1 UNet / VisionTransformer restatements against outputs of the unmodified reference modules; the 3-D v1 case
+    is one the reference itself cannot run (`time_pe[..., None, None]`, unet.py:130-132) and the fixture records its error."""
+    from oracle.cases import BACKBONE_CASES
+    g = load_golden("backbones.pt")
+    for case, spec in BACKBONE_CASES.items():
+        e = g[case]
+        sd = synth_state_dict(e["manifest"], seed=777)
+        x = synth_input(case + ".x", spec["x_shape"])
+        t = torch.tensor(spec["t"], dtype=torch.long)
+        fn = O.unet1_forward if spec["model"] == "UNet" else O.vit_forward
+        y = fn(sd, spec["kwargs"], x, t)
+        if "out" in e:
+            assert float((y - e["out"]).abs().max() / e["out"].abs().max()) < 2e-6, case
+        else:
+            assert case == "unet1_3d" and "must match the size" in e["reference_error"]
+            assert y.shape == x.shape and torch.isfinite(y).all()
