@@ -115,3 +115,21 @@ BACKBONE_CASES = {
                                                           dropout=0.0, num_heads=2),
                    x_shape=(3, 2, 128), t=[1, 500, 999]),
 }
+
+
+def spectroscopy_records():
+    """Three synthetic SpectroscopyDataset records (spectroscopy.py:103-109: group str(index) -> 'transitions' [2, n] = centre
+    frequencies / log10 intensities, plus the parameters the spectrum was generated from), as '<index>/<name>' arrays."""
+    import numpy as np
+    rng = np.random.RandomState(20240607)
+    rec = {}
+    for i, n in enumerate((40, 17, 1)):
+        centers = rng.uniform(500.0, 34000.0, size=n)            # some fall outside the default 1000 .. 32000 grid
+        logint = rng.uniform(-12.0, -1.0, size=n)                # some beyond the [-10, -2] clip
+        if n == 1:
+            centers[0] = 16000.0
+        rec[f"{i}/transitions"] = np.stack([centers, logint]).astype(np.float64)
+        rec[f"{i}/A"] = np.array([3000.0 + 10 * i])
+        rec[f"{i}/B"] = np.array([2000.0 + 5 * i])
+        rec[f"{i}/C"] = np.array([1500.0 + i])
+    return rec

@@ -413,6 +413,53 @@ def gen_backbones(ref):
     torch.save(out, os.path.join(OUT, "backbones.pt"))
 
 
+def gen_spectroscopy(ref):
+    """SpectroscopyDataset.__getitem__ of the unmodified reference (spectroscopy.py:103-133) on three synthetic records.  The
+    reference opens the file with h5py (absent here): a 15-line stand-in `h5py.File` serves the same records from an .npz archive;
+    `random.seed` pins the per-item line width."""
+    import importlib
+    import random
+    import tempfile
+    import types
+    import numpy as np
+    from oracle.cases import spectroscopy_records
+
+    class _File:
+        def __init__(self, path, mode="r"):
+            z = np.load(path)
+            self._g = {}
+            for k in z.files:
+                g, _, name = k.partition("/")
+                self._g.setdefault(g, {})[name] = z[k]
+
+        def __len__(self):
+            return len(self._g)
+
+        def __getitem__(self, g):
+            return self._g[g]
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    sys.modules.setdefault("h5py", types.SimpleNamespace(File=_File))
+    mod = importlib.import_module("rho_diffusion.data.spectroscopy")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "records.npz")
+        np.savez(path, **spectroscopy_records())
+        ds = mod.SpectroscopyDataset(path, grid_size=4096)
+        for i in range(3):
+            random.seed(1000 + i)
+            item = ds[i]
+            out[i] = {k: v.clone() for k, v in item.items()}
+        out["frequency_grid"] = torch.from_numpy(ds.frequency_grid.copy())
+    torch.save(out, os.path.join(OUT, "spectroscopy.pt"))
+    print("spectroscopy fixture:", {k: tuple(v.shape) for k, v in out[0].items()}, float(out[0]["spectrum"].sum()))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -429,6 +476,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "deep_galaxy":
         gen_deep_galaxy(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "spectroscopy":
+        gen_spectroscopy(ref)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "backbones":
         gen_backbones(ref)
         return
@@ -443,6 +493,7 @@ def main():
     gen_sph_harm(ref)
     gen_deep_galaxy(ref)
     gen_backbones(ref)
+    gen_spectroscopy(ref)
     gen_loss_curve(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

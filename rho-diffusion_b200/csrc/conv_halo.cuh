@@ -301,23 +301,42 @@ static HaloPlan halo_plan(int N, int D, int H, int W, int C1, int C2, int Cout, 
   const bool k1 = kd == 1 && kh == 1 && kw == 1;
   if (!k1 && (kh != 3 || kw != 3 || (kd != 1 && kd != 3))) return pl;
   const int bk = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : ((C1 % 32 == 0 && C2 % 32 == 0) ? 32 : 0);
-  if (bk == 0 || (Cout != 32 && Cout != 64 && Cout != 128) || (Cout == 128 && bk != 64)) return pl;
+  // RHO_HALO_WIDE_K1=1 (opt-in): wide 1x1 convs (the attention blocks' qkv / proj_out: 256 -> 768 / 256 over T = 16384 positions)
+  // stream through this pipeline in 128-channel output blocks, 1-D sequences re-factored into rows of <= 255 positions.  Parity-
+  // green (tests/test_gpu_switches.py) but measured SLOWER than the per-tap kernel (256 -> 768: 170 vs 146 us, 1.6 vs 1.8 TB/s:
+  // every output block reloads the A slab, 128 B/clk/SM of L2 -> shared-memory traffic) and the power-capped sampling step is
+  // unchanged (48.18 ms both ways, profiles/r02_wide_k1_streaming.txt), so it stays off; the A-stationary loop order is the fix.
+  static int wide_k1 = -1;
+  if (wide_k1 < 0) { const char* e = getenv("RHO_HALO_WIDE_K1"); wide_k1 = (e && e[0] == '1') ? 1 : 0; }
+  const int n_blocks = (k1 && wide_k1 && Cout > 128 && Cout % 128 == 0 && Cout <= 4096) ? Cout / 128 : 1;
+  const int bn = n_blocks > 1 ? 128 : Cout;
+  if (bk == 0 || (bn != 32 && bn != 64 && bn != 128) || (bn == 128 && bk != 64)) return pl;
+  if (k1 && wide_k1 && (W < 16 || W > 255 || (long long)H * (W + 1) < 256)) {
+    // a 1x1 conv is position-independent: any factorisation of the D H W positions of a sample into rows of W' columns serves
+    // (1-D sequences arrive as D = H = 1, W = T)
+    const long long S = (long long)D * H * W;
+    int wf = 0;
+    for (int c = 255; c >= 16 && !wf; --c)
+      if (S % c == 0 && (S / c) * (c + 1) >= 256 && S / c <= 2147483647LL) wf = c;
+    if (!wf) return pl;
+    D = 1; H = (int)(S / wf); W = wf;
+  }
   if (W < 16 || W > 255 || (long long)H * (W + 1) < 256) return pl;
-  pl.bn = Cout;
+  pl.bn = bn;
   pl.bk = bk;
   HaloParams& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Wp = W + 1;
   p.C1 = C1; p.C2 = C2; p.Cin = C1 + C2; p.Cout = Cout;
   p.kd = kd; p.pd = kd / 2;
   p.k1 = k1 ? 1 : 0;
-  p.n_blocks = 1;
+  p.n_blocks = n_blocks;
   p.tiles_per_plane = (int)ceil_div((long long)H * p.Wp, 128);
   // static shared memory: statistics scratch (8 warps x BLOCK_N channels x 2 floats), bias, barriers; 1 KB alignment slack, 1 KB reserve
   const size_t budget = 227 * 1024 - ((size_t)64 * pl.bn + 1536) - 1024 - 1024;
   const size_t b_bytes = (size_t)pl.bn * (size_t)(2 * bk);
   // tiles per work item: as many as TMEM (2 x MT x BLOCK_N <= 512 columns) and two slab stages in shared memory allow
   bool fits = false;
-  for (int mt = 256 / Cout; mt >= 1 && !fits; mt >>= 1) {
+  for (int mt = 256 / pl.bn; mt >= 1 && !fits; mt >>= 1) {
     pl.mt = mt;
     p.groups_per_plane = (int)ceil_div(p.tiles_per_plane, mt);
     int R = 0;

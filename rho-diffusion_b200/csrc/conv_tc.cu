@@ -814,7 +814,7 @@ int conv_fwd_tc_stats_rows(const ConvGeom& g, const rho_conv_params* p) {
   if (!fuse) return 0;
   if (is_plain(g)) {
     const HaloPlan hp = halo_plan(g.N, g.D, g.H, g.W, g.C1, g.C2, g.Cout, g.kd, g.kh, g.kw);
-    if (hp.ok) return g.D * hp.p.groups_per_plane;
+    if (hp.ok) return hp.p.D * hp.p.groups_per_plane;
   }
   if (!tma_store_enabled() || pick_block_n(g.Cout) < 64 || g.Cout % 64 != 0) return 0;
   TcParams tp;

@@ -80,7 +80,58 @@ def test_host_philox_matches_the_known_answer():
 
 
 # ---- device generators ----------------------------------------------------------------------------------------------
+def _spectroscopy_dataset(tmp_path, **kw):
+    from oracle.cases import spectroscopy_records
+    from rho_diffusion.data import SpectroscopyDataset
+    path = os.path.join(str(tmp_path), "records.npz")
+    np.savez(path, **spectroscopy_records())
+    return SpectroscopyDataset(path, **kw)
+
+
+def test_spectroscopy_dataset_matches_the_reference_items(tmp_path):
+    """SpectroscopyDataset.__getitem__ / simulate_lineprofile (spectroscopy.py:103-189) against items of the UNMODIFIED reference
+    on the same records and the same `random.gauss` line widths (tests/golden/spectroscopy.pt): bit-exact."""
+    import random
+    from conftest import load_golden
+    from rho_diffusion.registry import registry
+    g = load_golden("spectroscopy.pt")
+    ds = _spectroscopy_dataset(tmp_path, grid_size=4096)
+    assert registry.get("datasets", "SpectroscopyDataset") is type(ds) and len(ds) == 3
+    assert torch.equal(torch.from_numpy(ds.frequency_grid), g["frequency_grid"])
+    for i in range(3):
+        random.seed(1000 + i)
+        item = ds[i]
+        assert set(item) == set(g[i])
+        for k, v in g[i].items():
+            assert item[k].dtype == torch.float32 and torch.equal(item[k], v), (i, k)
+        assert item["spectrum"].shape == (1, 4096) and float(item["spectrum"].max()) == 1.0
+    with pytest.raises(AssertionError):
+        type(ds)(os.path.join(str(tmp_path), "missing.npz"))
+
+
 gpu = pytest.mark.gpu
+
+
+@gpu
+def test_device_line_profiles_match_the_host_restatement(tmp_path):
+    """rho_lineprofile (one ragged-batch kernel) against the host path on the same records and widths, at the fixture's grid and at
+    the reference's default 50 000-channel grid."""
+    import random
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    for grid_size in (4096, 50_000):
+        ds = _spectroscopy_dataset(tmp_path, grid_size=grid_size)
+        random.seed(7)
+        host = [ds[i] for i in (0, 1, 2, 1)]
+        random.seed(7)
+        batch = ds.device_batch(4, "cuda", indices=[0, 1, 2, 1])
+        assert batch["spectrum"].shape == (4, 1, grid_size) and batch["spectrum"].dtype == torch.float32
+        for j, item in enumerate(host):
+            ref, got = item["spectrum"], batch["spectrum"][j].cpu()
+            assert float((got - ref).abs().max()) < 2e-6, (grid_size, j, float((got - ref).abs().max()))
+            assert torch.equal(batch["max_int"][j].cpu(), item["max_int"])
+            for k in ("A", "B", "C"):
+                assert torch.equal(batch[k][j].cpu(), item[k])
 
 
 @gpu

@@ -231,3 +231,40 @@ def test_add_bcast_and_bias_expand():
     ge = synth_input("be.g", (24,)).to(DEV)
     e.backward(ge)
     assert torch.allclose(b.grad, ge.reshape(6, 4).sum(1), atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["unet1_2d", "vit_2d"])
+def test_ddpm_pipeline_trains_and_samples_with_the_other_backbones(case):
+    """DDPM(<registry name>) unconditional (ddpm.py:231-288, 132-229): the training-step loss equals the oracle's on shared (t, noise),
+    and a T = 50 ancestral trajectory with shared noise -- eager and through the replayed CUDA graph -- equals the oracle's, with the
+    final field's mean / variance equal to 1e-4."""
+    from rho_diffusion.b200 import set_compute_dtype
+    from rho_diffusion.diffusion import DDPM, LinearSchedule
+    spec = BACKBONE_CASES[case]
+    g = load_golden("backbones.pt")[case]
+    T = 50          # LinearSchedule scales beta by 1000 / T (schedule.py:141-168): T <= 20 gives beta > 1
+    ddpm = DDPM(spec["model"], dict(spec["kwargs"]), LinearSchedule(T, 1e-3, 0.02), "MSELoss", timesteps=T, optimizer="AdamW", opt_kwargs={"lr": 1e-4})
+    sd = synth_state_dict(g["manifest"], seed=777)
+    ddpm.backbone.load_state_dict(sd, strict=True)
+    ddpm = set_compute_dtype(ddpm.to(DEV), torch.float32)
+    fn = O.unet1_forward if spec["model"] == "UNet" else O.vit_forward
+    den = lambda x, tt, c: fn(sd, spec["kwargs"], x, tt)  # noqa: E731
+    sched = O.linear_schedule(T, 1e-3, 0.02)
+    x0 = synth_input(case + ".x0", spec["x_shape"], kind="rand") * 2 - 1
+    noise = synth_input(case + ".noise", spec["x_shape"])
+    t = torch.tensor(spec["t"]) % T
+    ddpm.train()
+    loss = ddpm.training_step([x0.to(DEV), None], t=t, noise=noise.to(DEV))
+    loss_ref = O.mse_loss(den(O.q_sample(sched, x0, t, noise), t, None), noise)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=2e-5)
+    ddpm.eval()
+    x_init = synth_input(case + ".x_init", spec["x_shape"])
+    zs = {s: synth_input(f"{case}.z{s}", spec["x_shape"]) for s in range(T)}
+    with torch.no_grad():
+        ref = O.reverse_process(sched, den, x_init, zs)
+    for graph in (False, True):
+        res = ddpm.reverse_process(torch.zeros(spec["x_shape"], device=DEV), conditions=None, x_init=x_init.to(DEV), noises=zs, use_cuda_graph=graph)
+        got = res["denoised"].cpu()
+        assert float((got - ref).abs().max()) < 1e-3, ("graph" if graph else "eager")     # 50 chained fp32 evals + clamps
+        a, b = got.double().flatten(), ref.double().flatten()
+        assert abs(float(a.mean() - b.mean())) < 1e-4 and abs(float(a.var() - b.var())) < 1e-4

@@ -178,6 +178,12 @@ CONV_CASES = [
     (2, 1, 32, 0, 64, (64, 64), 1, 1, 1, False),
     (3, 1, 64, 32, 32, (2, 24, 24), 1, 1, 1, False),
     (3, 2, 128, 64, 128, (2, 17, 20), 1, 1, 1, True),          # 1x1x1 on 64-channel blocks through the halo kernel's streaming mode, residual
+    # wide 1x1 convs in the streaming mode (128-channel output blocks, 1-D sequences re-factored into rows of <= 255 positions):
+    # the attention blocks' qkv / proj_out at real widths; their dgrad streams 768 -> 256
+    (1, 2, 256, 0, 768, (1024,), 1, 1, 1, False),
+    (1, 2, 256, 0, 256, (640,), 1, 1, 1, True),
+    (3, 1, 128, 128, 256, (2, 16, 24), 1, 1, 1, False),        # concat input, 3-D, two output blocks
+    (1, 1, 512, 0, 1536, (333,), 1, 1, 1, False),              # T = 333 = 3 x 111 rows, 12 output blocks, 8 K blocks
 ]
 
 

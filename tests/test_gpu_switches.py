@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # conv cases: per-tap tcgen05 (14, 16), strided / upsample (19, 20, 21), halo 64 / 128 / concat (30, 31, 33), config-D pairs (36, 44),
-# 32-channel halo (45, 46), 1x1 on 32-channel blocks (50, 51)
-CONV_IDS = (14, 16, 19, 20, 21, 30, 31, 33, 36, 44, 45, 46, 50, 51)
+# 32-channel halo (45, 46), 1x1 on 32-channel blocks (50, 51), wide 1x1 convs of the attention blocks (55, 56, 57, 58)
+CONV_IDS = (14, 16, 19, 20, 21, 30, 31, 33, 36, 44, 45, 46, 50, 51) + (55, 56, 57, 58)
 SELECT = "(test_conv_fwd_bwd and (" + " or ".join(f"[{i}-dtype1]" for i in CONV_IDS) + ")) " \
          "or test_conv_epilogue_groupnorm_statistics or (test_attention_fwd_bwd and dtype1) or test_conv_engines_agree_on_random_shapes"
 
@@ -30,6 +30,7 @@ VARIANTS = [
     {"RHO_ATTN_V2_MIN_T": "1", "RHO_ATTN_POLY": "0"},   # ... with every exponential on the MUFU
     {"RHO_ATTN_BWD_V2": "0"},           # first-generation attention backward (32-column tiles, P / dS through shared memory)
     {"RHO_ATTN_BWD_V2_MIN_T": "1"},     # second-generation backward (64-column tiles, P / dS in TMEM) forced for every head-dim-64 shape
+    {"RHO_HALO_WIDE_K1": "1"},          # wide 1x1 convs (attention qkv / proj_out) through the halo kernel's streaming mode
     {"RHO_CONV_CLUSTER": "1"},
     {"RHO_FP32_SPLIT": "1"},            # fp32 inference convs as six bf16 tensor-core products with flushed fp32 accumulation          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
 ]
