@@ -334,37 +334,12 @@ def run_b200(args):
         # ---- end-to-end leg: host buffers in, host buffers out, EVERY step.  The PCIe copies run on a second stream through
         #      double-buffered device staging tensors, so step k's upload / step k-1's download overlap step k's kernels; the
         #      compute stream only does two device-to-device copies around the graph replay.
-        copy_stream = torch.cuda.Stream(device=device)
-        stage_in = [torch.empty_like(sampler.x) for _ in range(2)]
-        stage_cond = [torch.empty_like(sampler.cond) for _ in range(2)]
-        stage_out = [torch.empty_like(sampler.x) for _ in range(2)]
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_done = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
-        ev_out_free = [torch.cuda.Event() for _ in range(2)]
-        e2e_k = [0]
+        #      (the staging pipeline is the product's: rho_diffusion.b200.sampler.HostStagedStepper)
+        from rho_diffusion.b200.sampler import HostStagedStepper
+        stepper = HostStagedStepper(sampler)
 
         def e2e_step():
-            k = e2e_k[0] & 1
-            e2e_k[0] += 1
-            main = torch.cuda.current_stream(device)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_free[k])               # the compute stream has consumed this staging slot
-                stage_in[k].copy_(x_pin, non_blocking=True)      # host -> device (pinned)
-                stage_cond[k].copy_(y_pin, non_blocking=True)
-                ev_in[k].record(copy_stream)
-            main.wait_event(ev_in[k])
-            sampler.x.copy_(stage_in[k], non_blocking=True)
-            sampler.cond.copy_(stage_cond[k], non_blocking=True)
-            ev_free[k].record(main)
-            sampler.graph.replay()
-            main.wait_event(ev_out_free[k])                  # the download of step k-2 has left this slot
-            stage_out[k].copy_(sampler.x, non_blocking=True)
-            ev_done[k].record(main)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_done[k])
-                x_out_pin.copy_(stage_out[k], non_blocking=True)  # device -> host (pinned) of this step's result
-                ev_out_free[k].record(copy_stream)
+            stepper.step(x_pin, y_pin, x_out_pin)
 
         sampler.tt.fill_(T_STEPS // 2)
         sampler.t_scalar.fill_(T_STEPS // 2)
@@ -375,11 +350,11 @@ def run_b200(args):
         f0.record()
         for _ in range(args.steps):
             e2e_step()
-        torch.cuda.current_stream(device).wait_stream(copy_stream)     # the last download is inside the timed region
+        stepper.finish()                                               # the last download is inside the timed region
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
-        del stage_in, stage_cond, stage_out
+        del stepper
 
         # ---- per-kernel roofline pass: one eager eval with CUDA events around every conv / GN / attention launch
         tt = torch.full((B,), 500, dtype=torch.int64, device=device)

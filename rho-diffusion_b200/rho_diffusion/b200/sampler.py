@@ -164,3 +164,61 @@ class X0Sampler:
                 buffer[:, idx].copy_(self.x)
                 idx += 1
         return {"buffer": buffer, "denoised": self.x.clone()}
+
+
+class HostStagedStepper:
+    """One sampler step per call with HOST buffers on both sides (the serving form of the loop: x_t and the labels arrive from the
+    host, x_{t-1} goes back to the host every step).  ``step(x_pinned, cond_pinned, out_pinned)`` uploads the inputs and downloads
+    the result on a second stream through double-buffered device staging tensors, so step k's upload and step k-1's download
+    overlap step k's kernels; the compute stream only does two device-to-device copies around the graph replay.  Call
+    ``finish()`` (or synchronise) before reading the last ``out_pinned``.  ``sampler`` is an :class:`AncestralSampler` or an
+    :class:`X0Sampler` whose step has been captured (``use_cuda_graph=True``) or not (eager steps)."""
+
+    def __init__(self, sampler):
+        self.sampler = sampler
+        dev = sampler.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        with torch.inference_mode(False):
+            self.stage_in = [torch.empty_like(sampler.x) for _ in range(2)]
+            self.stage_cond = [torch.empty_like(sampler.cond) for _ in range(2)] if sampler.cond is not None else None
+            self.stage_out = [torch.empty_like(sampler.x) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out_free = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        self.h2d_bytes = sampler.x.numel() * 4 + (sampler.cond.numel() * sampler.cond.element_size() if sampler.cond is not None else 0)
+        self.d2h_bytes = sampler.x.numel() * 4
+
+    def step(self, x_host, cond_host=None, out_host=None):
+        s = self.sampler
+        k = self.k & 1
+        self.k += 1
+        main = torch.cuda.current_stream(s.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_free[k])               # the compute stream has consumed this staging slot
+            self.stage_in[k].copy_(x_host, non_blocking=True)         # host -> device (pinned)
+            if self.stage_cond is not None:
+                self.stage_cond[k].copy_(cond_host, non_blocking=True)
+            self.ev_in[k].record(self.copy_stream)
+        main.wait_event(self.ev_in[k])
+        s.x.copy_(self.stage_in[k], non_blocking=True)
+        if self.stage_cond is not None:
+            s.cond.copy_(self.stage_cond[k], non_blocking=True)
+        self.ev_free[k].record(main)
+        if s.use_graph:
+            s.graph.replay()
+        else:
+            s._step()
+        if out_host is not None:
+            main.wait_event(self.ev_out_free[k])                       # the download of step k-2 has left this slot
+            self.stage_out[k].copy_(s.x, non_blocking=True)
+            self.ev_done[k].record(main)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.ev_done[k])
+                out_host.copy_(self.stage_out[k], non_blocking=True)   # device -> host (pinned) of this step's result
+                self.ev_out_free[k].record(self.copy_stream)
+
+    def finish(self):
+        """Makes the current stream wait for the outstanding download."""
+        torch.cuda.current_stream(self.sampler.device).wait_stream(self.copy_stream)
