@@ -37,6 +37,7 @@ struct HaloParams {
   int a_stage_bytes;          // R * Wp * 128 rounded up to 1024
   int SA, SB;                 // ring depths
   int out_split;              // > 0: channels >= out_split go to y2 (dgrad of a concat input)
+  int lean;                   // MMA issue loop: 1 = one thread, descriptor low words advanced by adds (default); 0 = first version
   float* stat_part;           // optional fused GroupNorm statistics: one row of channel sums per work item (see rho_b200.h)
 };
 
@@ -125,8 +126,72 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
         }
       }
     }
+  } else if (warp == 1 && p.lean) {
+    // ===== MMA issuer, lean form =====
+    // ncu's warp-state samples of the first version put this warp in scalar code ~70 % of the time and almost never on a full MMA
+    // queue: ~100 SASS instructions per tap (descriptor assembly, tap -> shift division, elect / reconverge) made an MMA cost
+    // 85 - 98 clk to ISSUE while the tensor pipe needs 45 (N = 64) / 64 (N = 128) clk to execute it.  Here ONE thread runs the whole
+    // loop; the nine tap shifts are registers, a descriptor is {low word, constant high word} and its low word (the shared-memory
+    // address in 16-byte units, < 2^14 for any address below 256 KB) advances by adds.
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t RB16 = ROW_BYTES / 16;                     // descriptor address units per operand row
+      constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((ROW_BYTES == 128 ? 2u : (ROW_BYTES == 64 ? 4u : 6u)) << 29);
+      const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_stage_lo = (uint32_t)p.a_stage_bytes >> 4;
+      int tap_off[9];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) tap_off[t9] = p.k1 ? 0 : ((t9 / 3 - 1) * p.Wp + (t9 % 3 - 1)) * (int)RB16;
+      int sa = 0, sb = 0, ab = 0;
+      uint32_t pha = 0, phb = 0, phacc = 0;
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int nb, q0, mt_here, d, n, h_lo;
+        decode(item, nb, q0, mt_here, d, n, h_lo);
+        mbar_wait(&acc_empty[ab], phacc ^ 1);       // the epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * MT * BLOCK_N);
+        const uint32_t item_off = (uint32_t)(q0 - h_lo * p.Wp) * RB16;
+        uint32_t acc = 0;                           // accumulate flag of each tile's k = 0 MMA: 0 on the first tap of the item only
+        auto tap = [&](uint32_t a_t) {
+          mbar_wait(&b_full[sb], phb);
+          tc_fence_after();
+          const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + (uint32_t)sb * (uint32_t)(B_BYTES >> 4));
+          const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)a_t;
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            if (i < mt_here) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                umma_f16(tacc + (uint32_t)(i * BLOCK_N), ad + (uint64_t)((uint32_t)(i * 128) * RB16 + (uint32_t)(2 * k)), bd + (uint64_t)(2 * k), idesc,
+                         k == 0 ? acc : 1u);
+            }
+          }
+          umma_commit(&b_empty[sb]);
+          acc = 1;
+          if (++sb == p.SB) { sb = 0; phb ^= 1; }
+        };
+        for (int kb = 0; kb < KB; ++kb) {
+          for (int dd = 0; dd < p.kd; ++dd) {
+            mbar_wait(&a_full[sa], pha);
+            const uint32_t a_base = a_lo0 + (uint32_t)sa * a_stage_lo + item_off;
+            if (p.k1) {
+              tap(a_base);
+            } else {
+#pragma unroll
+              for (int t9 = 0; t9 < 9; ++t9) tap(a_base + (uint32_t)tap_off[t9]);
+            }
+            umma_commit(&a_empty[sa]);
+            if (++sa == p.SA) { sa = 0; pha ^= 1; }
+          }
+        }
+        umma_commit(&acc_full[ab]);
+        if (++ab == 2) { ab = 0; phacc ^= 1; }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (first version, RHO_HALO_LEAN=0) =====
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int ntap = p.k1 ? 1 : 9;
     int sa = 0, sb = 0, ab = 0;
@@ -390,6 +455,9 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
   HaloParams& p = pl.p;
   p.out_split = out_split;
   p.stat_part = stat_part;
+  static int lean = -1;
+  if (lean < 0) { const char* e = getenv("RHO_HALO_LEAN"); lean = (e && e[0] == '0') ? 0 : 1; }
+  p.lean = lean;
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int box[5] = {pl.bk, p.Wp, p.R, 1, 1};
