@@ -30,6 +30,7 @@ struct AttnBwd2Params {
   int T, heads, C;
   int q_col, k_col, v_col, head_stride;
   float scale, scale_log2;
+  int lean;                 // MMA issue loop: 1 = one thread, compile-time ring / buffer indices, descriptors advanced by adds; 0 = first version
 };
 
 constexpr int B2_ROWS = 128;          // rows owned by a CTA
@@ -115,8 +116,75 @@ __global__ void __launch_bounds__(576, 1)
       }
       __syncwarp();
     }
+  } else if (warp == 1 && p.lean) {
+    // ===== MMA issuer, lean form =====
+    // The first version spent ~150 dependent uniform-datapath instructions per tile on 16 MMAs (descriptor assembly from rolled ring /
+    // buffer indices): ~85 clk to issue an MMA the tensor pipe executes in ~45, and the row owners never made the issuer wait -- the
+    // kernel was issue-bound (the same finding as in the halo conv kernel, profiles/r02_halo_lean_issue.txt).  Here one elected thread
+    // runs the whole loop, unrolled by 6 tiles so that the ring stage (i % 6) and the S / dP buffer (i % 3) are compile-time constants:
+    // every descriptor is a base register pair plus an immediate.  All operands share one descriptor high word (128-byte rows,
+    // SWIZZLE_128B, 1024-byte atoms); the low word is the address in 16-byte units (+ the leading-dimension field of the MN-major form).
+    if (elect_one()) {
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(B2_COLS >> 3) << 17) | ((uint32_t)(B2_ROWS >> 4) << 24);
+      const uint32_t idesc2 = idesc1 | (1u << 16);   // B MN-major
+      constexpr uint64_t HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
+      const uint64_t a1 = HI | (uint64_t)(((smem_u32(sA1) & 0x3FFFFu) >> 4) | (1u << 16));
+      const uint64_t a2 = HI | (uint64_t)(((smem_u32(sA2) & 0x3FFFFu) >> 4) | (1u << 16));
+      const uint64_t b1k = HI | (uint64_t)(((smem_u32(sB1) & 0x3FFFFu) >> 4) | (1u << 16));                              // K-major view of Q_i / K_j
+      const uint64_t b2k = HI | (uint64_t)(((smem_u32(sB2) & 0x3FFFFu) >> 4) | (1u << 16));
+      const uint64_t b1m = HI | (uint64_t)(((smem_u32(sB1) & 0x3FFFFu) >> 4) | ((uint32_t)(B2_COL_TILE >> 4) << 16));    // MN-major view
+      const uint64_t b2m = HI | (uint64_t)(((smem_u32(sB2) & 0x3FFFFu) >> 4) | ((uint32_t)(B2_COL_TILE >> 4) << 16));
+      constexpr uint32_t STAGE = B2_COL_TILE >> 4;          // descriptor units per ring stage
+      auto mma1 = [&](const int s, const int j) {           // S[j] = A1 B1^T, dP[j] = A2 B2^T of the tile in stage s
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + (uint32_t)(128 * j), a1 + (uint64_t)(2 * k), b1k + (uint64_t)(s * STAGE + 2 * k), idesc1, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + (uint32_t)(128 * j + 64), a2 + (uint64_t)(2 * k), b2k + (uint64_t)(s * STAGE + 2 * k), idesc1, k != 0);
+        umma_commit(&st_ready[j]);
+      };
+      mbar_wait(&a_full, 0);
+#pragma unroll
+      for (int u = 0; u < B2_NB; ++u) {
+        if (u < ni) {
+          mbar_wait(&b_full[u], 0);
+          tc_fence_after();
+          mma1(u, u);
+        }
+      }
+      uint32_t acc = 0;                                     // 0 only for the first accumulating MMAs of the kernel
+      for (int i0 = 0; i0 < ni; i0 += B2_ST) {
+        const uint32_t ph6 = (uint32_t)(i0 / B2_ST) & 1;    // ring parity of tiles i0 .. i0 + 5
+#pragma unroll
+        for (int u = 0; u < B2_ST; ++u) {
+          const int i = i0 + u;
+          if (i < ni) {
+            const int s = u, j = u % B2_NB, sn = (u + B2_NB) % B2_ST;
+            if (i + B2_NB < ni) mbar_wait(&b_full[sn], u + B2_NB < B2_ST ? ph6 : ph6 ^ 1);    // not on the critical loop
+            mbar_wait(&pds_ready[j], (uint32_t)(i / B2_NB) & 1);   // P / dS of tile i are in TMEM (in place of S / dP[j])
+            tc_fence_after();
+            // accumulating MMAs of tile i first: the in-order tensor pipe then guarantees they have read P / dS before S / dP of
+            // tile i + 3 overwrite the buffer.  K step k covers 16 columns = 8 TMEM columns at 32 (k / 2) + 8 (k % 2).
+            if (DKV) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(tmem + 448u, tmem + (uint32_t)(128 * j + 32 * (k >> 1) + 8 * (k & 1)), b2m + (uint64_t)(s * STAGE + k * 128), idesc2,
+                            k == 0 ? acc : 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(tmem + 384u, tmem + (uint32_t)(128 * j + 64 + 32 * (k >> 1) + 8 * (k & 1)), b1m + (uint64_t)(s * STAGE + k * 128), idesc2,
+                          k == 0 ? acc : 1u);
+            acc = 1;
+            umma_commit(&b_empty[s]);
+            if (i + B2_NB < ni) mma1(sn, j);
+            if (i == ni - 1) umma_commit(&acc_final);
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (first version, RHO_ATTN_BWD_LEAN=0) =====
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(B2_COLS >> 3) << 17) | ((uint32_t)(B2_ROWS >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B MN-major */ | ((uint32_t)(64 >> 3) << 17) |
                             ((uint32_t)(B2_ROWS >> 4) << 24);
@@ -290,6 +358,9 @@ int attention_bwd_tc2(const rho_attn_bwd_params* p, cudaStream_t st) {
   else { ap.q_col = 0; ap.k_col = ap.C; ap.v_col = 2 * ap.C; ap.head_stride = f.ch; }
   ap.scale = 1.0f / sqrtf((float)f.ch);
   ap.scale_log2 = ap.scale * 1.4426950408889634f;
+  static int lean = -1;
+  if (lean < 0) { const char* e = getenv("RHO_ATTN_BWD_LEAN"); lean = (e && e[0] == '0') ? 0 : 1; }
+  ap.lean = lean;
   constexpr size_t SMEM = (size_t)(2 * B2_ROW_TILE + 2 * B2_ST * B2_COL_TILE) + 1024;   // 129 KB
   auto kq = attn_bwd2_kernel<false>;
   auto kkv = attn_bwd2_kernel<true>;
