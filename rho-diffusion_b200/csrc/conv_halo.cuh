@@ -15,7 +15,7 @@
 // The kernel is persistent (one CTA per SM, static round-robin over work items) with double-buffered TMEM accumulators,
 // so the epilogue of item i overlaps the MMAs of item i + 1.  Rows with q % Wp == 0 are the padding column: computed and
 // dropped (1 / Wp waste).
-// Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per scheduler, alternating tiles of an
+// Warps: 0 = TMA producer of the activation slabs, 10 = TMA producer of the weight tiles, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per scheduler, alternating tiles of an
 // item; a single epilogue warp per scheduler ran at 0.36 IPC and bounded the 32-channel layers).
 // 1x1 convs (k1) run through the same pipeline as a streaming GEMM: one tap, shift 0, slabs without halo rows.  In the
 // per-tap kernel their short K loops leave every tile latency-bound (3.0 TB/s); here they reach 4.9 - 5.2 TB/s.
@@ -47,7 +47,7 @@ struct HaloMaps {
 };
 
 template <int BLOCK_N, int MT, int BLOCK_K>
-__global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
+__global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
                                                            const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                            bf16* __restrict__ y, bf16* __restrict__ y2) {
   constexpr int ROW_BYTES = BLOCK_K * 2;          // one position's channels of a K block: 128 B (64 ch) or 64 B (32 ch)
@@ -95,37 +95,51 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    const int ntap = p.k1 ? 1 : 9;
-    int sa = 0, sb = 0;
-    uint32_t pha = 0, phb = 0;
-    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int nb, q0, mt_here, d, n, h_lo;
-      decode(item, nb, q0, mt_here, d, n, h_lo);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int c = kb * BLOCK_K;
-        const int src = c >= p.C1 ? 1 : 0;
-        const int cc = src ? c - p.C1 : c;
-        for (int dd = 0; dd < p.kd; ++dd) {
-          mbar_wait(&a_empty[sa], pha ^ 1);
-          if (elect_one()) {
+    // ===== TMA producer of the activation slabs =====
+    // (its own warp: with one producer for both operands the next slab could only be requested once all nine weight tiles of the
+    // current one were in flight, i.e. at most SB taps ahead of the MMAs -- less than a slab's HBM latency)
+    if (elect_one()) {
+      int sa = 0;
+      uint32_t pha = 0;
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int nb, q0, mt_here, d, n, h_lo;
+        decode(item, nb, q0, mt_here, d, n, h_lo);
+        for (int kb = 0; kb < KB; ++kb) {
+          const int c = kb * BLOCK_K;
+          const int src = c >= p.C1 ? 1 : 0;
+          const int cc = src ? c - p.C1 : c;
+          for (int dd = 0; dd < p.kd; ++dd) {
+            mbar_wait(&a_empty[sa], pha ^ 1);
             mbar_expect_tx(&a_full[sa], (uint32_t)(p.R * p.Wp * ROW_BYTES));
             tma_load_5d(sA + (size_t)sa * p.a_stage_bytes, &maps.a[src], &a_full[sa], cc, -1, h_lo, d + dd - p.pd, n);
-          }
-          __syncwarp();
-          if (++sa == p.SA) { sa = 0; pha ^= 1; }
-          for (int t9 = 0; t9 < ntap; ++t9) {
-            mbar_wait(&b_empty[sb], phb ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&b_full[sb], B_BYTES);
-              tma_load_2d(sB + sb * B_BYTES, &maps.w, &b_full[sb], (dd * 9 + t9) * p.Cin + c, nb * BLOCK_N);
-            }
-            __syncwarp();
-            if (++sb == p.SB) { sb = 0; phb ^= 1; }
+            if (++sa == p.SA) { sa = 0; pha ^= 1; }
           }
         }
       }
     }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ===== TMA producer of the weight tiles =====
+    if (elect_one()) {
+      const int ntap = p.k1 ? 1 : 9;
+      int sb = 0;
+      uint32_t phb = 0;
+      for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int nb = (int)(item % p.n_blocks);
+        for (int kb = 0; kb < KB; ++kb) {
+          const int c = kb * BLOCK_K;
+          for (int dd = 0; dd < p.kd; ++dd) {
+            for (int t9 = 0; t9 < ntap; ++t9) {
+              mbar_wait(&b_empty[sb], phb ^ 1);
+              mbar_expect_tx(&b_full[sb], B_BYTES);
+              tma_load_2d(sB + sb * B_BYTES, &maps.w, &b_full[sb], (dd * 9 + t9) * p.Cin + c, nb * BLOCK_N);
+              if (++sb == p.SB) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1 && p.lean) {
     // ===== MMA issuer, lean form =====
     // ncu's warp-state samples of the first version put this warp in scalar code ~70 % of the time and almost never on a full MMA
@@ -443,7 +457,7 @@ static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bi
     attr_bytes = pl.smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(pl.p.total_items, (long long)sm_count());
-  kern<<<grid, 320, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
+  kern<<<grid, 352, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
   RHO_CHECK_LAUNCH("conv_halo_tcgen05");
   return RHO_OK;
 }
