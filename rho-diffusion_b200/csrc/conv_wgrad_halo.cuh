@@ -31,6 +31,7 @@ struct WgHaloParams {
   long long chunks_total, chunks_per_split;
   int Rx, Ry;                  // slab rows of the X / dY boxes
   int x_bytes, y_bytes;        // stage sizes (1024-aligned)
+  int lean;                    // MMA issue loop: 1 = one thread, per-group shifts in registers, descriptors advanced by adds; 0 = first version
 };
 
 struct WgHaloMaps {
@@ -120,7 +121,63 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       __syncwarp();
       if (++stage == 2) { stage = 0; phase ^= 1; }
     }
+  } else if (warp == 1 && p.lean) {
+    // ===== MMA issuer, lean form (see conv_halo.cuh: the first version rebuilt both descriptors with masks and shifts for each of the
+    // 80 MMAs of a chunk and divided by 3 per tap pair -- far more scalar work per MMA than the 45 clk the tensor pipe needs) =====
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint64_t HI_X = ((uint64_t)(((8u * XROW) >> 4) | (1u << 14) | ((XROW == 128 ? 2u : 4u) << 29))) << 32;
+      constexpr uint64_t HI_Y = ((uint64_t)(((8u * YROW) >> 4) | (1u << 14) | ((YROW == 128 ? 2u : 4u) << 29))) << 32;
+      constexpr uint32_t XR16 = XROW / 16, YR16 = YROW / 16;
+      // per group: row shift of the first atom (in descriptor units) and the leading-dimension field (distance to the second atom)
+      int g_off[GROUPS];
+      uint32_t g_lbo[GROUPS];
+#pragma unroll
+      for (int gi = 0; gi < GROUPS; ++gi) {
+        int sa;
+        uint32_t lbo;
+        if (p.k1) { sa = 0; lbo = (uint32_t)XROW; }
+        else if (CK == 64) {
+          const int ta = 2 * gi, tb = 2 * gi + 1;
+          sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
+          const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;
+          lbo = (uint32_t)(sb - sa) * (uint32_t)XROW;
+        } else { sa = (gi - 1) * p.Wp - 1; lbo = (uint32_t)XROW; }
+        g_off[gi] = sa * (int)XR16;
+        g_lbo[gi] = ((lbo >> 4) & 0x3FFFu) << 16;
+      }
+      const uint32_t x_lo0 = (smem_u32(sX) & 0x3FFFFu) >> 4, y_lo0 = ((smem_u32(sY) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);
+      const uint32_t x_stage = (uint32_t)p.x_bytes >> 4, y_stage = (uint32_t)p.y_bytes >> 4;
+      int stage = 0;
+      uint32_t phase = 0, acc = 0;
+      for (long long c = c_begin; c < c_end; ++c) {
+        int n, d, q0; bool live;
+        decode(c, n, d, q0, live);
+        if (!live) continue;
+        const int hx = (q0 + p.Wp - 1) / p.Wp - 2;
+        const int hy = q0 / p.Wp;
+        const uint32_t x_c = x_lo0 + (uint32_t)stage * x_stage + (uint32_t)(q0 - hx * p.Wp) * XR16;
+        const uint64_t yb = HI_Y | (uint64_t)(y_lo0 + (uint32_t)stage * y_stage + (uint32_t)(q0 - hy * p.Wp) * YR16);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) {
+          if (gi == 0 || !p.k1) {
+            const uint64_t xb = HI_X | (uint64_t)((x_c + (uint32_t)g_off[gi]) | g_lbo[gi]);
+#pragma unroll
+            for (int k = 0; k < WH_CH / 16; ++k)
+              umma_f16(tmem_base + (uint32_t)(gi * CN), xb + (uint64_t)(k * 16 * XR16), yb + (uint64_t)(k * 16 * YR16), idesc, k == 0 ? acc : 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        acc = 1;
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&accum_bar);
+    }
+    __syncwarp();
   } else if (warp == 1) {
+    // ===== MMA issuer (first version, RHO_WGRAD_HALO_LEAN=0) =====
     // D fp32, A / B bf16, both MN-major, M = 128, N = CN
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int stage = 0;
@@ -279,7 +336,10 @@ static int wg_halo_encode(CUtensorMap* m, const void* base, int C, const WgHaloP
 }
 
 static int conv_wgrad_halo_run(const WgHaloPlan& pl, const ConvGeom& g, const rho_conv_bwd_params* bp, float* partial, cudaStream_t st) {
-  const WgHaloParams& p = pl.p;
+  WgHaloParams p = pl.p;
+  static int lean = -1;
+  if (lean < 0) { const char* e = getenv("RHO_WGRAD_HALO_LEAN"); lean = (e && e[0] == '0') ? 0 : 1; }
+  p.lean = lean;
   WgHaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = wg_halo_encode(&maps.x[0], bp->fwd.x, g.C1, p, p.Rx, p.ck);
