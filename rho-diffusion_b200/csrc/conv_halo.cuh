@@ -15,7 +15,8 @@
 // The kernel is persistent (one CTA per SM, static round-robin over work items) with double-buffered TMEM accumulators,
 // so the epilogue of item i overlaps the MMAs of item i + 1.  Rows with q % Wp == 0 are the padding column: computed and
 // dropped (1 / Wp waste).
-// Warps: 0 = TMA producer of the activation slabs, 10 = TMA producer of the weight tiles, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per scheduler, alternating tiles of an
+// Warps: 0 = TMA producer of the activation slabs, 10 = TMA producer of the weight tiles, 1 = TMEM allocator + MMA issuer, 11 = second MMA issuer,
+// 2..9 = epilogue (two warps per scheduler, alternating tiles of an
 // item; a single epilogue warp per scheduler ran at 0.36 IPC and bounded the 32-channel layers).
 // 1x1 convs (k1) run through the same pipeline as a streaming GEMM: one tap, shift 0, slabs without halo rows.  In the
 // per-tap kernel their short K loops leave every tile latency-bound (3.0 TB/s); here they reach 4.9 - 5.2 TB/s.
@@ -37,7 +38,7 @@ struct HaloParams {
   int a_stage_bytes;          // R * Wp * 128 rounded up to 1024
   int SA, SB;                 // ring depths
   int out_split;              // > 0: channels >= out_split go to y2 (dgrad of a concat input)
-  int lean;                   // MMA issue loop: 1 = one thread, descriptor low words advanced by adds (default); 0 = first version
+  int issuers;                // MMA issuer threads: 2 (warps 1 and 11 take the even / odd tiles of an item; MT >= 2) or 1 (RHO_HALO_ISSUERS)
   float* stat_part;           // optional fused GroupNorm statistics: one row of channel sums per work item (see rho_b200.h)
 };
 
@@ -47,7 +48,7 @@ struct HaloMaps {
 };
 
 template <int BLOCK_N, int MT, int BLOCK_K>
-__global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
+__global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams p,
                                                            const float* __restrict__ bias, const bf16* __restrict__ residual,
                                                            bf16* __restrict__ y, bf16* __restrict__ y2) {
   constexpr int ROW_BYTES = BLOCK_K * 2;          // one position's channels of a K block: 128 B (64 ch) or 64 B (32 ch)
@@ -68,8 +69,9 @@ __global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant
   const int KB = p.Cin / BLOCK_K;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    const uint32_t ni = (uint32_t)p.issuers;      // every issuer commits on the barriers that release operands / publish accumulators
+    for (int s = 0; s < HALO_MAX_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], ni); mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], ni); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], ni); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -140,14 +142,19 @@ __global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 1 && p.lean) {
-    // ===== MMA issuer, lean form =====
-    // ncu's warp-state samples of the first version put this warp in scalar code ~70 % of the time and almost never on a full MMA
-    // queue: ~100 SASS instructions per tap (descriptor assembly, tap -> shift division, elect / reconverge) made an MMA cost
-    // 85 - 98 clk to ISSUE while the tensor pipe needs 45 (N = 64) / 64 (N = 128) clk to execute it.  Here ONE thread runs the whole
-    // loop; the nine tap shifts are registers, a descriptor is {low word, constant high word} and its low word (the shared-memory
-    // address in 16-byte units, < 2^14 for any address below 256 KB) advances by adds.
+  } else if (warp == 1 || (warp == 11 && p.issuers == 2)) {
+    // ===== MMA issuer(s) =====
+    // Two issuers (warps 1 and 11, on different schedulers) split the tiles of a work item: even tiles / odd tiles.  tcgen05.mma
+    // may be issued by any thread; the two streams target different accumulators, each thread's tcgen05.commit covers its own
+    // MMAs, and every operand / accumulator barrier counts both commits.  One thread could not issue N = 64 MMAs as fast as the
+    // tensor pipe executes them even in the lean form below (~70 clk per MMA against 45).
+    // Lean issue loop: ncu's warp-state samples of the first version (one warp, descriptors assembled with masks and shifts per MMA, a
+    // division per tap, elect / reconverge per tap) put the issuer in scalar code ~70 % of the time and almost never on a full MMA
+    // queue -- an MMA cost 85 - 98 clk to ISSUE while the tensor pipe needs 45 (N = 64) / 64 (N = 128) clk to execute it.  Here one
+    // thread per issuer runs the whole loop, the nine tap shifts are registers, and a descriptor is a per-tap base plus an immediate
+    // (its low word is the shared-memory address in 16-byte units, < 2^14 for any address below 256 KB).
     if (elect_one()) {
+      const int first_tile = warp == 1 ? 0 : 1, tile_step = p.issuers;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t RB16 = ROW_BYTES / 16;                     // descriptor address units per operand row
       constexpr uint32_t DESC_HI = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((ROW_BYTES == 128 ? 2u : (ROW_BYTES == 64 ? 4u : 6u)) << 29);
@@ -172,13 +179,27 @@ __global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant
           tc_fence_after();
           const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo0 + (uint32_t)sb * (uint32_t)(B_BYTES >> 4));
           const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)a_t;
+          if (tile_step == 1) {
 #pragma unroll
-          for (int i = 0; i < MT; ++i) {
-            if (i < mt_here) {
+            for (int i = 0; i < MT; ++i) {
+              if (i < mt_here) {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k)
-                umma_f16(tacc + (uint32_t)(i * BLOCK_N), ad + (uint64_t)((uint32_t)(i * 128) * RB16 + (uint32_t)(2 * k)), bd + (uint64_t)(2 * k), idesc,
-                         k == 0 ? acc : 1u);
+                for (int k = 0; k < BLOCK_K / 16; ++k)
+                  umma_f16(tacc + (uint32_t)(i * BLOCK_N), ad + (uint64_t)((uint32_t)(i * 128) * RB16 + (uint32_t)(2 * k)), bd + (uint64_t)(2 * k), idesc,
+                           k == 0 ? acc : 1u);
+              }
+            }
+          } else {
+            const uint64_t ad1 = ad + (uint64_t)((uint32_t)(first_tile * 128) * RB16);
+            const uint32_t tacc1 = tacc + (uint32_t)(first_tile * BLOCK_N);
+#pragma unroll
+            for (int h = 0; h < (MT + 1) / 2; ++h) {                // this issuer's tiles: first_tile + 2 h
+              if (first_tile + 2 * h < mt_here) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)
+                  umma_f16(tacc1 + (uint32_t)(2 * h * BLOCK_N), ad1 + (uint64_t)((uint32_t)(2 * h * 128) * RB16 + (uint32_t)(2 * k)), bd + (uint64_t)(2 * k),
+                           idesc, k == 0 ? acc : 1u);
+              }
             }
           }
           umma_commit(&b_empty[sb]);
@@ -204,55 +225,7 @@ __global__ void __launch_bounds__(352, 1) conv_halo_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer (first version, RHO_HALO_LEAN=0) =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int ntap = p.k1 ? 1 : 9;
-    int sa = 0, sb = 0, ab = 0;
-    uint32_t pha = 0, phb = 0, phacc = 0;
-    for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      int nb, q0, mt_here, d, n, h_lo;
-      decode(item, nb, q0, mt_here, d, n, h_lo);
-      mbar_wait(&acc_empty[ab], phacc ^ 1);       // the epilogue has drained this accumulator set
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(ab * MT * BLOCK_N);
-      const int row_base = q0 - h_lo * p.Wp;
-      bool first = true;
-      for (int kb = 0; kb < KB; ++kb) {
-        for (int dd = 0; dd < p.kd; ++dd) {
-          mbar_wait(&a_full[sa], pha);
-          const uint32_t a_addr = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
-          for (int t9 = 0; t9 < ntap; ++t9) {
-            const int shift = p.k1 ? 0 : (t9 / 3 - 1) * p.Wp + (t9 % 3 - 1);
-            mbar_wait(&b_full[sb], phb);
-            tc_fence_after();
-            const uint64_t bdesc = umma_desc<ROW_BYTES>(smem_u32(sB + sb * B_BYTES));
-            if (elect_one()) {
-#pragma unroll
-              for (int i = 0; i < MT; ++i) {
-                if (i < mt_here) {
-                  const uint64_t adesc = umma_desc<ROW_BYTES>(a_addr + (uint32_t)(row_base + i * 128 + shift) * (uint32_t)ROW_BYTES);
-#pragma unroll
-                  for (int k = 0; k < BLOCK_K / 16; ++k)
-                    umma_f16(tacc + (uint32_t)(i * BLOCK_N), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, !(first && k == 0));
-                }
-              }
-              umma_commit(&b_empty[sb]);
-            }
-            __syncwarp();
-            first = false;
-            if (++sb == p.SB) { sb = 0; phb ^= 1; }
-          }
-          if (elect_one()) umma_commit(&a_empty[sa]);
-          __syncwarp();
-          if (++sa == p.SA) { sa = 0; pha ^= 1; }
-        }
-      }
-      if (elect_one()) umma_commit(&acc_full[ab]);
-      __syncwarp();
-      if (++ab == 2) { ab = 0; phacc ^= 1; }
-    }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 * (w % 4) .. + 31, warps 2..5 take the even tiles of an item and
     // warps 6..9 the odd ones (two warps per scheduler: one hides the other's tcgen05.ld / store latency).  The fused
     // GroupNorm statistics are accumulated per lane (= per row) over the warp's tiles and transposed across the warp once
@@ -457,7 +430,7 @@ static int launch_halo(const HaloMaps& maps, const HaloPlan& pl, const float* bi
     attr_bytes = pl.smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(pl.p.total_items, (long long)sm_count());
-  kern<<<grid, 352, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
+  kern<<<grid, 384, pl.smem, st>>>(maps, pl.p, bias, residual, y, y2);
   RHO_CHECK_LAUNCH("conv_halo_tcgen05");
   return RHO_OK;
 }
@@ -469,9 +442,9 @@ static int conv_halo_run(const HaloPlan& pl_in, const void* x, const void* x2, c
   HaloParams& p = pl.p;
   p.out_split = out_split;
   p.stat_part = stat_part;
-  static int lean = -1;
-  if (lean < 0) { const char* e = getenv("RHO_HALO_LEAN"); lean = (e && e[0] == '0') ? 0 : 1; }
-  p.lean = lean;
+  static int issuers = -1;
+  if (issuers < 0) { const char* e = getenv("RHO_HALO_ISSUERS"); issuers = (e && e[0] == '1') ? 1 : 2; }
+  p.issuers = pl.mt >= 2 ? issuers : 1;
   HaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int box[5] = {pl.bk, p.Wp, p.R, 1, 1};
