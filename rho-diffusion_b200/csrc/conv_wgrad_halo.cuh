@@ -31,7 +31,7 @@ struct WgHaloParams {
   long long chunks_total, chunks_per_split;
   int Rx, Ry;                  // slab rows of the X / dY boxes
   int x_bytes, y_bytes;        // stage sizes (1024-aligned)
-  int lean;                    // MMA issue loop: 1 = one thread, per-group shifts in registers, descriptors advanced by adds; 0 = first version
+  int issuers;                 // MMA issuer threads: 2 (warps 1 and 6 take the even / odd accumulator groups) or 1 (RHO_WGRAD_HALO_ISSUERS)
 };
 
 struct WgHaloMaps {
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint64_t wgh_desc_mn(uint32_t saddr, uint32_t lbo_byt
 // CK input channels per unit: 64 -> an M = 128 MMA pairs two taps (WH_PAIRS groups); 32 -> it takes the three dw taps of one
 // dh (atoms one row apart) plus an unused fourth (3 groups).  CN output channels per unit (N of the MMA).
 template <int CK, int CN>
-__global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const __grid_constant__ WgHaloParams p,
+__global__ void __launch_bounds__(224, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgHaloMaps maps, const __grid_constant__ WgHaloParams p,
                                                                  float* __restrict__ partial) {
   constexpr int XROW = CK * 2, YROW = CN * 2;
   constexpr int GROUPS = CK == 64 ? WH_PAIRS : 3;
@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
   const int xcc = src ? xc - p.C1 : xc;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)p.issuers); }
+    mbar_init(&accum_bar, (uint32_t)p.issuers);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -121,10 +121,12 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       __syncwarp();
       if (++stage == 2) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && p.lean) {
-    // ===== MMA issuer, lean form (see conv_halo.cuh: the first version rebuilt both descriptors with masks and shifts for each of the
-    // 80 MMAs of a chunk and divided by 3 per tap pair -- far more scalar work per MMA than the 45 clk the tensor pipe needs) =====
+  } else if (warp == 1 || (warp == 6 && p.issuers == 2)) {
+    // ===== MMA issuer(s), lean form (see conv_halo.cuh: the first version rebuilt both descriptors with masks and shifts for each of
+    // the 80 MMAs of a chunk and divided by 3 per tap pair -- far more scalar work per MMA than the 45 clk the tensor pipe needs).
+    // Two issuers (warps 1 and 6) take the even / odd accumulator groups; both commit on the stage and accumulator barriers. =====
     if (elect_one()) {
+      const int g_first = warp == 1 ? 0 : 1, g_step = p.issuers;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint64_t HI_X = ((uint64_t)(((8u * XROW) >> 4) | (1u << 14) | ((XROW == 128 ? 2u : 4u) << 29))) << 32;
       constexpr uint64_t HI_Y = ((uint64_t)(((8u * YROW) >> 4) | (1u << 14) | ((YROW == 128 ? 2u : 4u) << 29))) << 32;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
         tc_fence_after();
 #pragma unroll
         for (int gi = 0; gi < GROUPS; ++gi) {
-          if (gi == 0 || !p.k1) {
+          if ((gi == 0 || !p.k1) && (g_step == 1 || (gi & 1) == g_first)) {
             const uint64_t xb = HI_X | (uint64_t)((x_c + (uint32_t)g_off[gi]) | g_lbo[gi]);
 #pragma unroll
             for (int k = 0; k < WH_CH / 16; ++k)
@@ -176,57 +178,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_halo_kernel(const __grid_co
       umma_commit(&accum_bar);
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer (first version, RHO_WGRAD_HALO_LEAN=0) =====
-    // D fp32, A / B bf16, both MN-major, M = 128, N = CN
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int stage = 0;
-    uint32_t phase = 0;
-    bool first = true;
-    for (long long c = c_begin; c < c_end; ++c) {
-      int n, d, q0; bool live;
-      decode(c, n, d, q0, live);
-      if (!live) continue;
-      const int hx = (q0 + p.Wp - 1) / p.Wp - 2;
-      const int hy = q0 / p.Wp;
-      const int xrow = q0 - hx * p.Wp, yrow = q0 - hy * p.Wp;
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      const uint32_t xa = smem_u32(sX + (size_t)stage * p.x_bytes), ya = smem_u32(sY + (size_t)stage * p.y_bytes);
-      if (elect_one()) {
-        const int ngroups = p.k1 ? 1 : GROUPS;
-#pragma unroll 1
-        for (int gi = 0; gi < ngroups; ++gi) {
-          int sa;
-          uint32_t lbo;
-          if (p.k1) {
-            sa = 0;
-            lbo = (uint32_t)XROW;
-          } else if (CK == 64) {
-            const int ta = 2 * gi, tb = 2 * gi + 1;
-            sa = (ta / 3 - 1) * p.Wp + (ta % 3 - 1);
-            const int sb = tb < 9 ? (tb / 3 - 1) * p.Wp + (tb % 3 - 1) : sa + 1;     // unused half of the last pair: any valid rows
-            lbo = (uint32_t)(sb - sa) * (uint32_t)XROW;
-          } else {
-            sa = (gi - 1) * p.Wp - 1;          // atoms: (dh, dw = -1), (dh, 0), (dh, +1), one unused row further
-            lbo = (uint32_t)XROW;
-          }
-#pragma unroll
-          for (int k = 0; k < WH_CH / 16; ++k) {
-            const uint64_t a = wgh_desc_mn<XROW>(xa + (uint32_t)(xrow + sa + k * 16) * (uint32_t)XROW, lbo);
-            const uint64_t b = wgh_desc_mn<YROW>(ya + (uint32_t)(yrow + k * 16) * (uint32_t)YROW, 1024u);
-            umma_f16(tmem_base + (uint32_t)(gi * CN), a, b, idesc, !(first && k == 0));
-          }
-        }
-        umma_commit(&empty_bar[stage]);
-      }
-      __syncwarp();
-      first = false;
-      if (++stage == 2) { stage = 0; phase ^= 1; }
-    }
-    if (elect_one()) umma_commit(&accum_bar);
-    __syncwarp();
-  } else {
+  } else if (warp >= 2 && warp < 6) {
     // epilogue: accumulator row r = (atom a = r / 64 -> tap 2 * pi + a, ci = r % 64), 64 output channels per pair
     bool any = false;
     for (long long c = c_begin; c < c_end; ++c) {
@@ -337,9 +289,9 @@ static int wg_halo_encode(CUtensorMap* m, const void* base, int C, const WgHaloP
 
 static int conv_wgrad_halo_run(const WgHaloPlan& pl, const ConvGeom& g, const rho_conv_bwd_params* bp, float* partial, cudaStream_t st) {
   WgHaloParams p = pl.p;
-  static int lean = -1;
-  if (lean < 0) { const char* e = getenv("RHO_WGRAD_HALO_LEAN"); lean = (e && e[0] == '0') ? 0 : 1; }
-  p.lean = lean;
+  static int issuers = -1;
+  if (issuers < 0) { const char* e = getenv("RHO_WGRAD_HALO_ISSUERS"); issuers = (e && e[0] == '1') ? 1 : 2; }
+  p.issuers = p.k1 ? 1 : issuers;
   WgHaloMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = wg_halo_encode(&maps.x[0], bp->fwd.x, g.C1, p, p.Rx, p.ck);
@@ -354,7 +306,7 @@ static int conv_wgrad_halo_run(const WgHaloPlan& pl, const ConvGeom& g, const rh
       if (e != cudaSuccess) return fail(RHO_ERR_CUDA, "conv_wgrad_halo: cudaFuncSetAttribute(%zu): %s", pl.smem, cudaGetErrorString(e)); \
       attr_bytes = pl.smem;                                                                                                   \
     }                                                                                                                         \
-    conv_wgrad_halo_kernel<CK, CN><<<(unsigned)(p.units * p.splits), 192, pl.smem, st>>>(maps, p, partial);                   \
+    conv_wgrad_halo_kernel<CK, CN><<<(unsigned)(p.units * p.splits), 224, pl.smem, st>>>(maps, p, partial);                   \
     RHO_CHECK_LAUNCH("conv_wgrad_halo_tcgen05");                                                                              \
     return RHO_OK;                                                                                                            \
   }
