@@ -27,8 +27,15 @@ inline int make_geom(const rho_conv_params* p, ConvGeom& g) {
   RHO_REQUIRE(ok_s(p->sd) && ok_s(p->sh) && ok_s(p->sw), "conv: strides must be 1 or 2");
   RHO_REQUIRE(ok_s(p->ud) && ok_s(p->uh) && ok_s(p->uw), "conv: upsample factors must be 1 or 2");
   g.N = p->N; g.D = p->D; g.H = p->H; g.W = p->W;
+  // A pointwise conv (every kernel extent 1, no stride, no upsample) sees the positions of a sample as one flat row-major list, so an
+  // extent beyond the tensor-core engines' 32767-coordinate limit folds into the next dimension: the attention projections of the
+  // 128^3 config are Conv1d(k = 1) over T = 128 x 16 x 16 = 32768 tokens (unet_v2.py:296-304) and would otherwise fall to the CUDA cores.
+  if (p->kd * p->kh * p->kw == 1 && p->sd * p->sh * p->sw == 1 && p->ud * p->uh * p->uw == 1) {
+    while (g.W > 32767 && g.W % 2 == 0 && g.H <= 16383) { g.W /= 2; g.H *= 2; }
+    while (g.H > 32767 && g.H % 2 == 0 && g.D <= 16383) { g.H /= 2; g.D *= 2; }
+  }
   g.ud = p->ud; g.uh = p->uh; g.uw = p->uw;
-  g.Du = p->D * p->ud; g.Hu = p->H * p->uh; g.Wu = p->W * p->uw;
+  g.Du = g.D * p->ud; g.Hu = g.H * p->uh; g.Wu = g.W * p->uw;
   g.kd = p->kd; g.kh = p->kh; g.kw = p->kw; g.taps = p->kd * p->kh * p->kw;
   g.sd = p->sd; g.sh = p->sh; g.sw = p->sw;
   g.pd = p->kd / 2; g.ph = p->kh / 2; g.pw = p->kw / 2;

@@ -184,6 +184,9 @@ CONV_CASES = [
     (1, 2, 256, 0, 256, (640,), 1, 1, 1, True),
     (3, 1, 128, 128, 256, (2, 16, 24), 1, 1, 1, False),        # concat input, 3-D, two output blocks
     (1, 1, 512, 0, 1536, (333,), 1, 1, 1, False),              # T = 333 = 3 x 111 rows, 12 output blocks, 8 K blocks
+    # T = 32768 tokens (the 128^3 config's attention at 128 x 16 x 16): beyond the tensor maps' 32767-coordinate limit, folded to
+    # (2, 16384) by make_geom -- must stay on the tcgen05 engine (forward, dgrad, wgrad)
+    (1, 1, 64, 0, 128, (32768,), 1, 1, 1, True),
 ]
 
 
@@ -230,7 +233,7 @@ def test_conv_fwd_bwd(ops, dtype, case):
         assert rel_err(nc(resd.grad), dy) < 1e-6
 
 
-@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20, 30, 31, 32, 33, 34, 35, 45, 46, 47, 48, 49)])
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14, 15, 16, 17, 18, 19, 20, 30, 31, 32, 33, 34, 35, 45, 46, 47, 48, 49, len(CONV_CASES) - 1)])
 def test_conv_tcgen05_engine_is_used_and_matches_simt(ops, case):
     """The bf16 shapes above must run on the tcgen05 engine (forced: an unsupported shape would raise), and agree with
     the CUDA-core engine on the same inputs to fp32-accumulation rounding."""

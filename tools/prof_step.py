@@ -9,8 +9,9 @@ from rho_diffusion.b200 import optimize
 mode = sys.argv[1] if len(sys.argv) > 1 else "train"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda", 0)
-ddpm, _ = bench.build_model(bench.CONFIGS['D'], dev, torch.bfloat16)
-x, y = bench.make_inputs(bench.CONFIGS['D'], B, 0)
+CFG = bench.CONFIGS[os.environ.get('RHO_PROF_CONFIG', 'D')]
+ddpm, _ = bench.build_model(CFG, dev, torch.bfloat16)
+x, y = bench.make_inputs(CFG, B, 0)
 x, y = x.to(dev), y.to(dev)
 if mode == "train":
     opt = ddpm.configure_optimizers(1)["optimizer"]
