@@ -396,11 +396,16 @@ static int encode_weight_maps(TcMaps& maps, const void* w, long long Ktot, int r
   return rc;
 }
 
-template <int BLOCK_N, int BLOCK_K, typename TOut, int CL = 1>
-static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2, cudaStream_t st) {
+// RHO_CONV_DEEP_RING=0: launches with no more CTAs than SMs keep the two-CTAs-per-SM ring depth (default: they take the deep ring)
+static int deep_ring_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RHO_CONV_DEEP_RING"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, typename TOut, int CL>
+static int launch_tc_st(const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2, cudaStream_t st) {
   constexpr int STAGE_BYTES = (TC_BM + BLOCK_N) * BLOCK_K * 2;
-  // ring depth: fill ~96 KB so that two CTAs fit in one SM's 227 KB
-  constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2 : ((96 * 1024 / STAGE_BYTES) > 8 ? 8 : (96 * 1024 / STAGE_BYTES));
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
   auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES, TOut, CL>;
   static bool attr_done = false;
@@ -427,6 +432,21 @@ static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, c
   kern<<<(unsigned)tiles, 192, SMEM, st>>>(maps, p, bias, residual, y, y2);
   RHO_CHECK_LAUNCH("conv_fwd_tcgen05");
   return RHO_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K, typename TOut, int CL = 1>
+static int launch_tc(const TcMaps& maps, const TcParams& p, const float* bias, const bf16* residual, TOut* y, TOut* y2, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (TC_BM + BLOCK_N) * BLOCK_K * 2;
+  // ring depth: fill ~96 KB so that two CTAs fit in one SM's 227 KB
+  constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2 : ((96 * 1024 / STAGE_BYTES) > 8 ? 8 : (96 * 1024 / STAGE_BYTES));
+  // A launch with no more CTAs than SMs (the deep UNet levels at batch 1-2) has one CTA per SM whatever its footprint, and the loads
+  // of a lone CTA are latency-bound (stages in flight x stage bytes / TMA round trip): such a launch takes ~200 KB for its ring.
+  constexpr int DEEP = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  if constexpr (CL == 1 && DEEP > STAGES) {
+    const long long ctas = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n * p.n_blocks;
+    if (ctas <= sm_count() && deep_ring_enabled()) return launch_tc_st<BLOCK_N, BLOCK_K, DEEP, TOut, 1>(maps, p, bias, residual, y, y2, st);
+  }
+  return launch_tc_st<BLOCK_N, BLOCK_K, STAGES, TOut, CL>(maps, p, bias, residual, y, y2, st);
 }
 
 // view of the output positions this launch writes: grid coordinate j <-> output index j * os + oo in every dim

@@ -1077,8 +1077,11 @@ int rho_gn_stats_from_partials(const rho_gn_params* p, const float* part1, int32
   RHO_REQUIRE(p->N <= 65535, "gn_stats_from_partials: N too large");
   const int cpg = (p->C1 + p->C2) / p->groups;
   const long long work = (long long)std::max(rows1, rows2) * cpg;        // (row, channel) pairs per (sample, group)
-  if (work <= 1024) {
-    const int NG = p->N * p->groups;
+  // one warp per (sample, group) walks its pairs serially at one L2 round trip (~0.4 us) each -- ptxas pairs every load with its use,
+  // also in an unrolled loop -- so it only takes the tiny cases (<= 4 trips per lane); the CTA kernel spreads the rest over 256 threads
+  // (measured: 28 launches of the 1024-pair case cost 12.9 us each on one warp per group)
+  const int NG = p->N * p->groups;
+  if (work <= 128 || (work <= 1024 && NG > 16 * sm_count())) {      // (many-sample batches: enough warps to hide the trips)
     gn_stats_from_partials_warp_kernel<<<(NG * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(part1, rows1, p->C1, part2, rows2, p->C2, p->S,
                                                                                            p->groups, NG, p->eps, p->stats);
   } else {
