@@ -39,6 +39,71 @@ def ddp_setup(port: int = 29600, backend: str | None = None):
     return world, rank, local_rank
 
 
+def _make_grid(images: torch.Tensor, nrow: int, padding: int = 2, pad_value: float = 1.0) -> torch.Tensor:
+    """``torchvision.utils.make_grid(images, nrow, padding, pad_value, normalize=True)`` restated for hosts without torchvision:
+    the batch is scaled to [0, 1] by its global min / max, single-channel images are repeated to three channels, and the tiles are
+    laid out row-major with ``padding`` pixels of ``pad_value`` around each."""
+    images = images.detach().float().cpu()
+    if images.shape[1] == 1:
+        images = images.repeat(1, 3, 1, 1)
+    lo, hi = float(images.min()), float(images.max())
+    images = (images.clamp(lo, hi) - lo) / max(hi - lo, 1e-5)
+    n, c, h, w = images.shape
+    xmaps = min(nrow, n)
+    ymaps = -(-n // xmaps)
+    H, W = h + padding, w + padding
+    grid = torch.full((c, H * ymaps + padding, W * xmaps + padding), float(pad_value))
+    for k in range(n):
+        y, x = divmod(k, xmaps)
+        grid[:, y * H + padding: y * H + padding + h, x * W + padding: x * W + padding + w] = images[k]
+    return grid
+
+
+def _write_png(grid: torch.Tensor, filename) -> None:
+    """8-bit RGB PNG of a [3, H, W] tensor in [0, 1] with the rounding of ``torchvision.utils.save_image`` (x * 255 + 0.5, clamped);
+    zlib / struct only."""
+    import struct
+    import zlib
+    arr = grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8).contiguous().numpy()
+    h, w, _ = arr.shape
+    raw = b"".join(b"\x00" + arr[y].tobytes() for y in range(h))
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(filename, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def plot_image_grid(img_grid: torch.Tensor, transpose: bool = False, filename=None):
+    """utils.py:84-117: a [rows, cols, C, H, W] tensor of images, clamped to [-1, 1], as one normalised grid (2 px white padding)
+    with ``cols`` tiles per line (``rows`` when ``transpose``); written to ``filename`` as a PNG or returned.  A [N, C, H, W]
+    batch (what ``generate()`` returns here) is one row.  torchvision renders it when importable; otherwise the restatement above."""
+    td = img_grid.detach().float().cpu().clamp(-1, 1)
+    if td.ndim == 4:
+        td = td.unsqueeze(0)
+    if td.ndim != 5:
+        raise ValueError("plot_image_grid expects [rows, cols, C, H, W] (or [N, C, H, W]) images, got %s" % (tuple(img_grid.shape),))
+    nrow = td.shape[0] if transpose else td.shape[1]
+    if transpose:
+        td = td.swapaxes(0, 1)
+    td = td.reshape(td.shape[0] * td.shape[1], *td.shape[2:])
+    try:
+        from torchvision.utils import make_grid, save_image
+        rendered = make_grid(td, nrow=nrow, padding=2, pad_value=1, normalize=True).cpu()
+        if filename is not None:
+            save_image(rendered, fp=filename)
+            return None
+        return rendered
+    except ImportError:
+        rendered = _make_grid(td, nrow=nrow, padding=2, pad_value=1.0)
+        if filename is not None:
+            _write_png(rendered, filename)
+            return None
+        return rendered
+
+
 def save_model_checkpoint(model, filename):
     """Backbone ``state_dict`` with the reference key names / fp32 PyTorch layouts (utils.py:166-167)."""
     torch.save({k: v.detach().float().cpu() for k, v in model.state_dict().items()}, filename)

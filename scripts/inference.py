@@ -3,7 +3,8 @@
 ``GaussianDiffusionPipeline`` exactly as the reference does (lines 122-143), loads ``model.pth`` strictly, and calls
 ``generate(parameter_space=config.inference.parameter_space)`` (DDIM eta = 0 with dynamic thresholding, one CUDA graph
 per step).  The result is written with ``torch.save`` (``--out``) and, when h5py is importable, to
-``config.inference.cache_file`` under the key ``data`` like the reference.
+``config.inference.cache_file`` under the key ``data`` like the reference; 2-D results are also rendered to
+``config.inference.plot_output_file`` (``rho_diffusion.utils.plot_image_grid``).
 
     python scripts/inference.py examples/config_spherical_harmonics.json -p model.pth -d cuda -n 10
 """
@@ -52,6 +53,7 @@ def main():
     parser.add_argument("--out", default="inference_output.pt")
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--steps", type=int, default=0, help="override the number of diffusion steps (0 = config)")
+    parser.add_argument("--plot", default=None, help="PNG grid of a 2-D result (default: config.inference.plot_output_file)")
     args = parser.parse_args()
 
     from rho_diffusion import b200 as accel
@@ -80,6 +82,12 @@ def main():
         pred = model.reverse_process(torch.zeros(shape, device=device), conditions=cond)["denoised"]
     torch.save(pred.cpu(), args.out)
     print("generated", tuple(pred.shape), "mean %.4f std %.4f ->" % (float(pred.mean()), float(pred.std())), args.out)
+    plot_file = args.plot or config.inference.plot_output_file
+    if plot_file is not None and pred.ndim == 4:
+        # scripts/inference.py:172-176 of the reference (2-D fields; volumes and profiles have no grid rendering there either)
+        from rho_diffusion.utils import plot_image_grid
+        plot_image_grid(pred, transpose=False, filename=plot_file)
+        print("grid ->", plot_file)
     cache = config.inference.cache_file
     if cache:
         try:

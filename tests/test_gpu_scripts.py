@@ -52,9 +52,11 @@ def test_inference_script_on_the_deep_galaxy_config(tmp_path):
     torch.save(synth_state_dict(g["manifest"], seed=777), ckpt)
     gen = str(tmp_path / "gen.pt")
     cfg = os.path.join(ROOT, "examples", "config_deep_galaxy.json")
-    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "4", "--steps", "4", "--out", gen])
+    png = tmp_path / "grid.png"
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "4", "--steps", "4", "--out", gen, "--plot", str(png)])
     x = torch.load(gen)
     assert x.shape == (4, 1, 128, 128) and torch.isfinite(x).all(), out[-1500:]
+    assert png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"        # the grid of scripts/inference.py:172-176 (utils.plot_image_grid)
     assert float(x.abs().max()) <= 1.0 + 1e-6           # dynamic thresholding keeps samples in [-1, 1]
 
 
@@ -71,7 +73,8 @@ def test_training_script_builds_cond_fn_and_saves_the_ema_checkpoint(tmp_path):
     assert sd.keys() == ema.keys() and "cond_fn.embedding_layers.n.weight" in sd and sd["cond_fn.embedding_layers.w.weight"].shape == (3, 128)
     assert any(not torch.equal(sd[k], ema[k]) for k in sd)          # the shadow lags the weights
     gen = str(tmp_path / "gen.pt")
-    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "5", "--steps", "5", "--out", gen])
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "5", "--steps", "5", "--out", gen, "--plot", str(tmp_path / "blobs.png")])
+    assert (tmp_path / "blobs.png").stat().st_size > 0
     x = torch.load(gen)
     assert x.shape == (5, 1, 64, 64) and torch.isfinite(x).all(), out[-1500:]
     # the same script on the host data path (DataLoader workers, pinned copies)

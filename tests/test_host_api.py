@@ -253,3 +253,33 @@ def test_deep_galaxy_config_builds_the_reference_checkpoint_layout():
     got = {k: tuple(v.shape) for k, v in pipe.backbone.state_dict().items()}
     assert got == g["manifest"]
     assert sum(int(torch.tensor(s).prod()) for s in got.values()) == 15863457
+
+
+def test_plot_image_grid_matches_torchvision_and_writes_a_png(tmp_path):
+    """utils.py:84-117 of the reference: clamp to [-1, 1], flatten [rows, cols, C, H, W], make_grid(nrow = cols, padding 2, white,
+    normalize) -> PNG.  The dependency-free restatement (hosts without torchvision) equals torchvision's grid and file pixel for pixel."""
+    import zlib
+    from rho_diffusion import utils
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.randn(2, 3, 1, 9, 7, generator=g) * 0.8            # [rows, cols, C, H, W], single channel, values beyond [-1, 1]
+    flat = imgs.clamp(-1, 1).reshape(6, 1, 9, 7)
+    mine = utils._make_grid(flat, nrow=3)
+    assert mine.shape == (3, 2 * 11 + 2, 3 * 9 + 2)
+    tv = pytest.importorskip("torchvision.utils")
+    ref = tv.make_grid(flat, nrow=3, padding=2, pad_value=1, normalize=True)
+    assert torch.allclose(mine, ref, atol=1e-6)
+    assert torch.allclose(utils.plot_image_grid(imgs), ref, atol=1e-6)
+    assert torch.allclose(utils.plot_image_grid(imgs, transpose=True),
+                          tv.make_grid(imgs.clamp(-1, 1).swapaxes(0, 1).reshape(6, 1, 9, 7), nrow=2, padding=2, pad_value=1, normalize=True), atol=1e-6)
+    # [N, C, H, W] (what generate() returns) is one row
+    assert utils.plot_image_grid(flat).shape == (3, 11 + 2, 6 * 9 + 2)
+    # files: torchvision's writer and the zlib writer decode to the same pixels
+    f1, f2 = tmp_path / "tv.png", tmp_path / "own.png"
+    assert utils.plot_image_grid(imgs, filename=f1) is None and f1.stat().st_size > 0
+    utils._write_png(mine, f2)
+    from PIL import Image
+    import numpy as np
+    a, b = np.asarray(Image.open(f1).convert("RGB")), np.asarray(Image.open(f2).convert("RGB"))
+    assert a.shape == b.shape == (24, 29, 3) and int(np.abs(a.astype(int) - b.astype(int)).max()) <= 1   # (x*255+.5 on 1e-7-different floats)
+    with pytest.raises(ValueError):
+        utils.plot_image_grid(torch.zeros(2, 3, 4))
