@@ -3,8 +3,9 @@
 ``GaussianDiffusionPipeline`` exactly as the reference does (lines 122-143), loads ``model.pth`` strictly, and calls
 ``generate(parameter_space=config.inference.parameter_space)`` (DDIM eta = 0 with dynamic thresholding, one CUDA graph
 per step).  The result is written with ``torch.save`` (``--out``) and, when h5py is importable, to
-``config.inference.cache_file`` under the key ``data`` like the reference; 2-D results are also rendered to
-``config.inference.plot_output_file`` (``rho_diffusion.utils.plot_image_grid``).
+``config.inference.cache_file`` under the key ``data`` like the reference (``<cache_file>.npz`` without h5py); 2-D results are also
+rendered to ``config.inference.plot_output_file`` (``rho_diffusion.utils.plot_image_grid``).  As in the reference, an existing cache is
+plotted instead of sampling again unless ``-f`` is given.
 
     python scripts/inference.py examples/config_spherical_harmonics.json -p model.pth -d cuda -n 10
 """
@@ -43,6 +44,43 @@ def build_pipeline(config, device, n_samples: int, steps: int = 0):
     return model, cond_kwargs
 
 
+def read_cache(path):
+    """The cached samples of an earlier run (scripts/inference.py:94-107 of the reference: HDF5, key ``data``); ``<path>.npz`` is the
+    h5py-free fallback this script writes when h5py is not importable.  None when there is no cache."""
+    if os.path.isfile(path):
+        try:
+            import h5py
+            with h5py.File(path, "r") as h5f:
+                return torch.tensor(h5f["data"][()])
+        except ImportError:
+            pass
+    if os.path.isfile(str(path) + ".npz"):
+        import numpy as np
+        with np.load(str(path) + ".npz") as z:
+            return torch.from_numpy(z["data"])
+    return None
+
+
+def write_cache(path, pred) -> str:
+    try:
+        import h5py
+        with h5py.File(path, "w") as h5f:
+            h5f["data"] = pred.cpu().numpy()
+        return str(path)
+    except ImportError:
+        import numpy as np
+        np.savez(str(path) + ".npz", data=pred.cpu().numpy())
+        return str(path) + ".npz"
+
+
+def plot(pred, plot_file) -> None:
+    # scripts/inference.py:103-107, 172-176 of the reference (2-D fields; volumes and profiles have no grid rendering there either)
+    if plot_file is not None and pred.ndim in (4, 5) and pred.shape[-3] in (1, 3):
+        from rho_diffusion.utils import plot_image_grid
+        plot_image_grid(pred, transpose=False, filename=plot_file)
+        print("grid ->", plot_file)
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("json_config", type=Path)
@@ -54,11 +92,22 @@ def main():
     parser.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--steps", type=int, default=0, help="override the number of diffusion steps (0 = config)")
     parser.add_argument("--plot", default=None, help="PNG grid of a 2-D result (default: config.inference.plot_output_file)")
+    parser.add_argument("--cache", default=None, help="sample cache file (default: config.inference.cache_file)")
     args = parser.parse_args()
+
+    config = ExperimentConfig.from_json(args.json_config)
+    plot_file = args.plot or config.inference.plot_output_file
+    cache = args.cache or config.inference.cache_file
+    if cache and not args.forced_overwrite:
+        cached = read_cache(cache)
+        if cached is not None:
+            print("Found a cache copy of the generated data: %s. Will plot this file. If you wish to plot newly generated data, "
+                  "please use the `-f` argument to overwrite." % cache)
+            plot(cached, plot_file)
+            return
 
     from rho_diffusion import b200 as accel
 
-    config = ExperimentConfig.from_json(args.json_config)
     torch.manual_seed(config.inference.seed)
     device = torch.device(args.device)
     model, cond_kwargs = build_pipeline(config, device, args.n_samples, args.steps)
@@ -82,21 +131,11 @@ def main():
         pred = model.reverse_process(torch.zeros(shape, device=device), conditions=cond)["denoised"]
     torch.save(pred.cpu(), args.out)
     print("generated", tuple(pred.shape), "mean %.4f std %.4f ->" % (float(pred.mean()), float(pred.std())), args.out)
-    plot_file = args.plot or config.inference.plot_output_file
-    if plot_file is not None and pred.ndim == 4:
-        # scripts/inference.py:172-176 of the reference (2-D fields; volumes and profiles have no grid rendering there either)
-        from rho_diffusion.utils import plot_image_grid
-        plot_image_grid(pred, transpose=False, filename=plot_file)
-        print("grid ->", plot_file)
-    cache = config.inference.cache_file
-    if cache:
-        try:
-            import h5py
-            if args.forced_overwrite or not os.path.isfile(cache):
-                with h5py.File(cache, "w") as h5f:
-                    h5f["data"] = pred.cpu().numpy()
-        except ImportError:
-            pass
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0:     # (sharded runs: rank 0's slice)
+        plot(pred, plot_file)
+        if cache:
+            print("cache ->", write_cache(cache, pred))
 
 
 if __name__ == "__main__":

@@ -36,7 +36,7 @@ def test_training_script_then_inference_script(tmp_path):
     assert "input_blocks.0.0.weight" in sd and sd["input_blocks.0.0.weight"].shape == (64, 1, 3, 3, 3)
     assert all(v.dtype == torch.float32 for v in sd.values())
     gen = str(tmp_path / "gen.pt")
-    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "3", "--steps", "6", "--out", gen])
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "3", "--steps", "6", "--out", gen, "-f", "--cache", str(tmp_path / "c.h5")])
     x = torch.load(gen)
     assert x.shape == (3, 1, 32, 32, 32) and torch.isfinite(x).all(), out[-1500:]
 
@@ -53,7 +53,7 @@ def test_inference_script_on_the_deep_galaxy_config(tmp_path):
     gen = str(tmp_path / "gen.pt")
     cfg = os.path.join(ROOT, "examples", "config_deep_galaxy.json")
     png = tmp_path / "grid.png"
-    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "4", "--steps", "4", "--out", gen, "--plot", str(png)])
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "4", "--steps", "4", "--out", gen, "--plot", str(png), "-f", "--cache", str(tmp_path / "c.h5")])
     x = torch.load(gen)
     assert x.shape == (4, 1, 128, 128) and torch.isfinite(x).all(), out[-1500:]
     assert png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"        # the grid of scripts/inference.py:172-176 (utils.plot_image_grid)
@@ -73,8 +73,14 @@ def test_training_script_builds_cond_fn_and_saves_the_ema_checkpoint(tmp_path):
     assert sd.keys() == ema.keys() and "cond_fn.embedding_layers.n.weight" in sd and sd["cond_fn.embedding_layers.w.weight"].shape == (3, 128)
     assert any(not torch.equal(sd[k], ema[k]) for k in sd)          # the shadow lags the weights
     gen = str(tmp_path / "gen.pt")
-    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "5", "--steps", "5", "--out", gen, "--plot", str(tmp_path / "blobs.png")])
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "-n", "5", "--steps", "5", "--out", gen, "--plot", str(tmp_path / "blobs.png"),
+               "-f", "--cache", str(tmp_path / "c.h5")])
     assert (tmp_path / "blobs.png").stat().st_size > 0
+    # a second call without -f finds the cache (HDF5 `data`, or <file>.npz without h5py), plots it and does not sample again
+    (tmp_path / "blobs.png").unlink()
+    out = run(["scripts/inference.py", cfg, "-p", ckpt, "-d", "cuda", "--out", str(tmp_path / "never.pt"), "--plot", str(tmp_path / "blobs.png"),
+               "--cache", str(tmp_path / "c.h5")])
+    assert "Found a cache copy" in out and (tmp_path / "blobs.png").stat().st_size > 0 and not (tmp_path / "never.pt").exists()
     x = torch.load(gen)
     assert x.shape == (5, 1, 64, 64) and torch.isfinite(x).all(), out[-1500:]
     # the same script on the host data path (DataLoader workers, pinned copies)

@@ -283,3 +283,25 @@ def test_plot_image_grid_matches_torchvision_and_writes_a_png(tmp_path):
     assert a.shape == b.shape == (24, 29, 3) and int(np.abs(a.astype(int) - b.astype(int)).max()) <= 1   # (x*255+.5 on 1e-7-different floats)
     with pytest.raises(ValueError):
         utils.plot_image_grid(torch.zeros(2, 3, 4))
+
+
+def test_inference_script_plots_an_existing_cache_without_sampling(tmp_path):
+    """scripts/inference.py:94-107 of the reference: with a cache file present and no ``-f`` the script only plots it (no model, no
+    device).  Without h5py the cache is ``<cache_file>.npz`` with the same ``data`` key."""
+    import subprocess
+    import sys
+    import numpy as np
+    cache = tmp_path / "cache.h5"
+    data = torch.randn(5, 1, 16, 16, generator=torch.Generator().manual_seed(1)).numpy()
+    try:
+        import h5py
+        with h5py.File(cache, "w") as f:
+            f["data"] = data
+    except ImportError:
+        np.savez(str(cache) + ".npz", data=data)
+    png = tmp_path / "grid.png"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "inference.py"), os.path.join(ROOT, "examples", "config_gaussian_blobs.json"),
+                        "--cache", str(cache), "--plot", str(png), "--out", str(tmp_path / "never.pt")],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert "Found a cache copy" in r.stdout and png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n" and not (tmp_path / "never.pt").exists()
