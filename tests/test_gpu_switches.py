@@ -31,10 +31,10 @@ VARIANTS = [
     {"RHO_ATTN_BWD_V2": "0"},           # first-generation attention backward (32-column tiles, P / dS through shared memory)
     {"RHO_ATTN_BWD_V2_MIN_T": "1"},     # second-generation backward (64-column tiles, P / dS in TMEM) forced for every head-dim-64 shape
     {"RHO_HALO_WIDE_K1": "1"},          # wide 1x1 convs (attention qkv / proj_out) through the halo kernel's streaming mode
-    {"RHO_CONV_CLUSTER": "1"},
+    {"RHO_CONV_CLUSTER": "1"},          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
     {"RHO_CONV_DEEP_RING": "0"},        # small launches (<= 1 CTA per SM: every test shape) on the 96 KB ring of the full-size launches
     {"RHO_HALO_ISSUERS": "1", "RHO_WGRAD_HALO_ISSUERS": "1"},   # one MMA issuer thread in the halo conv / weight-gradient kernels
-    {"RHO_FP32_SPLIT": "1"},            # fp32 inference convs as six bf16 tensor-core products with flushed fp32 accumulation          # CTA pairs sharing the weight tile through TMA multicast (per-tap kernel, BLOCK_N >= 128)
+    {"RHO_FP32_SPLIT": "1"},            # fp32 inference convs as six bf16 tensor-core products with flushed fp32 accumulation
 ]
 
 
